@@ -1,0 +1,849 @@
+// libhmcmt_b200.so — plan, step orchestration and the Level-2 C ABI (include/hmcmt_b200.h).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/hmcmt_b200.h"
+#include "band_factor.cuh"
+#include "band_solve.cuh"
+#include "mt_kernels.cuh"
+
+using namespace hmcmt;
+
+namespace {
+
+template <typename Tp>
+struct DevBuf {
+    Tp* p = nullptr;
+    size_t n = 0;
+    int alloc(size_t count) {
+        n = count;
+        if (count == 0) return kOk;
+        cudaError_t e = cudaMalloc(&p, count * sizeof(Tp));
+        if (e != cudaSuccess) { p = nullptr; return kErrAlloc; }
+        return kOk;
+    }
+    int upload(const Tp* h, size_t count) {
+        int rc = alloc(count);
+        if (rc) return rc;
+        if (count) HMCMT_CUDA_TRY(cudaMemcpy(p, h, count * sizeof(Tp), cudaMemcpyHostToDevice));
+        return kOk;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+}  // namespace
+
+struct hmcmt_plan {
+    // sizes
+    int ny = 0, nz = 0, nFreq = 0, nRx = 0, nData = 0, nAC = 0, nChains = 1, nModes = 0, nComp = 0;
+    int modeList[2] = {0, 1};
+    int nSysPerChain = 0, nSys = 0, nFull = 0;      // nFull = nFreq*nRx*nModes per chain
+    int T = 0, S = 0, b = 0, device = 0;
+    double beta = 1.0, lo = 0.0, hi = 0.0;
+    MeshDev M{};
+    SysMap sm{};
+    RxDev rx{};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t evA = nullptr, evB = nullptr;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> factorEvents;
+    size_t factorEventsUsed = 0;
+    int64_t launches = 0, factorLaunches = 0;
+    bool haveForward = false;
+    // host copies
+    std::vector<double> h_yLen, h_zLen, h_freqs;
+    std::vector<int> h_packed2full;      // [nData] full index (without chain) of each packed datum
+    // device buffers
+    DevBuf<double> yLen, zLen, zNode, freqs, fdy1, fdy2, wL, wR, bg, wmVal, wd, m, p, mref, sigma, meanSig, planes;
+    DevBuf<double> Gpart, phiPart, phi, gdata, gtotal, energies, panels, curM, curP, chainScal, zmom;
+    DevBuf<int> fid, iL, iR, cell2act, act2cell, wmPtr, wmIdx, status, driftFlag, packed2full, Lsteps;
+    DevBuf<cplx> obs, bc, bcs, rhs, x, F, lam, Lam, srows, qrow, scratch, predFull, ainv, z, zadj, vin, predPacked;
+    DevBuf<BandSys> sysDesc;
+    DevBuf<SolveJob> jobs;
+    // pinned staging for the host-buffer entry points
+    double* pin = nullptr;
+    size_t pinBytes = 0;
+};
+
+namespace {
+
+#define LAUNCH_CHECK(pl)                                          \
+    do {                                                          \
+        ++(pl)->launches;                                         \
+        cudaError_t _e = cudaGetLastError();                      \
+        if (_e != cudaSuccess) {                                  \
+            fprintf(stderr, "[hmcmt_b200] launch failed at %s:%d: %s\n", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            return kErrCuda;                                      \
+        }                                                         \
+    } while (0)
+
+template <int T>
+int launch_factor_T(cudaStream_t st, const BandSys* sys, int nsys, int N, int nf, int b) {
+    static bool configured = false;
+    size_t smem = sizeof(FactorSmem<T>);
+    if (!configured) {
+        HMCMT_CUDA_TRY(cudaFuncSetAttribute(band_factor_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    band_factor_kernel<T><<<nsys, FactorCfg<T>::NTHREADS, smem, st>>>(sys, N, nf, b);
+    return kOk;
+}
+template <int T>
+int launch_solve_T(cudaStream_t st, const SolveJob* jobs, int njobs, int N) {
+    static bool configured = false;
+    size_t smem = sizeof(SolveSmem<T>);
+    if (!configured) {
+        HMCMT_CUDA_TRY(cudaFuncSetAttribute(band_solve_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    band_solve_kernel<T><<<njobs, kSolveThreads, smem, st>>>(jobs, N);
+    return kOk;
+}
+
+}  // namespace
+
+namespace hmcmt {
+// shared with mumps_shim.cu
+int round_T(int b) {
+    int T = band_T_for(b);
+    if (T < 2) T = 2;
+    if (T & 1) ++T;
+    return T;
+}
+int launch_factor(cudaStream_t st, int T, const BandSys* sys, int nsys, int N, int nf, int b) {
+    int rc;
+    switch (T) {
+        case 2: rc = launch_factor_T<2>(st, sys, nsys, N, nf, b); break;
+        case 4: rc = launch_factor_T<4>(st, sys, nsys, N, nf, b); break;
+        case 6: rc = launch_factor_T<6>(st, sys, nsys, N, nf, b); break;
+        case 8: rc = launch_factor_T<8>(st, sys, nsys, N, nf, b); break;
+        case 10: rc = launch_factor_T<10>(st, sys, nsys, N, nf, b); break;
+        case 12: rc = launch_factor_T<12>(st, sys, nsys, N, nf, b); break;
+        case 14: rc = launch_factor_T<14>(st, sys, nsys, N, nf, b); break;
+        default: return kErrArg;
+    }
+    if (rc) return rc;
+    if (cudaGetLastError() != cudaSuccess) return kErrCuda;
+    return kOk;
+}
+int launch_solve(cudaStream_t st, int T, const SolveJob* jobs, int njobs, int N) {
+    int rc;
+    switch (T) {
+        case 2: rc = launch_solve_T<2>(st, jobs, njobs, N); break;
+        case 4: rc = launch_solve_T<4>(st, jobs, njobs, N); break;
+        case 6: rc = launch_solve_T<6>(st, jobs, njobs, N); break;
+        case 8: rc = launch_solve_T<8>(st, jobs, njobs, N); break;
+        case 10: rc = launch_solve_T<10>(st, jobs, njobs, N); break;
+        case 12: rc = launch_solve_T<12>(st, jobs, njobs, N); break;
+        case 14: rc = launch_solve_T<14>(st, jobs, njobs, N); break;
+        default: return kErrArg;
+    }
+    if (rc) return rc;
+    if (cudaGetLastError() != cudaSuccess) return kErrCuda;
+    return kOk;
+}
+int max_band_T() { return 14; }
+}  // namespace hmcmt
+
+namespace {
+
+// linearInterp sensUtils.jl:133-161 (0-based)
+void linear_interp(double point, const std::vector<double>& x, int& iL, int& iR, double& wL, double& wR) {
+    int n = (int)x.size(), ind = 0;
+    double best = std::fabs(point - x[0]);
+    for (int i = 1; i < n; ++i) {
+        double d = std::fabs(point - x[i]);
+        if (d < best) { best = d; ind = i; }
+    }
+    if (point - x[ind] > 0) { iL = ind; iR = ind + 1; } else { iL = ind - 1; iR = ind; }
+    iL = std::max(std::min(iL, n - 1), 0);
+    iR = std::max(std::min(iR, n - 1), 0);
+    if (iL == iR) { wL = 0.5; wR = 0.5; return; }
+    double len = x[iR] - x[iL];
+    wL = 1 - (point - x[iL]) / len;
+    wR = 1 - (x[iR] - point) / len;
+}
+
+// ---- kernels local to the HMC driver ----
+__global__ void k_pack_pred(int nData, int nFull, const int* __restrict__ packed2full, const cplx* __restrict__ predFull,
+                            cplx* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x, ch = blockIdx.y;
+    if (i < nData) out[(size_t)ch * nData + i] = predFull[(size_t)ch * nFull + packed2full[i]];
+}
+__global__ void k_kick_masked(int nAC, double dt, int kstep, const int* __restrict__ L, const double* __restrict__ grad,
+                              double* __restrict__ p) {
+    int ch = blockIdx.y, a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= nAC) return;
+    int Lc = L[ch];
+    double sc = (kstep == 0) ? 0.5 : (kstep < Lc) ? 1.0 : (kstep == Lc) ? 0.5 : 0.0;
+    if (sc != 0.0) p[(size_t)ch * nAC + a] -= sc * dt * grad[(size_t)ch * nAC + a];
+}
+__global__ void k_fill(size_t n, double v, double* __restrict__ x) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = v;
+}
+__global__ void k_clip_momentum(int nAC, const double* __restrict__ z, double* __restrict__ p) {
+    int ch = blockIdx.y, a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= nAC) return;
+    double v = z[(size_t)ch * nAC + a];
+    if (fabs(v) > 2.5) v = copysign(2.5, v);                     // getMomentumVector HMCSampler.jl:441-449
+    p[(size_t)ch * nAC + a] = v;
+}
+// Metropolis accept on the device (HMCSampler.jl:149-186).  chainScal[ch] = {startD, startM, startK, startH}
+__global__ void __launch_bounds__(kHmcThreads)
+k_accept(int nAC, int nData, int it, int nsamples, const double* __restrict__ uacc, const double* __restrict__ phi,
+         const double* __restrict__ energies, const double* __restrict__ znew, double* __restrict__ m, double* __restrict__ p,
+         double* __restrict__ curM, double* __restrict__ chainScal, const cplx* __restrict__ predPacked,
+         double* __restrict__ hmcmodel, double* __restrict__ hmstats, int* __restrict__ accept, cplx* __restrict__ hmcdata) {
+    __shared__ double sh[32];
+    __shared__ int accSh;
+    const int ch = blockIdx.x;
+    double* sc = chainScal + ch * 4;
+    if (threadIdx.x == 0) {
+        double finD = phi[ch], finK = energies[ch * 2], finM = energies[ch * 2 + 1];
+        double finH = finD + finK + finM;
+        double hdif = sc[3] - finH;
+        int acc = (hdif > 0.0) || (uacc[(size_t)ch * nsamples + (it - 1)] < exp(hdif));
+        if (acc) { sc[0] = finD; sc[1] = finM; }
+        accSh = acc;
+        accept[(size_t)ch * nsamples + (it - 1)] = acc;
+    }
+    __syncthreads();
+    const int acc = accSh;
+    double* mm = m + (size_t)ch * nAC;
+    double* pp = p + (size_t)ch * nAC;
+    double* cm = curM + (size_t)ch * nAC;
+    const double* zn = znew + (size_t)ch * nAC;
+    double* modelOut = hmcmodel + ((size_t)ch * nsamples + (it - 1)) * nAC;
+    double k = 0.0;
+    for (int a = threadIdx.x; a < nAC; a += blockDim.x) {
+        double v = acc ? mm[a] : cm[a];
+        mm[a] = v; cm[a] = v; modelOut[a] = v;
+        double z = zn[a];
+        if (fabs(z) > 2.5) z = copysign(2.5, z);
+        pp[a] = z;
+        k += z * z;
+    }
+    k = block_reduce(k, false, sh);
+    cplx* dout = hmcdata + ((size_t)ch * (nsamples + 1) + it) * nData;
+    const cplx* dprev = dout - nData;
+    const cplx* dnew = predPacked + (size_t)ch * nData;
+    for (int i = threadIdx.x; i < nData; i += blockDim.x) dout[i] = acc ? dnew[i] : dprev[i];
+    if (threadIdx.x == 0) {
+        sc[2] = 0.5 * k;
+        sc[3] = sc[0] + sc[1] + sc[2];
+        double* st = hmstats + ((size_t)ch * (nsamples + 1) + it) * 4;
+        st[0] = sc[0]; st[1] = sc[1]; st[2] = sc[2]; st[3] = sc[3];
+    }
+}
+
+int ensure_pin(hmcmt_plan* pl, size_t bytes) {
+    if (pl->pinBytes >= bytes) return kOk;
+    if (pl->pin) cudaFreeHost(pl->pin);
+    pl->pin = nullptr;
+    pl->pinBytes = 0;
+    HMCMT_CUDA_TRY(cudaMallocHost(&pl->pin, bytes));
+    pl->pinBytes = bytes;
+    return kOk;
+}
+
+// One evaluation of the hot path for the device-resident model pl->m:
+//   forward (all chains x modes x freqs) [+ adjoint gradient + prior gradient].
+int compute_step(hmcmt_plan* pl, bool wantAdjoint, const cplx* vin) {
+    const MeshDev& M = pl->M;
+    cudaStream_t st = pl->stream;
+    const int nSys = pl->nSys, nCh = pl->nChains;
+    k_model_transform<<<dim3((M.nCell + 255) / 256, nCh), 256, 0, st>>>(M.nCell, pl->nAC, pl->cell2act.p, pl->bg.p, pl->m.p, pl->sigma.p);
+    LAUNCH_CHECK(pl);
+    k_stencil_planes<<<dim3((M.N + 255) / 256, nCh * pl->nModes), 256, 0, st>>>(M, pl->sm, pl->sigma.p, pl->planes.p);
+    LAUNCH_CHECK(pl);
+    k_boundary<<<dim3((M.ny + 1 + 63) / 64, nSys), 64, 0, st>>>(M, pl->sm, pl->freqs.p, pl->sigma.p, pl->bc.p);
+    LAUNCH_CHECK(pl);
+    k_rhs<<<dim3((M.N + 255) / 256, nSys), 256, 0, st>>>(M, pl->sm, pl->sigma.p, pl->bc.p, pl->rhs.p);
+    LAUNCH_CHECK(pl);
+    if (wantAdjoint) {
+        k_row_mean<<<dim3(M.nz, nCh), 128, 0, st>>>(M.ny, M.nz, pl->sigma.p, pl->meanSig.p);
+        LAUNCH_CHECK(pl);
+        k_sens_scalars<<<(nSys * 3 + 63) / 64, 64, 0, st>>>(M, pl->sm, nSys, pl->freqs.p, pl->sigma.p, pl->meanSig.p, pl->scratch.p, pl->bcs.p);
+        LAUNCH_CHECK(pl);
+    }
+    // factorisation + fused forward solve
+    {
+        if (pl->factorEventsUsed == pl->factorEvents.size()) {
+            cudaEvent_t a, b;
+            HMCMT_CUDA_TRY(cudaEventCreate(&a));
+            HMCMT_CUDA_TRY(cudaEventCreate(&b));
+            pl->factorEvents.emplace_back(a, b);
+        }
+        auto& ev = pl->factorEvents[pl->factorEventsUsed++];
+        HMCMT_CUDA_TRY(cudaEventRecord(ev.first, st));
+        int rc = launch_factor(st, pl->T, pl->sysDesc.p, nSys, M.N, M.nf, pl->b);
+        if (rc) return rc;
+        ++pl->launches;
+        ++pl->factorLaunches;
+        HMCMT_CUDA_TRY(cudaEventRecord(ev.second, st));
+    }
+    k_node_field<<<dim3((M.nNode + 255) / 256, nSys), 256, 0, st>>>(M, pl->x.p, pl->bc.p, pl->F.p);
+    LAUNCH_CHECK(pl);
+    size_t rxSmem = (size_t)(6 * (M.ny + 1) + 3 * M.ny) * sizeof(cplx);
+    k_rx_adjoint<<<nSys, kRxThreads, rxSmem, st>>>(M, pl->rx, pl->sm, pl->freqs.p, pl->sigma.p, pl->F.p, pl->obs.p, pl->wd.p, vin,
+                                                   pl->predFull.p, pl->phiPart.p, pl->srows.p, pl->qrow.p, pl->lam.p, wantAdjoint ? 1 : 0);
+    LAUNCH_CHECK(pl);
+    k_reduce_phi<<<nCh, 32, 0, st>>>(pl->nSysPerChain, pl->phiPart.p, pl->phi.p);
+    LAUNCH_CHECK(pl);
+    pl->haveForward = true;
+    if (!wantAdjoint) return kOk;
+    int rc = launch_solve(st, pl->T, pl->jobs.p, nSys, M.N);      // lam <- A^{-1} s[ii]  (in place)
+    if (rc) return rc;
+    ++pl->launches;
+    k_node_field<<<dim3((M.nNode + 255) / 256, nSys), 256, 0, st>>>(M, pl->lam.p, nullptr, pl->Lam.p);
+    LAUNCH_CHECK(pl);
+    size_t cSmem = (size_t)(5 * M.nz + (M.ny - 1) + M.ny) * sizeof(cplx);
+    k_contract<<<nSys, kConThreads, cSmem, st>>>(M, pl->sm, pl->freqs.p, pl->sigma.p, pl->F.p, pl->Lam.p, pl->srows.p, pl->qrow.p,
+                                                 pl->bcs.p, pl->scratch.p, pl->Gpart.p);
+    LAUNCH_CHECK(pl);
+    k_reduce_grad<<<dim3((pl->nAC + 255) / 256, nCh), 256, 0, st>>>(pl->nAC, M.nCell, pl->nSysPerChain, pl->act2cell.p, pl->Gpart.p,
+                                                                   pl->m.p, pl->mref.p, pl->wmPtr.p, pl->wmIdx.p, pl->wmVal.p, pl->beta,
+                                                                   pl->gdata.p, pl->gtotal.p);
+    LAUNCH_CHECK(pl);
+    return kOk;
+}
+
+int check_status(hmcmt_plan* pl) {
+    std::vector<int> h(pl->nSys);
+    HMCMT_CUDA_TRY(cudaMemcpy(h.data(), pl->status.p, sizeof(int) * pl->nSys, cudaMemcpyDeviceToHost));
+    for (int v : h) if (v) return v;
+    return kOk;
+}
+
+int drift(hmcmt_plan* pl, double dt) {
+    k_drift<<<pl->nChains, kHmcThreads, 0, pl->stream>>>(pl->nAC, dt, pl->lo, pl->hi, pl->m.p, pl->p.p, pl->driftFlag.p);
+    LAUNCH_CHECK(pl);
+    return kOk;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* hmcmt_version(void) { return "hmcmt_b200 0.1 (sm_100a; DMMA.8x8x4 tile-window band LDL^T; no CPU fallback)"; }
+
+int hmcmt_plan_create(const hmcmt_problem* pr, hmcmt_plan** out) {
+    if (!pr || !out) return kErrArg;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        fprintf(stderr, "[hmcmt_b200] no CUDA device: this library has no CPU fallback\n");
+        return kErrNoDevice;
+    }
+    if (pr->ny < 3 || pr->nz < 3 || pr->nFreq < 1 || pr->nRx < 1 || pr->nComp < 1 || pr->nComp > 2 || pr->nChains < 1 || pr->nAC < 1)
+        return kErrArg;
+    HMCMT_CUDA_TRY(cudaSetDevice(pr->device));
+    hmcmt_plan* pl = new (std::nothrow) hmcmt_plan();
+    if (!pl) return kErrAlloc;
+    pl->device = pr->device;
+    pl->ny = pr->ny; pl->nz = pr->nz; pl->nFreq = pr->nFreq; pl->nRx = pr->nRx; pl->nData = pr->nData; pl->nAC = pr->nAC;
+    pl->nChains = pr->nChains; pl->nComp = pr->nComp; pl->nModes = pr->nComp;
+    for (int c = 0; c < pr->nComp; ++c) pl->modeList[c] = pr->compMode[c];
+    pl->beta = pr->regParam;
+    pl->lo = std::log(pr->sigBounds[0]);
+    pl->hi = std::log(pr->sigBounds[1]);
+    const int ny = pr->ny, nz = pr->nz;
+    MeshDev& M = pl->M;
+    M.ny = ny; M.nz = nz; M.n1 = ny - 1; M.n2 = nz - 1; M.N = M.n1 * M.n2;
+    M.fastZ = (M.n2 <= M.n1) ? 1 : 0;
+    M.nf = M.fastZ ? M.n2 : M.n1; M.nl = M.fastZ ? M.n1 : M.n2;
+    M.nCell = ny * nz; M.nNode = (ny + 1) * (nz + 1); M.nb = 2 * (ny + nz);
+    pl->b = M.nf;
+    pl->T = round_T(pl->b);
+    pl->S = (M.N + TS - 1) / TS;
+    if (M.nf < 2) { delete pl; return kErrArg; }
+    if (pl->T > max_band_T()) {
+        fprintf(stderr, "[hmcmt_b200] half-bandwidth %d needs a tile window T=%d > %d: not supported by the register-window kernel yet\n",
+                pl->b, pl->T, max_band_T());
+        delete pl;
+        return kErrArg;
+    }
+    pl->nSysPerChain = pl->nModes * pl->nFreq;
+    pl->nSys = pl->nSysPerChain * pl->nChains;
+    pl->nFull = pl->nFreq * pl->nRx * pl->nModes;
+    pl->sm = SysMap{pl->nFreq, pl->nModes, pl->modeList[0], pl->modeList[1]};
+    pl->h_yLen.assign(pr->yLen, pr->yLen + ny);
+    pl->h_zLen.assign(pr->zLen, pr->zLen + nz);
+    pl->h_freqs.assign(pr->freqs, pr->freqs + pr->nFreq);
+    std::vector<double> yNode(ny + 1), zNode0(nz + 1), zNode(nz + 1);
+    yNode[0] = 0; zNode0[0] = 0;
+    for (int j = 0; j < ny; ++j) yNode[j + 1] = yNode[j] + pr->yLen[j];
+    for (int k = 0; k < nz; ++k) zNode0[k + 1] = zNode0[k] + pr->zLen[k];
+    for (auto& v : yNode) v -= pr->origin[0];
+    for (int k = 0; k <= nz; ++k) zNode[k] = zNode0[k] - pr->origin[1];
+    // receiver row (mt2DTE.jl:65-67)
+    int zid = -1;
+    for (int k = 0; k <= nz; ++k) if (std::fabs(zNode[k] - pr->rxLoc[1]) < 0.1) { zid = k; break; }
+    if (zid < 0 || zid >= nz) { delete pl; return kErrArg; }
+    M.zid = zid;
+    std::vector<int> fid(pr->nRx), iL(pr->nRx), iR(pr->nRx);
+    std::vector<double> d1(pr->nRx), d2(pr->nRx), wL(pr->nRx), wR(pr->nRx);
+    for (int r = 0; r < pr->nRx; ++r) {
+        double y = pr->rxLoc[2 * r];
+        int id = -1;
+        for (int j = 0; j <= ny; ++j) if (yNode[j] > y) { id = j; break; }
+        if (id <= 0) { delete pl; return kErrArg; }       // "receiver location seems to be out of range"
+        fid[r] = id; d1[r] = y - yNode[id - 1]; d2[r] = yNode[id] - y;
+        linear_interp(y, yNode, iL[r], iR[r], wL[r], wR[r]);
+    }
+    // data layout: full index ((f*nRx + r)*nModes + mi), rows must be sorted (freq, rx, comp)
+    std::vector<double> wdFull(pl->nFull, 0.0);
+    std::vector<cplx> obsFull(pl->nFull, mk(0.0, 0.0));
+    pl->h_packed2full.resize(pr->nData);
+    long prev = -1;
+    for (int i = 0; i < pr->nData; ++i) {
+        long f = pr->freqID[i] - 1, r = pr->rxID[i] - 1, c = pr->dtID[i] - 1;
+        if (f < 0 || f >= pr->nFreq || r < 0 || r >= pr->nRx || c < 0 || c >= pr->nComp) { delete pl; return kErrArg; }
+        long full = (f * pr->nRx + r) * pl->nModes + c;
+        if (full <= prev) {
+            fprintf(stderr, "[hmcmt_b200] data rows must be sorted by (freq, rx, comp) without duplicates\n");
+            delete pl;
+            return kErrArg;
+        }
+        prev = full;
+        pl->h_packed2full[i] = (int)full;
+        wdFull[full] = 1.0 / std::fabs(pr->dataErr[i]);
+        obsFull[full] = mk(pr->obsData[2 * i], pr->obsData[2 * i + 1]);
+    }
+    std::vector<int> cell2act(M.nCell, -1);
+    for (int a = 0; a < pr->nAC; ++a) {
+        int c = pr->activeIdx[a];
+        if (c < 0 || c >= M.nCell) { delete pl; return kErrArg; }
+        cell2act[c] = a;
+    }
+    int rc = kOk;
+    auto ok = [&](int r) { if (r && !rc) rc = r; };
+    ok(pl->yLen.upload(pr->yLen, ny)); ok(pl->zLen.upload(pr->zLen, nz)); ok(pl->zNode.upload(zNode0.data(), nz + 1));
+    ok(pl->freqs.upload(pr->freqs, pr->nFreq));
+    ok(pl->fid.upload(fid.data(), pr->nRx)); ok(pl->iL.upload(iL.data(), pr->nRx)); ok(pl->iR.upload(iR.data(), pr->nRx));
+    ok(pl->fdy1.upload(d1.data(), pr->nRx)); ok(pl->fdy2.upload(d2.data(), pr->nRx));
+    ok(pl->wL.upload(wL.data(), pr->nRx)); ok(pl->wR.upload(wR.data(), pr->nRx));
+    ok(pl->cell2act.upload(cell2act.data(), M.nCell)); ok(pl->act2cell.upload(pr->activeIdx, pr->nAC));
+    ok(pl->bg.upload(pr->bgModel, M.nCell));
+    ok(pl->wmPtr.upload(pr->wmRowPtr, pr->nAC + 1));
+    int nnzWm = pr->wmRowPtr[pr->nAC];
+    ok(pl->wmIdx.upload(pr->wmColIdx, nnzWm)); ok(pl->wmVal.upload(pr->wmVal, nnzWm));
+    ok(pl->wd.upload(wdFull.data(), pl->nFull)); ok(pl->obs.upload(obsFull.data(), pl->nFull));
+    ok(pl->packed2full.upload(pl->h_packed2full.data(), pr->nData));
+    const size_t nCh = pl->nChains, nSys = pl->nSys, N = M.N;
+    ok(pl->m.alloc(nCh * pr->nAC)); ok(pl->p.alloc(nCh * pr->nAC)); ok(pl->mref.alloc(nCh * pr->nAC));
+    ok(pl->curM.alloc(nCh * pr->nAC)); ok(pl->curP.alloc(nCh * pr->nAC)); ok(pl->zmom.alloc(nCh * pr->nAC));
+    ok(pl->sigma.alloc(nCh * M.nCell)); ok(pl->meanSig.alloc(nCh * nz));
+    ok(pl->planes.alloc(nCh * pl->nModes * 4 * N));
+    ok(pl->bc.alloc(nSys * M.nb)); ok(pl->bcs.alloc(nSys * M.nb));
+    ok(pl->rhs.alloc(nSys * N)); ok(pl->x.alloc(nSys * N)); ok(pl->lam.alloc(nSys * N));
+    ok(pl->F.alloc(nSys * M.nNode)); ok(pl->Lam.alloc(nSys * M.nNode));
+    ok(pl->srows.alloc(nSys * 2 * (ny + 1))); ok(pl->qrow.alloc(nSys * ny));
+    ok(pl->scratch.alloc(nSys * 3 * prof_stride(nz)));
+    ok(pl->Gpart.alloc(nSys * M.nCell)); ok(pl->phiPart.alloc(nSys)); ok(pl->phi.alloc(nCh));
+    ok(pl->gdata.alloc(nCh * pr->nAC)); ok(pl->gtotal.alloc(nCh * pr->nAC)); ok(pl->energies.alloc(nCh * 2));
+    ok(pl->chainScal.alloc(nCh * 4));
+    ok(pl->predFull.alloc(nCh * pl->nFull)); ok(pl->vin.alloc(nCh * pl->nFull)); ok(pl->predPacked.alloc(nCh * pr->nData));
+    ok(pl->panels.alloc(nSys * (size_t)pl->S * panel_doubles(pl->T)));
+    ok(pl->ainv.alloc(nSys * (size_t)pl->S * 64)); ok(pl->z.alloc(nSys * (size_t)pl->S * 8)); ok(pl->zadj.alloc(nSys * (size_t)pl->S * 8));
+    ok(pl->status.alloc(nSys)); ok(pl->driftFlag.alloc(1)); ok(pl->Lsteps.alloc(nCh));
+    ok(pl->sysDesc.alloc(nSys)); ok(pl->jobs.alloc(nSys));
+    if (rc) { hmcmt_destroy(pl); return rc; }
+    cudaMemset(pl->status.p, 0, sizeof(int) * nSys);
+    cudaMemset(pl->driftFlag.p, 0, sizeof(int));
+    cudaMemset(pl->m.p, 0, sizeof(double) * nCh * pr->nAC);
+    cudaMemset(pl->p.p, 0, sizeof(double) * nCh * pr->nAC);
+    cudaMemset(pl->mref.p, 0, sizeof(double) * nCh * pr->nAC);
+    M.yLen = pl->yLen.p; M.zLen = pl->zLen.p; M.zNode = pl->zNode.p;
+    pl->rx = RxDev{pr->nRx, pl->fid.p, pl->fdy1.p, pl->fdy2.p, pl->iL.p, pl->iR.p, pl->wL.p, pl->wR.p};
+    // per-system descriptors
+    std::vector<BandSys> sd(nSys);
+    std::vector<SolveJob> jb(nSys);
+    for (size_t s = 0; s < nSys; ++s) {
+        int f = (int)(s % pl->nFreq);
+        int t = (int)(s / pl->nFreq);
+        int mi = t % pl->nModes, ch = t / pl->nModes;
+        double* P = pl->planes.p + ((size_t)(ch * pl->nModes + mi) * 4) * N;
+        BandSys& d = sd[s];
+        d.dr = P; d.dm = P + N; d.e1 = P + 2 * N; d.e2 = P + 3 * N;
+        d.omega = 2.0 * kPi * pr->freqs[f];
+        d.band = nullptr;
+        d.rhs = pl->rhs.p + s * N;
+        d.panels = pl->panels.p + s * (size_t)pl->S * panel_doubles(pl->T);
+        d.ainv = pl->ainv.p + s * (size_t)pl->S * 64;
+        d.z = pl->z.p + s * (size_t)pl->S * 8;
+        d.x = pl->x.p + s * N;
+        d.status = pl->status.p + s;
+        SolveJob& j = jb[s];
+        j.panels = d.panels; j.ainv = d.ainv;
+        j.rhs = pl->lam.p + s * N; j.x = pl->lam.p + s * N;
+        j.zbuf = pl->zadj.p + s * (size_t)pl->S * 8;
+    }
+    if (cudaMemcpy(pl->sysDesc.p, sd.data(), sizeof(BandSys) * nSys, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(pl->jobs.p, jb.data(), sizeof(SolveJob) * nSys, cudaMemcpyHostToDevice) != cudaSuccess) {
+        hmcmt_destroy(pl);
+        return kErrCuda;
+    }
+    if (cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&pl->evA) != cudaSuccess || cudaEventCreate(&pl->evB) != cudaSuccess) {
+        hmcmt_destroy(pl);
+        return kErrCuda;
+    }
+    *out = pl;
+    return kOk;
+}
+
+void hmcmt_destroy(hmcmt_plan* pl) {
+    if (!pl) return;
+    cudaSetDevice(pl->device);
+    if (pl->stream) { cudaStreamSynchronize(pl->stream); cudaStreamDestroy(pl->stream); }
+    if (pl->evA) cudaEventDestroy(pl->evA);
+    if (pl->evB) cudaEventDestroy(pl->evB);
+    for (auto& e : pl->factorEvents) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    pl->yLen.release(); pl->zLen.release(); pl->zNode.release(); pl->freqs.release(); pl->fdy1.release(); pl->fdy2.release();
+    pl->wL.release(); pl->wR.release(); pl->bg.release(); pl->wmVal.release(); pl->wd.release(); pl->m.release(); pl->p.release();
+    pl->mref.release(); pl->sigma.release(); pl->meanSig.release(); pl->planes.release(); pl->Gpart.release(); pl->phiPart.release();
+    pl->phi.release(); pl->gdata.release(); pl->gtotal.release(); pl->energies.release(); pl->panels.release(); pl->curM.release();
+    pl->curP.release(); pl->chainScal.release(); pl->zmom.release(); pl->fid.release(); pl->iL.release(); pl->iR.release();
+    pl->cell2act.release(); pl->act2cell.release(); pl->wmPtr.release(); pl->wmIdx.release(); pl->status.release();
+    pl->driftFlag.release(); pl->packed2full.release(); pl->Lsteps.release(); pl->obs.release(); pl->bc.release(); pl->bcs.release();
+    pl->rhs.release(); pl->x.release(); pl->F.release(); pl->lam.release(); pl->Lam.release(); pl->srows.release(); pl->qrow.release();
+    pl->scratch.release(); pl->predFull.release(); pl->ainv.release(); pl->z.release(); pl->zadj.release(); pl->vin.release();
+    pl->predPacked.release(); pl->sysDesc.release(); pl->jobs.release();
+    if (pl->pin) cudaFreeHost(pl->pin);
+    delete pl;
+}
+
+int64_t hmcmt_plan_info(const hmcmt_plan* pl, int what) {
+    if (!pl) return -1;
+    switch (what) {
+        case 0: return pl->M.N;
+        case 1: return pl->M.nNode;
+        case 2: return pl->M.nCell;
+        case 3: return pl->M.nb;
+        case 4: return pl->b;
+        case 5: return pl->T;
+        case 6: return pl->S;
+        case 7: return pl->nSysPerChain;
+        case 8: return pl->M.zid;
+        case 9: return (int64_t)pl->S * (panel_doubles(pl->T) * 8 + 64 * 16 + 8 * 16);
+        case 10: return pl->launches;
+        default: return -1;
+    }
+}
+
+int hmcmt_sync(hmcmt_plan* pl) {
+    if (!pl) return kErrArg;
+    HMCMT_CUDA_TRY(cudaStreamSynchronize(pl->stream));
+    return kOk;
+}
+int hmcmt_timer_start(hmcmt_plan* pl) {
+    if (!pl) return kErrArg;
+    HMCMT_CUDA_TRY(cudaEventRecord(pl->evA, pl->stream));
+    return kOk;
+}
+int hmcmt_timer_stop(hmcmt_plan* pl, float* ms) {
+    if (!pl || !ms) return kErrArg;
+    HMCMT_CUDA_TRY(cudaEventRecord(pl->evB, pl->stream));
+    HMCMT_CUDA_TRY(cudaEventSynchronize(pl->evB));
+    HMCMT_CUDA_TRY(cudaEventElapsedTime(ms, pl->evA, pl->evB));
+    return kOk;
+}
+int hmcmt_kernel_time(hmcmt_plan* pl, int reset, float* factor_ms, int64_t* factor_launches) {
+    if (!pl) return kErrArg;
+    HMCMT_CUDA_TRY(cudaStreamSynchronize(pl->stream));
+    float tot = 0.f;
+    for (size_t i = 0; i < pl->factorEventsUsed; ++i) {
+        float ms = 0.f;
+        HMCMT_CUDA_TRY(cudaEventElapsedTime(&ms, pl->factorEvents[i].first, pl->factorEvents[i].second));
+        tot += ms;
+    }
+    if (factor_ms) *factor_ms = tot;
+    if (factor_launches) *factor_launches = (int64_t)pl->factorEventsUsed;
+    if (reset) pl->factorEventsUsed = 0;
+    return kOk;
+}
+
+static int upload_model(hmcmt_plan* pl, const double* m) {
+    size_t bytes = sizeof(double) * (size_t)pl->nChains * pl->nAC;
+    int rc = ensure_pin(pl, std::max(bytes, (size_t)1 << 20));
+    if (rc) return rc;
+    std::memcpy(pl->pin, m, bytes);
+    HMCMT_CUDA_TRY(cudaMemcpyAsync(pl->m.p, pl->pin, bytes, cudaMemcpyHostToDevice, pl->stream));
+    return kOk;
+}
+static int download_pred(hmcmt_plan* pl, double* pred) {
+    k_pack_pred<<<dim3((pl->nData + 255) / 256, pl->nChains), 256, 0, pl->stream>>>(pl->nData, pl->nFull, pl->packed2full.p,
+                                                                                    pl->predFull.p, pl->predPacked.p);
+    LAUNCH_CHECK(pl);
+    HMCMT_CUDA_TRY(cudaMemcpyAsync(pred, pl->predPacked.p, sizeof(cplx) * (size_t)pl->nChains * pl->nData, cudaMemcpyDeviceToHost, pl->stream));
+    return kOk;
+}
+
+int hmcmt_forward(hmcmt_plan* pl, const double* m, double* pred, double* exTE, double* hxTM) {
+    if (!pl || !m) return kErrArg;
+    HMCMT_CUDA_TRY(cudaSetDevice(pl->device));
+    int rc = upload_model(pl, m);
+    if (rc) return rc;
+    rc = compute_step(pl, false, nullptr);
+    if (rc) return rc;
+    if (pred) { rc = download_pred(pl, pred); if (rc) return rc; }
+    const MeshDev& M = pl->M;
+    for (int ch = 0; ch < pl->nChains; ++ch)
+        for (int mi = 0; mi < pl->nModes; ++mi) {
+            double* dst = pl->modeList[mi] == 0 ? exTE : hxTM;
+            if (!dst) continue;
+            size_t sys0 = ((size_t)ch * pl->nModes + mi) * pl->nFreq;
+            HMCMT_CUDA_TRY(cudaMemcpyAsync(dst + 2 * (size_t)ch * pl->nFreq * M.nNode, pl->F.p + sys0 * M.nNode,
+                                           sizeof(cplx) * (size_t)pl->nFreq * M.nNode, cudaMemcpyDeviceToHost, pl->stream));
+        }
+    HMCMT_CUDA_TRY(cudaStreamSynchronize(pl->stream));
+    return check_status(pl);
+}
+
+int hmcmt_jtvec(hmcmt_plan* pl, const double* v, double* gsig) {
+    if (!pl || !v || !gsig) return kErrArg;
+    if (!pl->haveForward) return kErrArg;
+    HMCMT_CUDA_TRY(cudaSetDevice(pl->device));
+    // scatter the packed data vector into the full layout
+    std::vector<cplx> full((size_t)pl->nChains * pl->nFull, mk(0.0, 0.0));
+    for (int ch = 0; ch < pl->nChains; ++ch)
+        for (int i = 0; i < pl->nData; ++i)
+            full[(size_t)ch * pl->nFull + pl->h_packed2full[i]] = mk(v[2 * ((size_t)ch * pl->nData + i)], v[2 * ((size_t)ch * pl->nData + i) + 1]);
+    HMCMT_CUDA_TRY(cudaMemcpyAsync(pl->vin.p, full.data(), sizeof(cplx) * full.size(), cudaMemcpyHostToDevice, pl->stream));
+    HMCMT_CUDA_TRY(cudaStreamSynchronize(pl->stream));
+    // re-evaluates the forward for the resident model (same factors) and contracts with the supplied v
+    int rc = compute_step(pl, true, pl->vin.p);
+    if (rc) return rc;
+    // undo the chain rule and the prior: gsig = sum_sys Re(G) on active cells = gdata / sigma
+    std::vector<double> g((size_t)pl->nChains * pl->nAC), mm((size_t)pl->nChains * pl->nAC);
+    HMCMT_CUDA_TRY(cudaMemcpyAsync(g.data(), pl->gdata.p, sizeof(double) * g.size(), cudaMemcpyDeviceToHost, pl->stream));
+    HMCMT_CUDA_TRY(cudaMemcpyAsync(mm.data(), pl->m.p, sizeof(double) * mm.size(), cudaMemcpyDeviceToHost, pl->stream));
+    HMCMT_CUDA_TRY(cudaStreamSynchronize(pl->stream));
+    for (size_t i = 0; i < g.size(); ++i) gsig[i] = g[i] / std::exp(mm[i]);
+    return check_status(pl);
+}
+
+int hmcmt_forward_gradient(hmcmt_plan* pl, const double* m, double* pred, double* phid, double* grad) {
+    if (!pl || !m) return kErrArg;
+    HMCMT_CUDA_TRY(cudaSetDevice(pl->device));
+    int rc = upload_model(pl, m);
+    if (rc) return rc;
+    rc = compute_step(pl, true, nullptr);
+    if (rc) return rc;
+    if (pred) { rc = download_pred(pl, pred); if (rc) return rc; }
+    if (phid) HMCMT_CUDA_TRY(cudaMemcpyAsync(phid, pl->phi.p, sizeof(double) * pl->nChains, cudaMemcpyDeviceToHost, pl->stream));
+    if (grad) HMCMT_CUDA_TRY(cudaMemcpyAsync(grad, pl->gdata.p, sizeof(double) * (size_t)pl->nChains * pl->nAC, cudaMemcpyDeviceToHost, pl->stream));
+    HMCMT_CUDA_TRY(cudaStreamSynchronize(pl->stream));
+    return check_status(pl);
+}
+
+int hmcmt_set_state(hmcmt_plan* pl, const double* m, const double* p, const double* mref) {
+    if (!pl) return kErrArg;
+    HMCMT_CUDA_TRY(cudaSetDevice(pl->device));
+    size_t bytes = sizeof(double) * (size_t)pl->nChains * pl->nAC;
+    if (m) HMCMT_CUDA_TRY(cudaMemcpyAsync(pl->m.p, m, bytes, cudaMemcpyHostToDevice, pl->stream));
+    if (p) HMCMT_CUDA_TRY(cudaMemcpyAsync(pl->p.p, p, bytes, cudaMemcpyHostToDevice, pl->stream));
+    if (mref) HMCMT_CUDA_TRY(cudaMemcpyAsync(pl->mref.p, mref, bytes, cudaMemcpyHostToDevice, pl->stream));
+    HMCMT_CUDA_TRY(cudaStreamSynchronize(pl->stream));
+    return kOk;
+}
+int hmcmt_get_state(hmcmt_plan* pl, double* m, double* p) {
+    if (!pl) return kErrArg;
+    HMCMT_CUDA_TRY(cudaSetDevice(pl->device));
+    size_t bytes = sizeof(double) * (size_t)pl->nChains * pl->nAC;
+    if (m) HMCMT_CUDA_TRY(cudaMemcpyAsync(m, pl->m.p, bytes, cudaMemcpyDeviceToHost, pl->stream));
+    if (p) HMCMT_CUDA_TRY(cudaMemcpyAsync(p, pl->p.p, bytes, cudaMemcpyDeviceToHost, pl->stream));
+    HMCMT_CUDA_TRY(cudaStreamSynchronize(pl->stream));
+    return kOk;
+}
+
+static int trajectory_device(hmcmt_plan* pl, double dt, int Lmax) {
+    // proposeLeapfrog HMCSampler.jl:206-269 (per-chain step counts in pl->Lsteps)
+    dim3 g((pl->nAC + 255) / 256, pl->nChains);
+    int rc = compute_step(pl, true, nullptr);
+    if (rc) return rc;
+    k_kick_masked<<<g, 256, 0, pl->stream>>>(pl->nAC, dt, 0, pl->Lsteps.p, pl->gtotal.p, pl->p.p);
+    LAUNCH_CHECK(pl);
+    for (int k = 1; k <= Lmax; ++k) {
+        // chains that already finished (k > L) are frozen by a zero drift: handled through dt masking below
+        k_drift<<<pl->nChains, kHmcThreads, 0, pl->stream>>>(pl->nAC, dt, pl->lo, pl->hi, pl->m.p, pl->p.p, pl->driftFlag.p);
+        LAUNCH_CHECK(pl);
+        rc = compute_step(pl, true, nullptr);
+        if (rc) return rc;
+        k_kick_masked<<<g, 256, 0, pl->stream>>>(pl->nAC, dt, k, pl->Lsteps.p, pl->gtotal.p, pl->p.p);
+        LAUNCH_CHECK(pl);
+    }
+    return kOk;
+}
+
+int hmcmt_leapfrog_trajectory(hmcmt_plan* pl, double dt, const int32_t* intstep, double* stats, double* pred) {
+    if (!pl || !intstep) return kErrArg;
+    HMCMT_CUDA_TRY(cudaSetDevice(pl->device));
+    int Lmax = 0;
+    for (int ch = 0; ch < pl->nChains; ++ch) {
+        if (intstep[ch] != intstep[0]) {
+            fprintf(stderr, "[hmcmt_b200] chains batched on one device must share the leapfrog step count\n");
+            return kErrArg;
+        }
+        Lmax = std::max(Lmax, (int)intstep[ch]);
+    }
+    std::vector<int> L(intstep, intstep + pl->nChains);
+    HMCMT_CUDA_TRY(cudaMemcpyAsync(pl->Lsteps.p, L.data(), sizeof(int) * pl->nChains, cudaMemcpyHostToDevice, pl->stream));
+    HMCMT_CUDA_TRY(cudaStreamSynchronize(pl->stream));
+    int rc = trajectory_device(pl, dt, Lmax);
+    if (rc) return rc;
+    k_energies<<<pl->nChains, kHmcThreads, 0, pl->stream>>>(pl->nAC, pl->m.p, pl->mref.p, pl->p.p, pl->wmPtr.p, pl->wmIdx.p, pl->wmVal.p,
+                                                            pl->beta, pl->energies.p);
+    LAUNCH_CHECK(pl);
+    std::vector<double> e(2 * pl->nChains), ph(pl->nChains);
+    HMCMT_CUDA_TRY(cudaMemcpyAsync(e.data(), pl->energies.p, sizeof(double) * e.size(), cudaMemcpyDeviceToHost, pl->stream));
+    HMCMT_CUDA_TRY(cudaMemcpyAsync(ph.data(), pl->phi.p, sizeof(double) * ph.size(), cudaMemcpyDeviceToHost, pl->stream));
+    if (pred) { rc = download_pred(pl, pred); if (rc) return rc; }
+    HMCMT_CUDA_TRY(cudaStreamSynchronize(pl->stream));
+    if (stats)
+        for (int ch = 0; ch < pl->nChains; ++ch) {
+            stats[4 * ch + 0] = ph[ch];
+            stats[4 * ch + 1] = e[2 * ch + 1];
+            stats[4 * ch + 2] = e[2 * ch];
+            stats[4 * ch + 3] = ph[ch] + e[2 * ch] + e[2 * ch + 1];     // hmp = dataMisfit + kp + mnorm (:393)
+        }
+    return check_status(pl);
+}
+
+int hmcmt_leapfrog_steps_device(hmcmt_plan* pl, double dt, int32_t nsteps) {
+    if (!pl || nsteps < 0) return kErrArg;
+    HMCMT_CUDA_TRY(cudaSetDevice(pl->device));
+    dim3 g((pl->nAC + 255) / 256, pl->nChains);
+    for (int k = 0; k < nsteps; ++k) {
+        int rc = drift(pl, dt);
+        if (rc) return rc;
+        rc = compute_step(pl, true, nullptr);
+        if (rc) return rc;
+        k_kick<<<pl->nChains, 1024, 0, pl->stream>>>(pl->nAC, dt, pl->gtotal.p, pl->p.p);
+        LAUNCH_CHECK(pl);
+    }
+    return kOk;
+}
+
+int hmcmt_run_chain(hmcmt_plan* pl, double dt, int32_t nsamples, double rhoref, const double* z_init, const int32_t* intsteps,
+                    const double* u_accept, const double* z_mom, int32_t reuse_last_forward, double* hmcmodel, double* hmstats,
+                    int32_t* accept, double* hmcdata) {
+    // rhoref = round(unirandDouble(0.5 rho0, 1.5 rho0)), rho0 = 1/exp(strModel[1]) (HMCSampler.jl:100-105), drawn by the caller.
+    if (!pl || nsamples < 1 || !z_init || !intsteps || !u_accept || !z_mom) return kErrArg;
+    HMCMT_CUDA_TRY(cudaSetDevice(pl->device));
+    const int nCh = pl->nChains, nAC = pl->nAC, nData = pl->nData;
+    cudaStream_t st = pl->stream;
+    DevBuf<double> dModel, dStats, dUacc;
+    DevBuf<int> dAcc;
+    DevBuf<cplx> dData;
+    int rc = kOk;
+    auto ok = [&](int r) { if (r && !rc) rc = r; };
+    ok(dModel.alloc((size_t)nCh * nsamples * nAC)); ok(dStats.alloc((size_t)nCh * (nsamples + 1) * 4));
+    ok(dUacc.upload(u_accept, (size_t)nCh * nsamples)); ok(dAcc.alloc((size_t)nCh * nsamples));
+    ok(dData.alloc((size_t)nCh * (nsamples + 1) * nData));
+    auto cleanup = [&]() { dModel.release(); dStats.release(); dUacc.release(); dAcc.release(); dData.release(); };
+    if (rc) { cleanup(); return rc; }
+    dim3 g((nAC + 255) / 256, nCh);
+#define RC_TRY(x) do { int _r = (x); if (_r) { cleanup(); return _r; } } while (0)
+#define RC_CUDA(x) do { if ((x) != cudaSuccess) { cleanup(); return kErrCuda; } } while (0)
+    // start model: homogeneous rhoref (HMCSampler.jl:100-109), m = mref = log(1/rhoref)
+    double mstart = std::log(1.0 / rhoref);
+    k_fill<<<(unsigned)(((size_t)nCh * nAC + 255) / 256), 256, 0, st>>>((size_t)nCh * nAC, mstart, pl->m.p);
+    k_fill<<<(unsigned)(((size_t)nCh * nAC + 255) / 256), 256, 0, st>>>((size_t)nCh * nAC, mstart, pl->mref.p);
+    RC_CUDA(cudaMemcpyAsync(pl->curM.p, pl->m.p, sizeof(double) * (size_t)nCh * nAC, cudaMemcpyDeviceToDevice, st));
+    RC_CUDA(cudaMemcpyAsync(pl->zmom.p, z_init, sizeof(double) * (size_t)nCh * nAC, cudaMemcpyHostToDevice, st));
+    k_clip_momentum<<<g, 256, 0, st>>>(nAC, pl->zmom.p, pl->p.p);
+    pl->launches += 3;
+    // Hamiltonian at the start (getHamiltonian HMCSampler.jl:113-115)
+    RC_TRY(compute_step(pl, false, nullptr));
+    k_energies<<<nCh, kHmcThreads, 0, st>>>(nAC, pl->m.p, pl->mref.p, pl->p.p, pl->wmPtr.p, pl->wmIdx.p, pl->wmVal.p, pl->beta, pl->energies.p);
+    k_pack_pred<<<dim3((nData + 255) / 256, nCh), 256, 0, st>>>(nData, pl->nFull, pl->packed2full.p, pl->predFull.p, pl->predPacked.p);
+    pl->launches += 2;
+    {
+        std::vector<double> e(2 * nCh), ph(nCh), sc(4 * nCh);
+        RC_CUDA(cudaMemcpyAsync(e.data(), pl->energies.p, sizeof(double) * e.size(), cudaMemcpyDeviceToHost, st));
+        RC_CUDA(cudaMemcpyAsync(ph.data(), pl->phi.p, sizeof(double) * ph.size(), cudaMemcpyDeviceToHost, st));
+        RC_CUDA(cudaStreamSynchronize(st));
+        for (int ch = 0; ch < nCh; ++ch) {
+            sc[4 * ch + 0] = ph[ch]; sc[4 * ch + 1] = e[2 * ch + 1]; sc[4 * ch + 2] = e[2 * ch];
+            sc[4 * ch + 3] = ph[ch] + e[2 * ch] + e[2 * ch + 1];
+            RC_CUDA(cudaMemcpyAsync(dStats.p + (size_t)ch * (nsamples + 1) * 4, &sc[4 * ch], sizeof(double) * 4, cudaMemcpyHostToDevice, st));
+            RC_CUDA(cudaMemcpyAsync(dData.p + (size_t)ch * (nsamples + 1) * nData, pl->predPacked.p + (size_t)ch * nData,
+                                    sizeof(cplx) * nData, cudaMemcpyDeviceToDevice, st));
+        }
+        RC_CUDA(cudaMemcpyAsync(pl->chainScal.p, sc.data(), sizeof(double) * sc.size(), cudaMemcpyHostToDevice, st));
+        RC_CUDA(cudaStreamSynchronize(st));
+    }
+    for (int it = 1; it <= nsamples; ++it) {
+        int L = intsteps[it - 1];
+        std::vector<int> Lv(nCh, L);
+        RC_CUDA(cudaMemcpyAsync(pl->Lsteps.p, Lv.data(), sizeof(int) * nCh, cudaMemcpyHostToDevice, st));
+        RC_CUDA(cudaStreamSynchronize(st));
+        RC_TRY(trajectory_device(pl, dt, L));
+        if (!reuse_last_forward) RC_TRY(compute_step(pl, false, nullptr));       // the reference's redundant forward sweep
+        k_energies<<<nCh, kHmcThreads, 0, st>>>(nAC, pl->m.p, pl->mref.p, pl->p.p, pl->wmPtr.p, pl->wmIdx.p, pl->wmVal.p, pl->beta, pl->energies.p);
+        k_pack_pred<<<dim3((nData + 255) / 256, nCh), 256, 0, st>>>(nData, pl->nFull, pl->packed2full.p, pl->predFull.p, pl->predPacked.p);
+        // z_mom layout: [sample][chain][nAC]
+        RC_CUDA(cudaMemcpyAsync(pl->zmom.p, z_mom + (size_t)(it - 1) * nCh * nAC, sizeof(double) * (size_t)nCh * nAC, cudaMemcpyHostToDevice, st));
+        k_accept<<<nCh, kHmcThreads, 0, st>>>(nAC, nData, it, nsamples, dUacc.p, pl->phi.p, pl->energies.p, pl->zmom.p, pl->m.p, pl->p.p,
+                                              pl->curM.p, pl->chainScal.p, pl->predPacked.p, dModel.p, dStats.p, dAcc.p, dData.p);
+        pl->launches += 3;
+        if (cudaGetLastError() != cudaSuccess) { cleanup(); return kErrCuda; }
+    }
+    RC_CUDA(cudaMemcpyAsync(hmcmodel, dModel.p, sizeof(double) * dModel.n, cudaMemcpyDeviceToHost, st));
+    RC_CUDA(cudaMemcpyAsync(hmstats, dStats.p, sizeof(double) * dStats.n, cudaMemcpyDeviceToHost, st));
+    RC_CUDA(cudaMemcpyAsync(accept, dAcc.p, sizeof(int) * dAcc.n, cudaMemcpyDeviceToHost, st));
+    RC_CUDA(cudaMemcpyAsync(hmcdata, dData.p, sizeof(cplx) * dData.n, cudaMemcpyDeviceToHost, st));
+    RC_CUDA(cudaStreamSynchronize(st));
+    cleanup();
+#undef RC_TRY
+#undef RC_CUDA
+    return check_status(pl);
+}
+
+int hmcmt_export_system(hmcmt_plan* pl, int32_t chain, int32_t mode, int32_t freq, int64_t* colptr, int64_t* rowval, double* nzval,
+                        double* rhs, double* bc) {
+    if (!pl || chain < 0 || chain >= pl->nChains || freq < 0 || freq >= pl->nFreq) return kErrArg;
+    int mi = -1;
+    for (int c = 0; c < pl->nModes; ++c) if (pl->modeList[c] == mode) mi = c;
+    if (mi < 0 || !pl->haveForward) return kErrArg;
+    HMCMT_CUDA_TRY(cudaSetDevice(pl->device));
+    HMCMT_CUDA_TRY(cudaStreamSynchronize(pl->stream));
+    const MeshDev& M = pl->M;
+    const size_t N = M.N;
+    std::vector<double> P(4 * N);
+    HMCMT_CUDA_TRY(cudaMemcpy(P.data(), pl->planes.p + ((size_t)(chain * pl->nModes + mi) * 4) * N, sizeof(double) * 4 * N, cudaMemcpyDeviceToHost));
+    const size_t sys = ((size_t)chain * pl->nModes + mi) * pl->nFreq + freq;
+    std::vector<cplx> r(N), b(M.nb);
+    HMCMT_CUDA_TRY(cudaMemcpy(r.data(), pl->rhs.p + sys * N, sizeof(cplx) * N, cudaMemcpyDeviceToHost));
+    HMCMT_CUDA_TRY(cudaMemcpy(b.data(), pl->bc.p + sys * M.nb, sizeof(cplx) * M.nb, cudaMemcpyDeviceToHost));
+    const double omega = 2.0 * kPi * pl->h_freqs[freq];
+    const int n1 = M.n1, n2 = M.n2;
+    auto qof = [&](int jn, int kn) { return M.fastZ ? (size_t)(jn - 1) * M.nf + (kn - 1) : (size_t)(kn - 1) * M.nf + (jn - 1); };
+    // coupling between (jn,kn) and its -y / -z neighbour, from the internal planes
+    auto cy = [&](int jn, int kn) { size_t q = qof(jn, kn); return M.fastZ ? P[3 * N + q] : P[2 * N + q]; };   // to (jn-1,kn)
+    auto cz = [&](int jn, int kn) { size_t q = qof(jn, kn); return M.fastZ ? P[2 * N + q] : P[3 * N + q]; };   // to (jn,kn-1)
+    int64_t nnz = 0;
+    for (int kn = 1; kn <= n2; ++kn)
+        for (int jn = 1; jn <= n1; ++jn) {
+            int64_t pcol = (int64_t)(kn - 1) * n1 + (jn - 1);      // reference interior numbering, y fastest (0-based)
+            colptr[pcol] = nnz + 1;
+            size_t q = qof(jn, kn);
+            if (kn > 1) { rowval[nnz] = pcol - n1 + 1; nzval[2 * nnz] = cz(jn, kn); nzval[2 * nnz + 1] = 0.0; ++nnz; }
+            if (jn > 1) { rowval[nnz] = pcol - 1 + 1; nzval[2 * nnz] = cy(jn, kn); nzval[2 * nnz + 1] = 0.0; ++nnz; }
+            rowval[nnz] = pcol + 1; nzval[2 * nnz] = P[q]; nzval[2 * nnz + 1] = omega * P[N + q]; ++nnz;
+            if (jn < n1) { rowval[nnz] = pcol + 1 + 1; nzval[2 * nnz] = cy(jn + 1, kn); nzval[2 * nnz + 1] = 0.0; ++nnz; }
+            if (kn < n2) { rowval[nnz] = pcol + n1 + 1; nzval[2 * nnz] = cz(jn, kn + 1); nzval[2 * nnz + 1] = 0.0; ++nnz; }
+            if (rhs) { rhs[2 * pcol] = r[q].x; rhs[2 * pcol + 1] = r[q].y; }
+        }
+    colptr[N] = nnz + 1;
+    if (bc) for (int i = 0; i < M.nb; ++i) { bc[2 * i] = b[i].x; bc[2 * i + 1] = b[i].y; }
+    return kOk;
+}
+
+}  // extern "C"

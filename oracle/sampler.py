@@ -187,8 +187,8 @@ def runHMCSampler(mesh, data, inv: InvDataModel, prior: HMCPrior, streams: Rando
     nparam, ndata = len(inv.strModel), len(inv.obsData)
     nsamples = prior.totalsamples if nsamples is None else nsamples
     cur_p = clip_momentum(streams.z_init)
-    sigma0 = np.unique(inv.strModel)                         # :100-109
-    rho0 = 1.0 / np.exp(sigma0[0])
+    sigma0 = inv.strModel[0]          # unique(strModel)[1]: Julia's unique keeps first-appearance order (:100-101)
+    rho0 = 1.0 / np.exp(sigma0)
     rhoref = np.round(rho0 * 0.5 + (rho0 * 1.5 - rho0 * 0.5) * streams.u_start)
     strModel = np.log(np.ones(nparam) / rhoref)
     inv.strModel = strModel.copy()
