@@ -52,13 +52,13 @@ struct hmcmt_plan {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> factorEvents;
     size_t factorEventsUsed = 0;
     int64_t launches = 0, factorLaunches = 0;
-    bool haveForward = false;
+    bool haveForward = false, sigmaDirect = false;
     // host copies
     std::vector<double> h_yLen, h_zLen, h_freqs;
     std::vector<int> h_packed2full;      // [nData] full index (without chain) of each packed datum
     // device buffers
     DevBuf<double> yLen, zLen, zNode, freqs, fdy1, fdy2, wL, wR, bg, wmVal, wd, m, p, mref, sigma, meanSig, planes;
-    DevBuf<double> Gpart, phiPart, phi, gdata, gtotal, energies, panels, curM, curP, chainScal, zmom;
+    DevBuf<double> Gpart, phiPart, phi, gsig, gdata, gtotal, energies, panels, curM, curP, chainScal, zmom;
     DevBuf<int> fid, iL, iR, cell2act, act2cell, wmPtr, wmIdx, status, driftFlag, packed2full, Lsteps;
     DevBuf<cplx> obs, bc, bcs, rhs, x, F, lam, Lam, srows, qrow, scratch, predFull, ainv, z, zadj, vin, predPacked;
     DevBuf<BandSys> sysDesc;
@@ -256,8 +256,10 @@ int compute_step(hmcmt_plan* pl, bool wantAdjoint, const cplx* vin) {
     const MeshDev& M = pl->M;
     cudaStream_t st = pl->stream;
     const int nSys = pl->nSys, nCh = pl->nChains;
-    k_model_transform<<<dim3((M.nCell + 255) / 256, nCh), 256, 0, st>>>(M.nCell, pl->nAC, pl->cell2act.p, pl->bg.p, pl->m.p, pl->sigma.p);
-    LAUNCH_CHECK(pl);
+    if (!pl->sigmaDirect) {
+        k_model_transform<<<dim3((M.nCell + 255) / 256, nCh), 256, 0, st>>>(M.nCell, pl->nAC, pl->cell2act.p, pl->bg.p, pl->m.p, pl->sigma.p);
+        LAUNCH_CHECK(pl);
+    }
     k_stencil_planes<<<dim3((M.N + 255) / 256, nCh * pl->nModes), 256, 0, st>>>(M, pl->sm, pl->sigma.p, pl->planes.p);
     LAUNCH_CHECK(pl);
     k_boundary<<<dim3((M.ny + 1 + 63) / 64, nSys), 64, 0, st>>>(M, pl->sm, pl->freqs.p, pl->sigma.p, pl->bc.p);
@@ -307,7 +309,7 @@ int compute_step(hmcmt_plan* pl, bool wantAdjoint, const cplx* vin) {
     LAUNCH_CHECK(pl);
     k_reduce_grad<<<dim3((pl->nAC + 255) / 256, nCh), 256, 0, st>>>(pl->nAC, M.nCell, pl->nSysPerChain, pl->act2cell.p, pl->Gpart.p,
                                                                    pl->m.p, pl->mref.p, pl->wmPtr.p, pl->wmIdx.p, pl->wmVal.p, pl->beta,
-                                                                   pl->gdata.p, pl->gtotal.p);
+                                                                   pl->sigma.p, pl->gsig.p, pl->gdata.p, pl->gtotal.p);
     LAUNCH_CHECK(pl);
     return kOk;
 }
@@ -445,7 +447,7 @@ int hmcmt_plan_create(const hmcmt_problem* pr, hmcmt_plan** out) {
     ok(pl->srows.alloc(nSys * 2 * (ny + 1))); ok(pl->qrow.alloc(nSys * ny));
     ok(pl->scratch.alloc(nSys * 3 * prof_stride(nz)));
     ok(pl->Gpart.alloc(nSys * M.nCell)); ok(pl->phiPart.alloc(nSys)); ok(pl->phi.alloc(nCh));
-    ok(pl->gdata.alloc(nCh * pr->nAC)); ok(pl->gtotal.alloc(nCh * pr->nAC)); ok(pl->energies.alloc(nCh * 2));
+    ok(pl->gsig.alloc(nCh * pr->nAC)); ok(pl->gdata.alloc(nCh * pr->nAC)); ok(pl->gtotal.alloc(nCh * pr->nAC)); ok(pl->energies.alloc(nCh * 2));
     ok(pl->chainScal.alloc(nCh * 4));
     ok(pl->predFull.alloc(nCh * pl->nFull)); ok(pl->vin.alloc(nCh * pl->nFull)); ok(pl->predPacked.alloc(nCh * pr->nData));
     ok(pl->panels.alloc(nSys * (size_t)pl->S * panel_doubles(pl->T)));
@@ -507,7 +509,7 @@ void hmcmt_destroy(hmcmt_plan* pl) {
     pl->yLen.release(); pl->zLen.release(); pl->zNode.release(); pl->freqs.release(); pl->fdy1.release(); pl->fdy2.release();
     pl->wL.release(); pl->wR.release(); pl->bg.release(); pl->wmVal.release(); pl->wd.release(); pl->m.release(); pl->p.release();
     pl->mref.release(); pl->sigma.release(); pl->meanSig.release(); pl->planes.release(); pl->Gpart.release(); pl->phiPart.release();
-    pl->phi.release(); pl->gdata.release(); pl->gtotal.release(); pl->energies.release(); pl->panels.release(); pl->curM.release();
+    pl->phi.release(); pl->gsig.release(); pl->gdata.release(); pl->gtotal.release(); pl->energies.release(); pl->panels.release(); pl->curM.release();
     pl->curP.release(); pl->chainScal.release(); pl->zmom.release(); pl->fid.release(); pl->iL.release(); pl->iR.release();
     pl->cell2act.release(); pl->act2cell.release(); pl->wmPtr.release(); pl->wmIdx.release(); pl->status.release();
     pl->driftFlag.release(); pl->packed2full.release(); pl->Lsteps.release(); pl->obs.release(); pl->bc.release(); pl->bcs.release();
@@ -584,12 +586,28 @@ static int download_pred(hmcmt_plan* pl, double* pred) {
     return kOk;
 }
 
+static int forward_common(hmcmt_plan* pl, double* pred, double* exTE, double* hxTM);
+
 int hmcmt_forward(hmcmt_plan* pl, const double* m, double* pred, double* exTE, double* hxTM) {
     if (!pl || !m) return kErrArg;
     HMCMT_CUDA_TRY(cudaSetDevice(pl->device));
+    pl->sigmaDirect = false;
     int rc = upload_model(pl, m);
     if (rc) return rc;
-    rc = compute_step(pl, false, nullptr);
+    return forward_common(pl, pred, exTE, hxTM);
+}
+
+int hmcmt_forward_sigma(hmcmt_plan* pl, const double* sigma, double* pred, double* exTE, double* hxTM) {
+    if (!pl || !sigma) return kErrArg;
+    HMCMT_CUDA_TRY(cudaSetDevice(pl->device));
+    pl->sigmaDirect = true;
+    HMCMT_CUDA_TRY(cudaMemcpyAsync(pl->sigma.p, sigma, sizeof(double) * (size_t)pl->nChains * pl->M.nCell, cudaMemcpyHostToDevice, pl->stream));
+    HMCMT_CUDA_TRY(cudaStreamSynchronize(pl->stream));
+    return forward_common(pl, pred, exTE, hxTM);
+}
+
+static int forward_common(hmcmt_plan* pl, double* pred, double* exTE, double* hxTM) {
+    int rc = compute_step(pl, false, nullptr);
     if (rc) return rc;
     if (pred) { rc = download_pred(pl, pred); if (rc) return rc; }
     const MeshDev& M = pl->M;
@@ -619,18 +637,15 @@ int hmcmt_jtvec(hmcmt_plan* pl, const double* v, double* gsig) {
     // re-evaluates the forward for the resident model (same factors) and contracts with the supplied v
     int rc = compute_step(pl, true, pl->vin.p);
     if (rc) return rc;
-    // undo the chain rule and the prior: gsig = sum_sys Re(G) on active cells = gdata / sigma
-    std::vector<double> g((size_t)pl->nChains * pl->nAC), mm((size_t)pl->nChains * pl->nAC);
-    HMCMT_CUDA_TRY(cudaMemcpyAsync(g.data(), pl->gdata.p, sizeof(double) * g.size(), cudaMemcpyDeviceToHost, pl->stream));
-    HMCMT_CUDA_TRY(cudaMemcpyAsync(mm.data(), pl->m.p, sizeof(double) * mm.size(), cudaMemcpyDeviceToHost, pl->stream));
+    HMCMT_CUDA_TRY(cudaMemcpyAsync(gsig, pl->gsig.p, sizeof(double) * (size_t)pl->nChains * pl->nAC, cudaMemcpyDeviceToHost, pl->stream));
     HMCMT_CUDA_TRY(cudaStreamSynchronize(pl->stream));
-    for (size_t i = 0; i < g.size(); ++i) gsig[i] = g[i] / std::exp(mm[i]);
     return check_status(pl);
 }
 
 int hmcmt_forward_gradient(hmcmt_plan* pl, const double* m, double* pred, double* phid, double* grad) {
     if (!pl || !m) return kErrArg;
     HMCMT_CUDA_TRY(cudaSetDevice(pl->device));
+    pl->sigmaDirect = false;
     int rc = upload_model(pl, m);
     if (rc) return rc;
     rc = compute_step(pl, true, nullptr);
@@ -646,6 +661,7 @@ int hmcmt_set_state(hmcmt_plan* pl, const double* m, const double* p, const doub
     if (!pl) return kErrArg;
     HMCMT_CUDA_TRY(cudaSetDevice(pl->device));
     size_t bytes = sizeof(double) * (size_t)pl->nChains * pl->nAC;
+    pl->sigmaDirect = false;
     if (m) HMCMT_CUDA_TRY(cudaMemcpyAsync(pl->m.p, m, bytes, cudaMemcpyHostToDevice, pl->stream));
     if (p) HMCMT_CUDA_TRY(cudaMemcpyAsync(pl->p.p, p, bytes, cudaMemcpyHostToDevice, pl->stream));
     if (mref) HMCMT_CUDA_TRY(cudaMemcpyAsync(pl->mref.p, mref, bytes, cudaMemcpyHostToDevice, pl->stream));
@@ -738,6 +754,7 @@ int hmcmt_run_chain(hmcmt_plan* pl, double dt, int32_t nsamples, double rhoref, 
     HMCMT_CUDA_TRY(cudaSetDevice(pl->device));
     const int nCh = pl->nChains, nAC = pl->nAC, nData = pl->nData;
     cudaStream_t st = pl->stream;
+    pl->sigmaDirect = false;
     DevBuf<double> dModel, dStats, dUacc;
     DevBuf<int> dAcc;
     DevBuf<cplx> dData;

@@ -759,7 +759,8 @@ k_contract(MeshDev M, SysMap sm, const double* __restrict__ freqs, const double*
 __global__ void k_reduce_grad(int nAC, int nCell, int nSysPerChain, const int* __restrict__ act2cell,
                               const double* __restrict__ Gpart, const double* __restrict__ m, const double* __restrict__ mref,
                               const int* __restrict__ wmPtr, const int* __restrict__ wmIdx, const double* __restrict__ wmVal,
-                              double beta, double* __restrict__ gdata, double* __restrict__ gtotal) {
+                              double beta, const double* __restrict__ sigma, double* __restrict__ gsig,
+                              double* __restrict__ gdata, double* __restrict__ gtotal) {
     int a = blockIdx.x * blockDim.x + threadIdx.x, ch = blockIdx.y;
     if (a >= nAC) return;
     const int c = act2cell[a];
@@ -768,7 +769,8 @@ __global__ void k_reduce_grad(int nAC, int nCell, int nSysPerChain, const int* _
     for (int s = 0; s < nSysPerChain; ++s) acc += G[(size_t)s * nCell + c];
     const double* mm = m + (size_t)ch * nAC;
     const double* mr = mref + (size_t)ch * nAC;
-    double gd = exp(mm[a]) * acc;
+    gsig[(size_t)ch * nAC + a] = acc;                               // real(J^T v) w.r.t. conductivity
+    double gd = sigma[(size_t)ch * nCell + c] * acc;                // dsigma' * dataGrad, sigma_a = exp(m_a)
     double pr = 0.0;
     for (int k = wmPtr[a]; k < wmPtr[a + 1]; ++k) { int j = wmIdx[k]; pr += wmVal[k] * (mm[j] - mr[j]); }
     gdata[(size_t)ch * nAC + a] = gd;

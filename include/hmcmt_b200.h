@@ -111,6 +111,9 @@ int64_t hmcmt_plan_info(const hmcmt_plan* plan, int what);
  * exTE / hxTM (optional, may be NULL): [nChains][nFreq][nNode] complex, node numbering of SURVEY.md A.2.
  * Keeps the factors alive on the device for hmcmt_jtvec (the reference's AinvTE/AinvTM). */
 int hmcmt_forward(hmcmt_plan* plan, const double* m, double* pred, double* exTE, double* hxTM);
+/* Same, but with the cell conductivities given directly (mtMesh.sigma, [nChains][ny*nz]) — the literal
+ * MT2DFwdSolver(mtMesh, mtData) call without the log-conductivity transform. */
+int hmcmt_forward_sigma(hmcmt_plan* plan, const double* sigma, double* pred, double* exTE, double* hxTM);
 
 /* compJacTMatVec(exTE,hxTM,datVec,...)  compJacTMatVec.jl:8-329 for the state left by the last
  * hmcmt_forward: v [nChains][nData] complex -> gsig [nChains][nAC] = real(J^T v) w.r.t. conductivity. */
