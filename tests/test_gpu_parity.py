@@ -1,0 +1,182 @@
+"""Parity of the CUDA hot path (through the C ABI) against the CPU oracle on the same inputs.
+
+Tolerances.  north_star: 1e-9 relative in complex FP64.  The reference's 1-D boundary solver
+(mt1DAnalyticField / mt1DFieldSensMatrix) propagates up/down-going amplitudes top-down, which amplifies
+rounding errors by exp(2 z/skin-depth): its own boundary values at depth change by up to ~1e-6 when an input
+is perturbed by ONE ulp (measured below with the oracle itself).  Quantities that inherit this noise (deep
+fields, the gradient on the deepest cell rows) are compared with tolerance max(1e-9, 20 x the oracle's own
+1-ulp self-sensitivity); everything else is held to 1e-9."""
+import copy
+
+import numpy as np
+import pytest
+
+from tests.helpers import load_example, tiny_problem, to_product
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def _oracle_grad(mesh, data, inv, prior, m):
+    from oracle import sampler as osamp
+    inv.strModel = m.copy()
+    return osamp.compDataGradient(mesh, data, inv, prior)
+
+
+def _self_sensitivity(mesh, data, inv, prior, m, g0, pred0):
+    """Oracle vs oracle with the frequencies moved by one ulp."""
+    d2 = copy.copy(data)
+    d2.freqs = np.nextafter(data.freqs, np.inf)
+    pred1, _, g1 = _oracle_grad(mesh, d2, inv, prior, m)
+    return np.abs(g1 - g0).max() / np.abs(g0).max(), (np.abs(pred1 - pred0) / np.abs(pred0)).max()
+
+
+def _gpu(mesh, data, inv, prior, m):
+    from hmcmt2d_b200 import api
+    pm, pd, pi, pp = to_product(mesh, data, inv, prior)
+    pi.strModel = m.copy()
+    pred, phi, g = api.compDataGradient(pm, pd, pi, pp)
+    return pred, phi, g, (pm, pd, pi, pp)
+
+
+def test_tiny_problem_full_parity():
+    mesh, data, inv, prior = tiny_problem()
+    m = inv.strModel.copy()
+    opred, ophi, og = _oracle_grad(mesh, data, inv, prior, m)
+    pred, phi, g, _ = _gpu(mesh, data, inv, prior, m)
+    assert (np.abs(pred - opred) / np.abs(opred)).max() < TOL
+    assert abs(phi - ophi) / abs(ophi) < TOL
+    assert np.abs(g - og).max() / np.abs(og).max() < TOL
+
+
+@pytest.mark.parametrize("name", ["dprism3d", "coprod2"])
+def test_example_parity(name):
+    """cfg1 (examples/dprism3d verbatim) and the cfg5 geometry (examples/coprod2), random log-normal model."""
+    mesh, data, inv, prior = load_example(name)
+    rng = np.random.default_rng(1)
+    m = np.log(0.01) + 0.7 * rng.standard_normal(len(inv.strModel))
+    opred, ophi, og = _oracle_grad(mesh, data, inv, prior, m)
+    sens_g, sens_p = _self_sensitivity(mesh, data, inv, prior, m, og, opred)
+    pred, phi, g, _ = _gpu(mesh, data, inv, prior, m)
+    assert (np.abs(pred - opred) / np.abs(opred)).max() < max(TOL, 20 * sens_p)
+    assert abs(phi - ophi) / abs(ophi) < max(TOL, 20 * sens_p)
+    err = np.abs(g - og) / np.abs(og).max()
+    assert err.max() < max(TOL, 20 * sens_g), (err.max(), sens_g)
+    # away from the noisy deep boundary (all but the 8 deepest cell rows) the gradient is held much tighter
+    ny = mesh.gridSize[0]
+    upper = np.arange(len(g)) < len(g) - 8 * ny
+    assert err[upper].max() < max(TOL, 2 * sens_g)
+
+
+def test_low_frequency_subset_hits_1e9():
+    """When the mesh is only a few skin depths deep the 1-D recursions are well conditioned and the whole
+    gradient meets 1e-9."""
+    mesh, data, inv, prior = load_example("dprism3d")
+    keep = data.freqID >= 9                        # 0.063, 0.025, 0.01 Hz
+    d2 = copy.copy(data)
+    d2.freqs = data.freqs[8:]
+    d2.freqID = data.freqID[keep] - 8
+    d2.rxID, d2.dtID = data.rxID[keep], data.dtID[keep]
+    d2.dataID = np.ones(int(keep.sum()), bool)
+    from oracle import sampler as osamp
+    inv2 = osamp.setupInverseDataModel(mesh, [1e-8], inv.obsData[keep], 1.0 / inv.dataW[keep])
+    rng = np.random.default_rng(2)
+    m = np.log(0.01) + 0.5 * rng.standard_normal(len(inv2.strModel))
+    opred, ophi, og = _oracle_grad(mesh, d2, inv2, prior, m)
+    pred, phi, g, _ = _gpu(mesh, d2, inv2, prior, m)
+    assert (np.abs(pred - opred) / np.abs(opred)).max() < TOL
+    assert abs(phi - ophi) / abs(ophi) < TOL
+    assert np.abs(g - og).max() / np.abs(og).max() < TOL
+
+
+def test_system_export_pattern_is_bit_exact():
+    """Sparsity pattern and DOF indexing must match bit-exactly (north_star)."""
+    from oracle import forward as ofwd
+    from oracle import operators as ops
+    mesh, data, inv, prior = load_example("coprod2")
+    m = inv.strModel + 0.3 * np.random.default_rng(4).standard_normal(len(inv.strModel))
+    pred, phi, g, (pm, pd, pi, pp) = _gpu(mesh, data, inv, prior, m)
+    from hmcmt2d_b200 import api
+    pl = api._plan_for(pm, pd, pi, pp)
+    mesh.sigma = inv.activeCell @ np.exp(m) + inv.bgModel
+    ny, nz = mesh.gridSize
+    ii, io = ops.getBoundaryIndex(ny, nz)
+    for mode in (0, 1):
+        coe = ofwd.assemble_mode(mesh, mode == 0, ii, io)
+        for f in (0, 7):
+            om = 2 * np.pi * data.freqs[f]
+            A = (coe.rAii + 1j * om * coe.iAii).tocsc()
+            A.sort_indices()
+            colptr, rowval, nzval, rhs, bc = pl.export_system(mode, f)
+            assert np.array_equal(colptr, A.indptr.astype(np.int64) + 1)          # 1-based CSC, as Julia hands it to MUMPS
+            assert np.array_equal(rowval, A.indices.astype(np.int64) + 1)
+            assert np.abs(nzval - A.data).max() / np.abs(A.data).max() < 1e-14
+            assert np.abs(np.imag(nzval[rowval - 1 != np.repeat(np.arange(len(colptr) - 1), np.diff(colptr))])).max() == 0
+
+
+def test_fields_and_jtvec_match_reference_interface():
+    """MT2DFwdSolver -> (predData, MT2DFwdData) and compJacTMatVec with the reference's argument list."""
+    from hmcmt2d_b200 import api
+    from oracle import forward as ofwd
+    from oracle import sensitivity as osens
+    mesh, data, inv, prior = tiny_problem(seed=8)
+    pm, pd, pi, pp = to_product(mesh, data, inv, prior)
+    pred, fwd = api.MT2DFwdSolver(pm, pd)
+    opred, ofw = ofwd.MT2DFwdSolver(mesh, data)
+    assert pred.shape == opred.shape and fwd.exTE.shape == ofw.exTE.shape == ((mesh.gridSize[0] + 1) * (mesh.gridSize[1] + 1), 3)
+    assert (np.abs(pred - opred) / np.abs(opred)).max() < TOL
+    assert np.abs(fwd.exTE - ofw.exTE).max() / np.abs(ofw.exTE).max() < TOL
+    assert np.abs(fwd.hxTM - ofw.hxTM).max() / np.abs(ofw.hxTM).max() < TOL
+    rng = np.random.default_rng(9)
+    v = rng.standard_normal(len(pred)) + 1j * rng.standard_normal(len(pred))
+    g = api.compJacTMatVec(fwd.exTE, fwd.hxTM, v, pm, pd, pi.activeCell, fwd.AinvTE, fwd.AinvTM)
+    og = osens.compJacTMatVec(ofw.exTE, ofw.hxTM, v, mesh, data, inv.activeCell, ofw.AinvTE, ofw.AinvTM)
+    assert np.abs(g - og).max() / np.abs(og).max() < TOL
+    # linearity in v (J^T is linear over the reals)
+    v2 = rng.standard_normal(len(pred)) + 1j * rng.standard_normal(len(pred))
+    g2 = api.compJacTMatVec(fwd.exTE, fwd.hxTM, v2, pm, pd, pi.activeCell, fwd.AinvTE, fwd.AinvTM)
+    g12 = api.compJacTMatVec(fwd.exTE, fwd.hxTM, 2.0 * v - 0.5 * v2, pm, pd, pi.activeCell, fwd.AinvTE, fwd.AinvTM)
+    assert np.abs(g12 - (2.0 * g - 0.5 * g2)).max() / np.abs(g).max() < 1e-12
+
+
+def test_ragged_data_and_single_mode():
+    """Missing data rows (dataID mask) and a TE-only survey."""
+    from oracle import sampler as osamp
+    mesh, data, inv, prior = tiny_problem(seed=5)
+    rng = np.random.default_rng(6)
+    keep = rng.random(len(inv.obsData)) > 0.3
+    keep[:2] = True
+    d2 = copy.copy(data)
+    d2.freqID, d2.rxID, d2.dtID = data.freqID[keep], data.rxID[keep], data.dtID[keep]
+    d2.dataID = keep.copy()
+    inv2 = osamp.setupInverseDataModel(mesh, [1e-8], inv.obsData[keep], 1.0 / inv.dataW[keep])
+    m = inv2.strModel.copy()
+    opred, ophi, og = _oracle_grad(mesh, d2, inv2, prior, m)
+    pred, phi, g, _ = _gpu(mesh, d2, inv2, prior, m)
+    assert pred.shape == opred.shape == (int(keep.sum()),)
+    assert (np.abs(pred - opred) / np.abs(opred)).max() < TOL and abs(phi - ophi) / ophi < TOL
+    assert np.abs(g - og).max() / np.abs(og).max() < TOL
+    te = data.dtID == 1
+    d3 = copy.copy(data)
+    d3.dataComp = ["ZXY"]
+    d3.compTM = False
+    d3.freqID, d3.rxID, d3.dtID = data.freqID[te], data.rxID[te], data.dtID[te]
+    d3.dataID = np.ones(int(te.sum()), bool)
+    inv3 = osamp.setupInverseDataModel(mesh, [1e-8], inv.obsData[te], 1.0 / inv.dataW[te])
+    opred, ophi, og = _oracle_grad(mesh, d3, inv3, prior, m)
+    pred, phi, g, _ = _gpu(mesh, d3, inv3, prior, m)
+    assert (np.abs(pred - opred) / np.abs(opred)).max() < TOL and np.abs(g - og).max() / np.abs(og).max() < TOL
+
+
+def test_batched_chains_equal_single_chains():
+    from hmcmt2d_b200 import api
+    mesh, data, inv, prior = tiny_problem(seed=12)
+    pm, pd, pi, pp = to_product(mesh, data, inv, prior)
+    rng = np.random.default_rng(13)
+    ms = pi.strModel[None, :] + 0.3 * rng.standard_normal((3, len(pi.strModel)))
+    pl3 = api.Plan(pm, pd, pi, pp, nChains=3)
+    pred3, phi3, g3 = pl3.forward_gradient(ms)
+    pl1 = api.Plan(pm, pd, pi, pp, nChains=1)
+    for c in range(3):
+        pred, phi, g = pl1.forward_gradient(ms[c])
+        assert np.array_equal(pred[0], pred3[c]) and phi[0] == phi3[c] and np.array_equal(g[0], g3[c])      # bit-identical
