@@ -106,6 +106,14 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
         : "d"(a), "d"(b));
 }
 
+// same, predicated on a warp-uniform flag: no branch, so independent MMAs can be scheduled across tiles
+__device__ __forceinline__ void dmma884_p(double (&c)[2], double a, double b, int pred) {
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %4, 0;\n\t"
+        "@q mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n\t}"
+        : "+d"(c[0]), "+d"(c[1])
+        : "d"(a), "d"(b), "r"(pred));
+}
+
 // ---- named barriers -------------------------------------------------------------------
 __device__ __forceinline__ void bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -126,6 +134,9 @@ __device__ __forceinline__ void fence_mbar_init() {
 }
 __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() {
+    asm volatile("fence.proxy.async;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)

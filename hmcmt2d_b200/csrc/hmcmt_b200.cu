@@ -60,7 +60,7 @@ struct hmcmt_plan {
     DevBuf<double> yLen, zLen, zNode, freqs, fdy1, fdy2, wL, wR, bg, wmVal, wd, m, p, mref, sigma, meanSig, planes;
     DevBuf<double> Gpart, phiPart, phi, gsig, gdata, gtotal, energies, panels, curM, curP, chainScal, zmom;
     DevBuf<int> fid, iL, iR, cell2act, act2cell, wmPtr, wmIdx, status, driftFlag, packed2full, Lsteps;
-    DevBuf<cplx> obs, bc, bcs, rhs, x, F, lam, Lam, srows, qrow, scratch, predFull, ainv, z, zadj, vin, predPacked;
+    DevBuf<cplx> obs, bc, bcs, rhs, x, F, lam, Lam, srows, qrow, scratch, predFull, ainvz, zadj, vin, predPacked;
     DevBuf<BandSys> sysDesc;
     DevBuf<SolveJob> jobs;
     // pinned staging for the host-buffer entry points
@@ -451,7 +451,7 @@ int hmcmt_plan_create(const hmcmt_problem* pr, hmcmt_plan** out) {
     ok(pl->chainScal.alloc(nCh * 4));
     ok(pl->predFull.alloc(nCh * pl->nFull)); ok(pl->vin.alloc(nCh * pl->nFull)); ok(pl->predPacked.alloc(nCh * pr->nData));
     ok(pl->panels.alloc(nSys * (size_t)pl->S * panel_doubles(pl->T)));
-    ok(pl->ainv.alloc(nSys * (size_t)pl->S * 64)); ok(pl->z.alloc(nSys * (size_t)pl->S * 8)); ok(pl->zadj.alloc(nSys * (size_t)pl->S * 8));
+    ok(pl->ainvz.alloc(nSys * (size_t)pl->S * AZ)); ok(pl->zadj.alloc(nSys * (size_t)pl->S * 8));
     ok(pl->status.alloc(nSys)); ok(pl->driftFlag.alloc(1)); ok(pl->Lsteps.alloc(nCh));
     ok(pl->sysDesc.alloc(nSys)); ok(pl->jobs.alloc(nSys));
     if (rc) { hmcmt_destroy(pl); return rc; }
@@ -476,12 +476,11 @@ int hmcmt_plan_create(const hmcmt_problem* pr, hmcmt_plan** out) {
         d.band = nullptr;
         d.rhs = pl->rhs.p + s * N;
         d.panels = pl->panels.p + s * (size_t)pl->S * panel_doubles(pl->T);
-        d.ainv = pl->ainv.p + s * (size_t)pl->S * 64;
-        d.z = pl->z.p + s * (size_t)pl->S * 8;
+        d.ainvz = pl->ainvz.p + s * (size_t)pl->S * AZ;
         d.x = pl->x.p + s * N;
         d.status = pl->status.p + s;
         SolveJob& j = jb[s];
-        j.panels = d.panels; j.ainv = d.ainv;
+        j.panels = d.panels; j.ainvz = d.ainvz;
         j.rhs = pl->lam.p + s * N; j.x = pl->lam.p + s * N;
         j.zbuf = pl->zadj.p + s * (size_t)pl->S * 8;
     }
@@ -514,7 +513,7 @@ void hmcmt_destroy(hmcmt_plan* pl) {
     pl->cell2act.release(); pl->act2cell.release(); pl->wmPtr.release(); pl->wmIdx.release(); pl->status.release();
     pl->driftFlag.release(); pl->packed2full.release(); pl->Lsteps.release(); pl->obs.release(); pl->bc.release(); pl->bcs.release();
     pl->rhs.release(); pl->x.release(); pl->F.release(); pl->lam.release(); pl->Lam.release(); pl->srows.release(); pl->qrow.release();
-    pl->scratch.release(); pl->predFull.release(); pl->ainv.release(); pl->z.release(); pl->zadj.release(); pl->vin.release();
+    pl->scratch.release(); pl->predFull.release(); pl->ainvz.release(); pl->zadj.release(); pl->vin.release();
     pl->predPacked.release(); pl->sysDesc.release(); pl->jobs.release();
     if (pl->pin) cudaFreeHost(pl->pin);
     delete pl;
@@ -532,7 +531,7 @@ int64_t hmcmt_plan_info(const hmcmt_plan* pl, int what) {
         case 6: return pl->S;
         case 7: return pl->nSysPerChain;
         case 8: return pl->M.zid;
-        case 9: return (int64_t)pl->S * (panel_doubles(pl->T) * 8 + 64 * 16 + 8 * 16);
+        case 9: return (int64_t)pl->S * (panel_doubles(pl->T) * 8 + AZ * 16);
         case 10: return pl->launches;
         default: return -1;
     }

@@ -27,7 +27,7 @@ struct Factor {
     int n = 0, b = 0, T = 0, S = 0;
     bool isReal = false;
     double* panels = nullptr;
-    cplx* ainv = nullptr;
+    cplx* ainvz = nullptr;
 };
 std::mutex g_mu;
 std::unordered_map<int64_t, Factor*> g_factors;
@@ -36,7 +36,7 @@ int64_t g_next = 1;
 void free_factor(Factor* f) {
     if (!f) return;
     if (f->panels) cudaFree(f->panels);
-    if (f->ainv) cudaFree(f->ainv);
+    if (f->ainvz) cudaFree(f->ainvz);
     delete f;
 }
 
@@ -83,7 +83,7 @@ int64_t factor_common(int64_t n, int64_t sym, const double* nzval, const int64_t
     auto cleanup = [&]() { if (dband) cudaFree(dband); if (dsys) cudaFree(dsys); if (dstatus) cudaFree(dstatus); };
     if (cudaMalloc(&dband, band.size() * sizeof(cplx)) != cudaSuccess ||
         cudaMalloc(&f->panels, (size_t)f->S * panel_doubles(T) * sizeof(double)) != cudaSuccess ||
-        cudaMalloc(&f->ainv, (size_t)f->S * 64 * sizeof(cplx)) != cudaSuccess || cudaMalloc(&dsys, sizeof(BandSys)) != cudaSuccess ||
+        cudaMalloc(&f->ainvz, (size_t)f->S * AZ * sizeof(cplx)) != cudaSuccess || cudaMalloc(&dsys, sizeof(BandSys)) != cudaSuccess ||
         cudaMalloc(&dstatus, sizeof(int)) != cudaSuccess) {
         cleanup(); free_factor(f);
         return fail(kErrAlloc);
@@ -91,7 +91,7 @@ int64_t factor_common(int64_t n, int64_t sym, const double* nzval, const int64_t
     cudaMemcpy(dband, band.data(), band.size() * sizeof(cplx), cudaMemcpyHostToDevice);
     cudaMemset(dstatus, 0, sizeof(int));
     BandSys s{};
-    s.band = dband; s.omega = 0.0; s.rhs = nullptr; s.panels = f->panels; s.ainv = f->ainv; s.z = nullptr; s.x = nullptr; s.status = dstatus;
+    s.band = dband; s.omega = 0.0; s.rhs = nullptr; s.panels = f->panels; s.ainvz = f->ainvz; s.x = nullptr; s.status = dstatus;
     cudaMemcpy(dsys, &s, sizeof(BandSys), cudaMemcpyHostToDevice);
     int rc = launch_factor(nullptr, T, dsys, 1, (int)n, (int)b, (int)b);
     int hst = 0;
@@ -129,7 +129,7 @@ int64_t solve_common(int64_t h, int64_t nrhs, const double* rhs, double* x, bool
     cudaMemcpy(dx, hb.data(), hb.size() * sizeof(cplx), cudaMemcpyHostToDevice);
     std::vector<SolveJob> jobs(nrhs);
     for (int64_t r = 0; r < nrhs; ++r) {
-        jobs[r].panels = f->panels; jobs[r].ainv = f->ainv;
+        jobs[r].panels = f->panels; jobs[r].ainvz = f->ainvz;
         jobs[r].rhs = dx + r * n; jobs[r].x = dx + r * n; jobs[r].zbuf = dz + (size_t)r * f->S * 8;
     }
     cudaMemcpy(djobs, jobs.data(), sizeof(SolveJob) * nrhs, cudaMemcpyHostToDevice);
@@ -218,7 +218,7 @@ int64_t hmcmt_debug_get_factor(int64_t handle, double* panels, double* ainv, int
     if (!f) return kErrArg;
     if (dims) { dims[0] = f->n; dims[1] = f->b; dims[2] = f->T; dims[3] = f->S; }
     if (panels) cudaMemcpy(panels, f->panels, (size_t)f->S * panel_doubles(f->T) * sizeof(double), cudaMemcpyDeviceToHost);
-    if (ainv) cudaMemcpy(ainv, f->ainv, (size_t)f->S * 64 * sizeof(cplx), cudaMemcpyDeviceToHost);
+    if (ainv) cudaMemcpy(ainv, f->ainvz, (size_t)f->S * AZ * sizeof(cplx), cudaMemcpyDeviceToHost);
     return kOk;
 }
 int64_t destroy_mumps_(const int64_t* handle) { return handle ? destroy_common(*handle) : kErrArg; }
