@@ -35,6 +35,7 @@ METRIC = "leapfrog_steps_per_sec"
 UNIT = "steps/s"
 WORKLOAD = dict(workload="cfg2: synthetic 200x100-cell mesh, 30 frequencies, TE+TM, 1 HMC chain per GPU",
                 ny=200, nz=100, nfreq=30, nrx=40, modes="TE+TM", chains_per_gpu=1)
+NCU_FACTOR_DRAM_BYTES = 2.264725e9 + 2.312753e9     # per launch, profiles/r01_factor_ncu.txt
 FP64_DMMA_PEAK_TFLOPS = 37.1     # measured on this pool's B200 with DMMA.8x8x4 (profiles/r01_fp64_peak_ubench.txt)
 
 
@@ -255,7 +256,9 @@ def run_gpu(args, rank, world, local_rank):
                     achieved=achieved, peak=FP64_DMMA_PEAK_TFLOPS, unit="TFLOP/s", frac=achieved / FP64_DMMA_PEAK_TFLOPS,
                     peak_source="measured FP64 DMMA m8n8k4 rate on this pool's B200 (profiles/r01_fp64_peak_ubench.txt); "
                                 "MEASURED_PEAKS.json holds only bf16/HBM peaks: " + peak_src,
-                    traffic=None, algorithmic_flops_per_launch=flops_launch, algorithmic_bytes_per_launch=bytes_launch,
+                    traffic=NCU_FACTOR_DRAM_BYTES, traffic_source="dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture "
+                                   "of this kernel at this workload (profiles/r01_factor_ncu.txt)",
+                    algorithmic_flops_per_launch=flops_launch, algorithmic_bytes_per_launch=bytes_launch,
                     hbm_achieved_gbs=bytes_launch / (fac_ms * 1e-3) / 1e9, hbm_peak_gbs=peaks.get("hbm_gbs"),
                     avg_launch_ms=fac_ms, launches_timed=factor_n, share_of_step=fac_ms / (ms / K))
 

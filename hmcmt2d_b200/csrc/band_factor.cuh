@@ -288,6 +288,23 @@ band_factor_kernel(const BandSys* __restrict__ systems, int N, int nf, int b) {
             }
             if (sys.rhs && warp == NW - 1 && lane >= 8 && lane < 16)      // recycle the rhs window slot p: global block s+T
                 sm.y[p * TS + lane - 8] = sm.ringRhs[s % kRing][lane - 8];
+            if (warp == T - 1) {
+                // this warp has no M' block: it streams the finished panel s and [A11^{-1} | z] to HBM (coalesced 16-byte stores)
+                const double2* src = reinterpret_cast<const double2*>(&sm.raw[buf][0][0][0][0]);
+                double2* dst = reinterpret_cast<double2*>(sys.panels + (size_t)s * panel_doubles(T));
+                constexpr int NQ = panel_doubles(T) / 2 / 32;      // 16-byte chunks per lane
+                constexpr int HQ = (NQ + 1) / 2;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    double2 tmp[HQ];
+#pragma unroll
+                    for (int qq = 0; qq < HQ; ++qq) if (h * HQ + qq < NQ) tmp[qq] = src[lane + 32 * (h * HQ + qq)];
+#pragma unroll
+                    for (int qq = 0; qq < HQ; ++qq) if (h * HQ + qq < NQ) dst[lane + 32 * (h * HQ + qq)] = tmp[qq];
+                }
+                cplx* dz = sys.ainvz + (size_t)s * AZ;
+                for (int qq = lane; qq < AZ; qq += 32) dz[qq] = sm.ainvz[buf][qq];
+            }
             bar_sync(BAR_M, NW * 32);
             // recycle the tile touching slot block p: its panel (raw(s)) is already published, and it now holds
             // entries of global block s+T, whose untouched stencil couplings may already reach the next pivot block.
@@ -340,29 +357,44 @@ band_factor_kernel(const BandSys* __restrict__ systems, int N, int nf, int b) {
         cplx a0, a1;                                        // A11^{-1}[i][j0], [i][j0+1] of the CURRENT panel
         bool bad = false;
         // in-register Gauss-Jordan inversion of an 8x8 complex block held as (row i, cols j0, j0+1)
+        // Fraction-free Gauss-Jordan (validated in numpy): rows i != k take  row_i <- (p row_i - a_ik row_k) 2^-e
+        // with an exact power-of-two rescale, so no reciprocal sits on the 8-pivot dependency chain; every row carries
+        // its accumulated scale q_i and the true inverse is  a_ij / q_i, formed with one reciprocal per row at the end.
         auto invert = [&]() {
+            cplx q = mk(1.0, 0.0);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const int srcRow = 4 * k + t, srcCol = 4 * i + (k >> 1), srcPiv = 4 * k + (k >> 1);
                 const cplx mine = (k & 1) ? a1 : a0;
-                cplx pk = mk(__shfl_sync(0xffffffffu, mine.x, srcPiv), __shfl_sync(0xffffffffu, mine.y, srcPiv));
-                cplx f = mk(__shfl_sync(0xffffffffu, mine.x, srcCol), __shfl_sync(0xffffffffu, mine.y, srcCol));
+                const cplx pk = mk(__shfl_sync(0xffffffffu, mine.x, srcPiv), __shfl_sync(0xffffffffu, mine.y, srcPiv));
+                const cplx f = mk(__shfl_sync(0xffffffffu, mine.x, srcCol), __shfl_sync(0xffffffffu, mine.y, srcCol));
+                const cplx ck = mk(__shfl_sync(0xffffffffu, q.x, 4 * k), __shfl_sync(0xffffffffu, q.y, 4 * k));
                 cplx r0 = mk(__shfl_sync(0xffffffffu, a0.x, srcRow), __shfl_sync(0xffffffffu, a0.y, srcRow));
                 cplx r1 = mk(__shfl_sync(0xffffffffu, a1.x, srcRow), __shfl_sync(0xffffffffu, a1.y, srcRow));
-                const double den = fma(pk.x, pk.x, pk.y * pk.y);
-                if (!(den > 0.0) || isinf(den)) bad = true;
-                const double iden = __drcp_rn(den);
-                const cplx rinv = mk(pk.x * iden, -pk.y * iden);
-                // row k: a <- r * rinv ; other rows: a <- a - (f rinv) r ; column k holds the multiplier itself
-                const bool rowk = (i == k);
-                const cplx g = f * rinv;
-                const cplx tm = rowk ? rinv : -g;
-                cplx n0 = rowk ? mk(0.0, 0.0) : a0, n1 = rowk ? mk(0.0, 0.0) : a1;
-                cfma(n0, tm, r0);
-                cfma(n1, tm, r1);
-                a0 = (j0 == k) ? tm : n0;
-                a1 = (j0 + 1 == k) ? tm : n1;
+                if (j0 == k) r0 = ck;                       // slot (k,k) switches to the right-hand block: value c_k
+                if (j0 + 1 == k) r1 = ck;
+                const double mag = fmax(fabs(pk.x), fabs(pk.y));
+                if (!(mag > 1e-290) || !(mag < 1e290)) bad = true;
+                const int eb = (__double2hiint(mag) >> 20) & 0x7ff;
+                const double sc = __hiloint2double((2046 - eb) << 20, 0);          // 2^-(exponent of the pivot), exact
+                const cplx ps = mk(pk.x * sc, pk.y * sc), fs = mk(f.x * sc, f.y * sc);
+                if (i == k) {
+                    a0 = r0; a1 = r1; q = pk;
+                } else {
+                    const cplx b0 = (j0 == k) ? mk(0.0, 0.0) : a0, b1 = (j0 + 1 == k) ? mk(0.0, 0.0) : a1;
+                    cplx n0 = ps * b0, n1 = ps * b1;
+                    cfma(n0, -fs, r0);
+                    cfma(n1, -fs, r1);
+                    a0 = n0; a1 = n1;
+                    q = ps * q;
+                }
             }
+            const double den = fma(q.x, q.x, q.y * q.y);
+            if (!(den > 0.0) || isinf(den)) bad = true;
+            const double iden = __drcp_rn(den);
+            const cplx qi = mk(q.x * iden, -q.y * iden);
+            a0 = a0 * qi;
+            a1 = a1 * qi;
         };
         auto publish = [&](int buf) {      // -A11^{-1} as B-fragments, plain A11^{-1} for the TMA store
             // B-fragment layout wants plane[kk][n][tt] = -Ainv[4kk+tt][n]; Ainv is symmetric, so write -Ainv[i][j] at [j>>2][i][j&3]
@@ -436,26 +468,13 @@ band_factor_kernel(const BandSys* __restrict__ systems, int N, int nf, int b) {
                 invert();
                 publish(buf ^ 1);
             }
-            // ---- off the critical chain: stream the panel image and [A11^{-1} | z] of panel s to HBM (coalesced 16-byte stores) ----
-            {
-                const double2* src = reinterpret_cast<const double2*>(&sm.raw[buf][0][0][0][0]);
-                double2* dst = reinterpret_cast<double2*>(sys.panels + (size_t)s * panel_doubles(T));
-                constexpr int NQ = panel_doubles(T) / 2 / 32;      // 16-byte chunks per lane (8T*8*2*... / 32 lanes)
-                double2 tmp[NQ];
-#pragma unroll
-                for (int q = 0; q < NQ; ++q) tmp[q] = src[lane + 32 * q];
-#pragma unroll
-                for (int q = 0; q < NQ; ++q) dst[lane + 32 * q] = tmp[q];
-                cplx* dz = sys.ainvz + (size_t)s * AZ;
-                for (int q = lane; q < AZ; q += 32) dz[q] = sm.ainvz[buf][q];
-            }
             // ring slot of step s+kPre: its previous content (step s+kPre-kRing) was consumed before BAR_M(s+kPre-kRing)
             sm.ringRow[(s + kPre) % kRing][lane >> 3][lane & 7] = rowv;
             if (lane < 8) sm.ringRhs[(s + kPre) % kRing][lane] = rhsv;
             if (s + 1 < S) bar_sync(BAR_RAW, NTHR);         // raw(s+1) complete (y_p(s+1) final as well)
         }
-        fence_proxy_async_all();                            // the panels are read back below through the async proxy (TMA)
     }
+    fence_proxy_async_all();                                // the panels are read back below through the async proxy (TMA)
     __threadfence();
     __syncthreads();
     if (!sys.rhs || sm.fail) return;

@@ -47,7 +47,8 @@ struct hmcmt_plan {
     MeshDev M{};
     SysMap sm{};
     RxDev rx{};
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, side = nullptr;      // side: 1-D sensitivity scalars overlap the factorisation
+    cudaEvent_t evFork = nullptr, evJoin = nullptr;
     cudaEvent_t evA = nullptr, evB = nullptr;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> factorEvents;
     size_t factorEventsUsed = 0;
@@ -267,10 +268,15 @@ int compute_step(hmcmt_plan* pl, bool wantAdjoint, const cplx* vin) {
     k_rhs<<<dim3((M.N + 255) / 256, nSys), 256, 0, st>>>(M, pl->sm, pl->sigma.p, pl->bc.p, pl->rhs.p);
     LAUNCH_CHECK(pl);
     if (wantAdjoint) {
-        k_row_mean<<<dim3(M.nz, nCh), 128, 0, st>>>(M.ny, M.nz, pl->sigma.p, pl->meanSig.p);
+        // the layered-earth sensitivity scalars depend on sigma only: run them on the side stream, on the SMs the
+        // 60-CTA factorisation leaves idle, and join before the contraction
+        HMCMT_CUDA_TRY(cudaEventRecord(pl->evFork, st));
+        HMCMT_CUDA_TRY(cudaStreamWaitEvent(pl->side, pl->evFork, 0));
+        k_row_mean<<<dim3(M.nz, nCh), 128, 0, pl->side>>>(M.ny, M.nz, pl->sigma.p, pl->meanSig.p);
         LAUNCH_CHECK(pl);
-        k_sens_scalars<<<(nSys * 3 + 63) / 64, 64, 0, st>>>(M, pl->sm, nSys, pl->freqs.p, pl->sigma.p, pl->meanSig.p, pl->scratch.p, pl->bcs.p);
+        k_sens_scalars<<<(nSys * 3 + 63) / 64, 64, 0, pl->side>>>(M, pl->sm, nSys, pl->freqs.p, pl->sigma.p, pl->meanSig.p, pl->scratch.p, pl->bcs.p);
         LAUNCH_CHECK(pl);
+        HMCMT_CUDA_TRY(cudaEventRecord(pl->evJoin, pl->side));
     }
     // factorisation + fused forward solve
     {
@@ -303,6 +309,7 @@ int compute_step(hmcmt_plan* pl, bool wantAdjoint, const cplx* vin) {
     ++pl->launches;
     k_node_field<<<dim3((M.nNode + 255) / 256, nSys), 256, 0, st>>>(M, pl->lam.p, nullptr, pl->Lam.p);
     LAUNCH_CHECK(pl);
+    HMCMT_CUDA_TRY(cudaStreamWaitEvent(st, pl->evJoin, 0));
     size_t cSmem = (size_t)(5 * M.nz + (M.ny - 1) + M.ny) * sizeof(cplx);
     k_contract<<<nSys, kConThreads, cSmem, st>>>(M, pl->sm, pl->freqs.p, pl->sigma.p, pl->F.p, pl->Lam.p, pl->srows.p, pl->qrow.p,
                                                  pl->bcs.p, pl->scratch.p, pl->Gpart.p);
@@ -490,6 +497,9 @@ int hmcmt_plan_create(const hmcmt_problem* pr, hmcmt_plan** out) {
         return kErrCuda;
     }
     if (cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&pl->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&pl->evFork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&pl->evJoin, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&pl->evA) != cudaSuccess || cudaEventCreate(&pl->evB) != cudaSuccess) {
         hmcmt_destroy(pl);
         return kErrCuda;
@@ -502,6 +512,9 @@ void hmcmt_destroy(hmcmt_plan* pl) {
     if (!pl) return;
     cudaSetDevice(pl->device);
     if (pl->stream) { cudaStreamSynchronize(pl->stream); cudaStreamDestroy(pl->stream); }
+    if (pl->side) { cudaStreamSynchronize(pl->side); cudaStreamDestroy(pl->side); }
+    if (pl->evFork) cudaEventDestroy(pl->evFork);
+    if (pl->evJoin) cudaEventDestroy(pl->evJoin);
     if (pl->evA) cudaEventDestroy(pl->evA);
     if (pl->evB) cudaEventDestroy(pl->evB);
     for (auto& e : pl->factorEvents) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
