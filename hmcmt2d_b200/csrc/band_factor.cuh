@@ -15,13 +15,21 @@
 //     mma.sync.m8n8k4.f64 (DMMA.8x8x4, measured full-rate 37.1 TF/s on B200); the next pivot
 //     column is updated first and published to shared memory;
 //   * the "factor warp" runs one panel AHEAD of them: it applies the current panel's update to the
-//     next 8x8 pivot block itself (16 DMMAs), inverts it in registers (Gauss-Jordan through warp
-//     shuffles, pivot-free), forms z = A11^{-1} y_p for the fused right-hand side and streams the
-//     finished panel to HBM with TMA bulk stores — the sequential pivot chain never stalls the tiles;
+//     next 8x8 pivot block itself (16 DMMAs), inverts it in registers (fraction-free Gauss-Jordan
+//     through warp shuffles, pivot-free) and forms z = A11^{-1} y_p for the fused right-hand side;
 //   * recycled slots are refilled from the 5-point stencil planes (assembly is fused: the matrix is
 //     never written to memory); those rows are prefetched into a shared-memory ring two steps ahead.
-// The stored factor is { raw_s (8T x 8), [A11_s^{-1} (8x8) | z_s (8)] } per macro-step; it serves the
-// forward solve (back-substitution fused below) and the adjoint solve (band_solve.cuh).
+//
+// Two CTAs per system (`split`): the mesh lines are cut at a separator line; CTA 0 eliminates the
+// lines before it, CTA 1 the lines after it in reverse order, both towards the separator (launch
+// FM_OWN, 2 CTAs per system).  Each exports its window — its share of the separator's Schur
+// complement — to global scratch; a second launch (FM_SEP, 1 CTA per system) sums the two images,
+// eliminates the separator and back-substitutes it; a third launch (FM_BACK, 2 CTAs per system)
+// back-substitutes the two halves.  Stream order is the only synchronisation between the CTAs of a
+// system.  This halves the sequential pivot chain and doubles the SMs a single chain can use.
+//
+// The stored factor is { raw_s (8T x 8), [A11_s^{-1} (8x8) | z_s (8)] } per macro-step and rank; it
+// serves the forward solve (back-substitution fused below) and the adjoint solve (band_solve.cuh).
 #pragma once
 #include <type_traits>
 
@@ -32,10 +40,10 @@ namespace hmcmt {
 constexpr int TS = 8;         // tile size == DMMA m,n
 constexpr int AZ = 72;        // complex entries per macro-step in the ainv stream: A11^{-1} (64) + z (8)
 
-// Per-system description for a batched launch (one CTA per system).
+// Per-system description for a batched launch (one CTA, or two CTAs, per system).
 struct BandSys {
-    // stencil provider (internal ordering, see mt_kernels.cuh): A[g][g] = dr[g] + i*omega*dm[g],
-    // A[g][g-1] = e1[g] (0 at line starts), A[g][g-nf] = e2[g] (0 on the first line)
+    // stencil provider (internal ordering q = line*nf + f, see mt_kernels.cuh): A[q][q] = dr[q] + i*omega*dm[q],
+    // A[q][q-1] = e1[q] (0 at line starts), A[q][q-nf] = e2[q] (0 on the first line)
     const double* dr;
     const double* dm;
     const double* e1;
@@ -44,10 +52,62 @@ struct BandSys {
     // dense lower-band provider (generic matrices through the MUMPS-shim ABI): band[g*(b+1)+d] = A[g][g-d]
     const cplx* band;
     const cplx* rhs;     // fused forward right-hand side (internal ordering, length N) or nullptr
-    double* panels;      // [S][16*R] doubles: re/im x kk x R x 4 (exactly the smem operand layout)
-    cplx* ainvz;         // [S][72]: A11^{-1} row-major, then z = A11^{-1} * (forward-eliminated rhs block)
     cplx* x;             // [N] solution of the fused system — only if rhs != nullptr
+    double* panels[2];   // per half (rank): [steps][16*R] doubles: re/im x kk x R x 4 (exactly the smem operand layout)
+    cplx* ainvz[2];      // per half (rank): [steps][72]: A11^{-1} row-major, then z = A11^{-1} * (forward-eliminated rhs block)
+    cplx* wexp;          // split only: hand-over scratch [2][R*R] window images, [2][R] rhs windows, [R] separator solution
     int* status;         // 0 ok, -10 zero/NaN pivot block
+};
+
+// Geometry of the elimination order (uniform over the batch).
+struct BandDom {
+    int N;        // unknowns of the full system
+    int nf;       // line length == half-bandwidth of the stencil systems
+    int b;        // half-bandwidth
+    int nl;       // number of lines (stencil systems); unused for the band provider
+    int split;    // 1: two CTAs per system (FM_OWN / FM_SEP / FM_BACK launches)
+    int lineSep;  // separator line (split only)
+};
+
+// Local ordering of one half (rank): [head padding | own lines | separator line | tail padding]; the padding makes
+// the separator start on a tile boundary so that both ranks' windows can be merged tile by tile.
+struct LocalDom {
+    int rank, split, nf, nl, lineSep, N;
+    int pad, nOwn, lineStart, lineStep, sOwn, sTot, nLoc;
+    __host__ __device__ static LocalDom make(const BandDom& d, int rank) {
+        LocalDom L;
+        L.rank = rank; L.split = d.split; L.nf = d.nf; L.nl = d.nl; L.lineSep = d.lineSep; L.N = d.N;
+        if (!d.split) {
+            L.pad = 0; L.nOwn = d.N; L.lineStart = 0; L.lineStep = 1; L.nLoc = d.N;
+            L.sOwn = L.sTot = (d.N + TS - 1) / TS;
+        } else {
+            int lines = rank == 0 ? d.lineSep : d.nl - 1 - d.lineSep;
+            L.nOwn = lines * d.nf;
+            L.lineStart = rank == 0 ? 0 : d.nl - 1;
+            L.lineStep = rank == 0 ? 1 : -1;
+            L.pad = (TS - L.nOwn % TS) % TS;
+            L.nLoc = L.pad + L.nOwn + d.nf;
+            L.sOwn = (L.pad + L.nOwn) / TS;
+            L.sTot = rank == 0 ? (L.nLoc + TS - 1) / TS : L.sOwn;
+        }
+        return L;
+    }
+    // local row -> global internal index; -1 head padding, -2 tail padding.  kind: 0 own row, 1 separator row.
+    __host__ __device__ int map(int g, int& kind, int& lrel) const {
+        kind = 0; lrel = 0;
+        if (!split) return g < N ? g : -2;
+        if (g < pad) return -1;
+        int u = g - pad;
+        if (u >= nOwn) {
+            u -= nOwn;
+            if (u >= nf) return -2;
+            kind = 1;
+            return lineSep * nf + u;
+        }
+        lrel = u / nf;
+        int f = u - lrel * nf;
+        return (lineStart + lineStep * lrel) * nf + f;
+    }
 };
 
 __host__ __device__ constexpr int band_T_for(int b) { return (b + 7) / 8 + 1; }
@@ -78,7 +138,7 @@ struct FactorSmem {
     double nainv[2][2][2][8][4];   // -A11^{-1} in B-fragment layout [buf][re/im][kk][n][t]
     double mscr[2][2][8][4];       // factor warp: M' of the next pivot block (A-fragment layout)
     double dnext[2][2][8][8];      // [buf][re/im][row][col]: next-next pivot block, updated through the current panel
-    cplx ainvz[2][AZ];             // plain A11^{-1} (row-major) + z, staged for the TMA store
+    cplx ainvz[2][AZ];             // plain A11^{-1} (row-major) + z, staged for the store
     cplx y[R];                     // circular window of the forward-eliminated rhs / back-substituted x
     double ringRow[kRing][4][8];   // stencil planes (dr, dm, e1, e2) of the rows entering the window
     cplx ringRhs[kRing][8];
@@ -92,50 +152,101 @@ struct FactorSmem {
 };
 
 enum { BAR_RAW = 1, BAR_INV = 2, BAR_M = 3 };
+// what one launch does: the whole system / own lines of both halves / separator (+ its back-substitution) / back-substitution of the halves
+enum FactorMode { FM_FULL = 0, FM_OWN = 1, FM_SEP = 2, FM_BACK = 3 };
+__host__ __device__ constexpr size_t split_scratch_entries(int R) { return 2 * (size_t)R * R + 3 * (size_t)R; }
 
+// Matrix entries in the LOCAL ordering of a half (rank).
 struct EntryProvider {
     const double *dr, *dm, *e1, *e2;
     const cplx* band;
     double omega;
-    int N, nf, b;
-    // direct (global-memory) evaluation, hi >= lo
+    int b;
+    LocalDom L;
+    // one stencil plane (0 dr, 1 dm, 2 e1, 3 e2) of local row g
+    __device__ __forceinline__ double plane(int g, int pl) const {
+        int kind, lrel;
+        const int q = L.map(g, kind, lrel);
+        if (q == -1) return pl == 0 ? 1.0 : 0.0;                              // head padding: identity rows
+        if (q == -2) return (pl == 0 && L.rank == 0) ? 1.0 : 0.0;             // tail padding: identity, counted once
+        if (kind == 1 && L.rank == 1) return pl == 3 ? e2[q + L.nf] : 0.0;    // separator seen from behind: coupling only
+        if (pl == 0) return dr[q];
+        if (pl == 1) return dm[q];
+        if (pl == 2) return e1[q];
+        if (L.lineStep > 0 || kind == 1) return e2[q];
+        return lrel > 0 ? e2[q + L.nf] : 0.0;                                 // reversed lines: the previous local line is line+1
+    }
+    // direct (global-memory) evaluation, local indices hi >= lo
     __device__ __forceinline__ cplx get(int hi, int lo) const {
-        int d = hi - lo;
-        if (hi >= N) return mk(d == 0 ? 1.0 : 0.0, 0.0);      // identity padding past the end
-        if (band) return d <= b ? band[(size_t)hi * (b + 1) + d] : mk(0.0, 0.0);
-        if (d == 0) return mk(dr[hi], omega * dm[hi]);
-        if (d == 1) return mk(e1[hi], 0.0);
-        if (d == nf) return mk(e2[hi], 0.0);
+        const int d = hi - lo;
+        if (band) {
+            if (hi >= L.N) return mk(d == 0 ? 1.0 : 0.0, 0.0);               // identity padding past the end
+            return d <= b ? band[(size_t)hi * (b + 1) + d] : mk(0.0, 0.0);
+        }
+        if (d == 0) return mk(plane(hi, 0), omega * plane(hi, 1));
+        if (d == 1) return mk(plane(hi, 2), 0.0);
+        if (d == L.nf) return mk(plane(hi, 3), 0.0);
         return mk(0.0, 0.0);
     }
     // rows of one 8-row block staged in shared memory: row[plane][hi & 7]
     __device__ __forceinline__ cplx get_staged(const double (*row)[8], int hi, int lo) const {
-        int d = hi - lo, r = hi & 7;
+        const int d = hi - lo, r = hi & 7;
         if (d == 0) return mk(row[0][r], omega * row[1][r]);
         if (d == 1) return mk(row[2][r], 0.0);
-        if (d == nf) return mk(row[3][r], 0.0);
+        if (d == L.nf) return mk(row[3][r], 0.0);
         return mk(0.0, 0.0);
+    }
+    __device__ __forceinline__ cplx rhs_at(const cplx* rhs, int g) const {
+        int kind, lrel;
+        const int q = L.map(g, kind, lrel);
+        if (q < 0 || (kind == 1 && L.rank == 1)) return mk(0.0, 0.0);
+        return rhs[q];
+    }
+    __device__ __forceinline__ void x_store(cplx* x, int g, cplx v) const {
+        int kind, lrel;
+        const int q = L.map(g, kind, lrel);
+        if (q >= 0 && !(kind == 1 && L.rank == 1)) x[q] = v;
     }
 };
 
-// One CTA per system.  grid = nsys, block = FactorCfg<T>::NTHREADS, dynamic smem = sizeof(FactorSmem<T>)
+// grid = nsys CTAs (FM_FULL, FM_SEP) or 2*nsys CTAs (FM_OWN, FM_BACK: CTA = 2*system + rank), block = FactorCfg<T>::NTHREADS,
+// dynamic smem = sizeof(FactorSmem<T>)
 template <int T>
 __global__ void __launch_bounds__(FactorCfg<T>::NTHREADS, 1)
-band_factor_kernel(const BandSys* __restrict__ systems, int N, int nf, int b) {
+band_factor_kernel(const BandSys* __restrict__ systems, BandDom dom, int mode) {
     using Cfg = FactorCfg<T>;
-    constexpr int NT = Cfg::NT, NW = Cfg::NW, TPW = Cfg::TPW, R = Cfg::R, NTHR = Cfg::NTHREADS;
+    constexpr int NW = Cfg::NW, TPW = Cfg::TPW, R = Cfg::R, NTHR = Cfg::NTHREADS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FactorSmem<T>& sm = *reinterpret_cast<FactorSmem<T>*>(smem_raw);
 
-    const BandSys sys = systems[blockIdx.x];
-    const int S = (N + TS - 1) / TS;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool paired = (mode == FM_OWN || mode == FM_BACK);
+    const int rank = paired ? (int)(blockIdx.x & 1) : 0;
+    const BandSys sys = systems[paired ? (blockIdx.x >> 1) : blockIdx.x];
+    const LocalDom L = LocalDom::make(dom, rank);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // tells the compiler the role branches are warp-uniform
     const int g = lane >> 2, t = lane & 3;
-    EntryProvider prov{sys.dr, sys.dm, sys.e1, sys.e2, sys.band, sys.omega, N, nf, b};
+    const int nf = dom.nf;
+    EntryProvider prov{sys.dr, sys.dm, sys.e1, sys.e2, sys.band, sys.omega, dom.b, L};
     const bool staged = (sys.band == nullptr);      // stencil rows come through the smem ring
+    double* const panels = sys.panels[rank];
+    cplx* const ainvz = sys.ainvz[rank];
+    const int nLoc = L.nLoc;
+    // macro-steps [sBeg, sEnd) of this launch (local numbering of this rank)
+    const int sBeg = (mode == FM_SEP) ? L.sOwn : 0;
+    const int sEnd = (mode == FM_FULL || mode == FM_SEP) ? L.sTot : (mode == FM_OWN ? L.sOwn : 0);
+    // hand-over scratch of a split system; window images / rhs windows are indexed relative to the separator start
+    cplx* const wimg0 = sys.wexp;
+    cplx* const wimg1 = sys.wexp + (size_t)R * R;
+    cplx* const yimg0 = sys.wexp + 2 * (size_t)R * R;
+    cplx* const yimg1 = yimg0 + R;
+    cplx* const xsep = yimg0 + 2 * R;
+    // window slot block -> position relative to local block `base`
+    auto rel = [&](int slot, int base) { int a = slot - base % T; return a < 0 ? a + T : a; };
 
+  if (mode != FM_BACK) {
     // tile tables: warp w owns the unordered slot pairs {X,Y}, X <= Y, with (X+Y) mod NW == w
-    for (int w = tid; w < NW; w += NTHR) {
+    for (int w_b = 0; w_b < NW; w_b += NTHR) if (const int w = w_b + tid; w < NW) {
         int cnt = 0;
         for (int bb = 0; bb < T; ++bb) sm.li[w][bb] = -1;
         for (int X = 0; X < T; ++X) {
@@ -148,31 +259,26 @@ band_factor_kernel(const BandSys* __restrict__ systems, int N, int nf, int b) {
             ++cnt;
         }
     }
-    for (int i = tid; i < R; i += NTHR) {
+    // rhs window: slot block X holds local block sBeg + rel(X)
+    for (int i_b = 0; i_b < R; i_b += NTHR) if (const int i = i_b + tid; i < R) {
         cplx v = mk(0.0, 0.0);
-        if (sys.rhs && i < N) v = sys.rhs[i];
+        if (sys.rhs) {
+            if (mode == FM_SEP) {
+                const int a = rel(i >> 3, sBeg) * TS + (i & 7);
+                v = yimg0[a] + yimg1[a];
+            } else if (i < nLoc) v = prov.rhs_at(sys.rhs, i);
+        }
         sm.y[i] = v;
     }
-    // prefetch ring: entry q holds the rows of global block (T + q) for q < kPre (consumed at steps 0..kPre-1)
-    auto ring_fetch = [&](int beta, int l, double& rowv, cplx& rhsv) {     // one warp, lane l
-        int gr = beta * TS + (l & 7), pl = l >> 3;
-        rowv = 0.0;
-        if (gr < N) {
-            if (staged) rowv = (pl == 0) ? sys.dr[gr] : (pl == 1) ? sys.dm[gr] : (pl == 2) ? sys.e1[gr] : sys.e2[gr];
-        } else if (pl == 0) rowv = 1.0;
-        rhsv = mk(0.0, 0.0);
-        if (sys.rhs && l < 8 && gr < N) rhsv = sys.rhs[gr];
-    };
-    if (warp == 0) {
+    if (warp == 0) {        // ring entries of steps sBeg..sBeg+kPre-1: blocks sBeg+T .. sBeg+T+kPre-1
         for (int q = 0; q < kPre; ++q) {
-            double rv; cplx hv;
-            ring_fetch(T + q, lane, rv, hv);
-            sm.ringRow[q % kRing][lane >> 3][lane & 7] = rv;
-            if (lane < 8) sm.ringRhs[q % kRing][lane] = hv;
+            const int gr = (sBeg + T + q) * TS + (lane & 7);
+            sm.ringRow[(sBeg + q) % kRing][lane >> 3][lane & 7] = staged ? prov.plane(gr, lane >> 3) : 0.0;
+            if (lane < 8) sm.ringRhs[(sBeg + q) % kRing][lane] = (sys.rhs && gr < nLoc) ? prov.rhs_at(sys.rhs, gr) : mk(0.0, 0.0);
         }
     }
     if (tid == 0) sm.fail = 0;
-    __syncthreads();
+    cta_sync();
 
     if (warp < NW) {
         // =============================== tile warps ===============================
@@ -180,16 +286,23 @@ band_factor_kernel(const BandSys* __restrict__ systems, int N, int nf, int b) {
         int tI[TPW], tJ[TPW];
 #pragma unroll
         for (int i = 0; i < TPW; ++i) {
-            const bool valid = true;
             tI[i] = sm.tI[warp * TPW + i];
             tJ[i] = sm.tJ[warp * TPW + i];
-            // initial window: slot block X holds global block X
-            cre[i][0] = cre[i][1] = cim[i][0] = cim[i][1] = 0.0;
-            if (valid) {
-                int gi = tI[i] * TS + g;
+            if (mode == FM_SEP) {
+                // window = sum of the two Schur-complement images exported by the FM_OWN launch
+                const int row = rel(tI[i], sBeg) * TS + g, col = rel(tJ[i], sBeg) * TS + 2 * t;
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    int gj = tJ[i] * TS + 2 * t + e;
+                    const cplx v = wimg0[(size_t)row * R + col + e] + wimg1[(size_t)row * R + col + e];
+                    cre[i][e] = v.x;
+                    cim[i][e] = v.y;
+                }
+            } else {
+                // initial window: slot block X holds local block X
+                const int gi = tI[i] * TS + g;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int gj = tJ[i] * TS + 2 * t + e;
                     cplx v = prov.get(max(gi, gj), min(gi, gj));
                     cre[i][e] = v.x;
                     cim[i][e] = v.y;
@@ -215,8 +328,7 @@ band_factor_kernel(const BandSys* __restrict__ systems, int N, int nf, int b) {
             *reinterpret_cast<double2*>(&sm.dnext[nb][0][g][2 * t]) = make_double2(cre[i][0], cre[i][1]);
             *reinterpret_cast<double2*>(&sm.dnext[nb][1][g][2 * t]) = make_double2(cim[i][0], cim[i][1]);
         };
-        // DMMA latency on B200 is ~138 cycles (tools/ubench): dependent accumulation chains are kept short
-        // (4 independent 2-link chains per tile here) and, in pass 2, interleaved across tiles.
+        // DMMA latency on B200 is ~138 cycles (tools/ubench): 4 independent 2-link accumulation chains per tile
         auto update = [&](int i, int buf) {
             const int ra = tI[i] * TS + g, rb = tJ[i] * TS + g;
             double t1[2] = {0.0, 0.0}, t2[2] = {0.0, 0.0};
@@ -236,14 +348,6 @@ band_factor_kernel(const BandSys* __restrict__ systems, int N, int nf, int b) {
             cre[i][0] += t1[0]; cre[i][1] += t1[1];
             cim[i][0] += t2[0]; cim[i][1] += t2[1];
         };
-        // prologue: publish panel 0 (tiles touching block 0) and the pivot block of panel 1
-#pragma unroll
-        for (int i = 0; i < TPW; ++i) {
-            if (tI[i] == 0) dump(i, 0, 0);      // tI==0 covers every tile touching block 0 (I<=J)
-            if (T > 1 && tI[i] == 1 && tJ[i] == 1) dump_diag(i, 1);
-        }
-        bar_arrive(BAR_RAW, NTHR);
-
         // fused forward elimination of the rhs for block X: y_X -= raw_X z   (z = A11^{-1} y_p from the factor warp)
         auto y_update = [&](int X, int buf) {
             if (lane < 8) {
@@ -257,98 +361,131 @@ band_factor_kernel(const BandSys* __restrict__ systems, int N, int nf, int b) {
                 sm.y[ry] = acc;
             }
         };
-        for (int s = 0; s < S; ++s) {
-            const int p = s % T, p1 = (s + 1) % T, p2 = (s + 2) % T, buf = s & 1;
-            // roles of this warp's tiles in this step (at most one tile per pivot column)
-            const int ip = sm.li[warp][p], ip1 = sm.li[warp][p1];
-            int idg = -1;                                   // the pivot block of panel s+2, if this warp owns it
-            if (s + 1 < S) { int c = sm.li[warp][p2]; if (c >= 0 && 2 * p2 == ((2 * p2 >= NW) ? warp + NW : warp)) idg = c; }
-            bar_sync(BAR_INV, NTHR);                       // raw(s) complete, -A11^{-1}(s) and z(s) published
-            if (sm.fail) break;
-            // M'_X = raw_X * (-A11^{-1}) for slot block X != p (one block per warp)
-            int myX = -1;
-            if (warp < T - 1) {
-                int X = p + 1 + warp; if (X >= T) X -= T;
-                myX = X;
-                double mre[2] = {0.0, 0.0}, mim[2] = {0.0, 0.0}, mr2[2] = {0.0, 0.0}, mi2[2] = {0.0, 0.0};
-                const int r = X * TS + g;
-#pragma unroll
-                for (int kk = 0; kk < 2; ++kk) {
-                    double are = sm.raw[buf][0][kk][r][t], aim = sm.raw[buf][1][kk][r][t];
-                    double bre = sm.nainv[buf][0][kk][g][t], bim = sm.nainv[buf][1][kk][g][t];
-                    dmma884(mre, are, bre);
-                    dmma884(mim, are, bim);
-                    dmma884(mr2, -aim, bim);
-                    dmma884(mi2, aim, bre);
-                }
-                mre[0] += mr2[0]; mre[1] += mr2[1]; mim[0] += mi2[0]; mim[1] += mi2[1];
-                *reinterpret_cast<double2*>(&sm.m[buf][0][t >> 1][r][(t & 1) * 2]) = make_double2(mre[0], mre[1]);
-                *reinterpret_cast<double2*>(&sm.m[buf][1][t >> 1][r][(t & 1) * 2]) = make_double2(mim[0], mim[1]);
-                if (sys.rhs && warp == 0) y_update(X, buf);     // X == p1: the factor warp needs y_{p1} for z(s+1)
-            }
-            if (sys.rhs && warp == NW - 1 && lane >= 8 && lane < 16)      // recycle the rhs window slot p: global block s+T
-                sm.y[p * TS + lane - 8] = sm.ringRhs[s % kRing][lane - 8];
-            if (warp == T - 1) {
-                // this warp has no M' block: it streams the finished panel s and [A11^{-1} | z] to HBM (coalesced 16-byte stores)
-                const double2* src = reinterpret_cast<const double2*>(&sm.raw[buf][0][0][0][0]);
-                double2* dst = reinterpret_cast<double2*>(sys.panels + (size_t)s * panel_doubles(T));
-                constexpr int NQ = panel_doubles(T) / 2 / 32;      // 16-byte chunks per lane
-                constexpr int HQ = (NQ + 1) / 2;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    double2 tmp[HQ];
-#pragma unroll
-                    for (int qq = 0; qq < HQ; ++qq) if (h * HQ + qq < NQ) tmp[qq] = src[lane + 32 * (h * HQ + qq)];
-#pragma unroll
-                    for (int qq = 0; qq < HQ; ++qq) if (h * HQ + qq < NQ) dst[lane + 32 * (h * HQ + qq)] = tmp[qq];
-                }
-                cplx* dz = sys.ainvz + (size_t)s * AZ;
-                for (int qq = lane; qq < AZ; qq += 32) dz[qq] = sm.ainvz[buf][qq];
-            }
-            bar_sync(BAR_M, NW * 32);
-            // recycle the tile touching slot block p: its panel (raw(s)) is already published, and it now holds
-            // entries of global block s+T, whose untouched stencil couplings may already reach the next pivot block.
-#pragma unroll
-            for (int i = 0; i < TPW; ++i) {
-                if (i != ip) continue;
-                int dI = tI[i] - p1; if (dI < 0) dI += T;      // position inside the window [s+1, s+T]
-                int dJ = tJ[i] - p1; if (dJ < 0) dJ += T;
-                // row/column distance between the entering block (position T-1) and the other block of the tile
-                const int delta = TS * (T - 1 - min(dI, dJ));
-                const bool cand = !staged || delta <= TS || (delta + 7 >= nf && delta - 7 <= nf);   // warp-uniform
-                cre[i][0] = cre[i][1] = cim[i][0] = cim[i][1] = 0.0;
-                if (cand) {
-                    int gi = (s + 1 + dI) * TS + g;
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        int gj = (s + 1 + dJ) * TS + 2 * t + e;
-                        int hi = max(gi, gj), lo = min(gi, gj);    // hi always lies in the entering block s+T
-                        cplx v = staged ? prov.get_staged(sm.ringRow[s % kRing], hi, lo) : prov.get(hi, lo);
-                        cre[i][e] = v.x;
-                        cim[i][e] = v.y;
-                    }
-                }
-            }
-            // pass 1: the tile of the next pivot column (and the pivot block after it) first, then publish
-            if (s + 1 < S) {
+
+        {
+            const int s0 = sBeg, s1 = sEnd;
+            // prologue: publish panel s0 (tiles touching its slot) and the pivot block of panel s0+1
+            {
+                const int q0 = s0 % T, q1 = (s0 + 1) % T;
+                const int i0 = sm.li[warp][q0];
 #pragma unroll
                 for (int i = 0; i < TPW; ++i) {
-                    if (i == ip1) {
-                        if (i != ip) update(i, buf);            // the recycled {p,p1} tile is fresh: no update
-                        dump(i, p1, buf ^ 1);
-                    } else if (i == idg) {
-                        if (i != ip) update(i, buf);            // (T == 2: p2 == p, already recycled)
-                        dump_diag(i, buf);                      // pivot block of panel s+2, updated through panel s
-                    }
+                    if (i == i0) dump(i, q0, s0 & 1);
+                    if (tI[i] == q1 && tJ[i] == q1) dump_diag(i, (s0 + 1) & 1);
                 }
                 bar_arrive(BAR_RAW, NTHR);
             }
-            if (sys.rhs && myX >= 0 && warp != 0) y_update(myX, buf);
-            // pass 2: the rest of the trailing window
+            for (int s = s0; s < s1; ++s) {
+                const int p = s % T, p1 = (s + 1) % T, p2 = (s + 2) % T, buf = s & 1;
+                // roles of this warp's tiles in this step (at most one tile per pivot column)
+                const int ip = sm.li[warp][p];
+                int ip1 = -1, idg = -1;                         // look-ahead tile / pivot block of panel s+2 (if owned)
+                if (s + 1 < s1) {
+                    ip1 = sm.li[warp][p1];
+                    int c = sm.li[warp][p2];
+                    if (c >= 0 && 2 * p2 == ((2 * p2 >= NW) ? warp + NW : warp)) idg = c;
+                }
+                bar_sync(BAR_INV, NTHR);                       // raw(s) complete, -A11^{-1}(s) and z(s) published
+                if (__any_sync(0xffffffffu, sm.fail != 0)) break;
+                // M'_X = raw_X * (-A11^{-1}) for slot block X != p (one block per warp)
+                int myX = -1;
+                if (warp < T - 1) {
+                    int X = p + 1 + warp; if (X >= T) X -= T;
+                    myX = X;
+                    double mre[2] = {0.0, 0.0}, mim[2] = {0.0, 0.0}, mr2[2] = {0.0, 0.0}, mi2[2] = {0.0, 0.0};
+                    const int r = X * TS + g;
 #pragma unroll
-            for (int i = 0; i < TPW; ++i) {
-                if (i == ip || i == ip1 || i == idg) continue;
-                update(i, buf);
+                    for (int kk = 0; kk < 2; ++kk) {
+                        double are = sm.raw[buf][0][kk][r][t], aim = sm.raw[buf][1][kk][r][t];
+                        double bre = sm.nainv[buf][0][kk][g][t], bim = sm.nainv[buf][1][kk][g][t];
+                        dmma884(mre, are, bre);
+                        dmma884(mim, are, bim);
+                        dmma884(mr2, -aim, bim);
+                        dmma884(mi2, aim, bre);
+                    }
+                    mre[0] += mr2[0]; mre[1] += mr2[1]; mim[0] += mi2[0]; mim[1] += mi2[1];
+                    *reinterpret_cast<double2*>(&sm.m[buf][0][t >> 1][r][(t & 1) * 2]) = make_double2(mre[0], mre[1]);
+                    *reinterpret_cast<double2*>(&sm.m[buf][1][t >> 1][r][(t & 1) * 2]) = make_double2(mim[0], mim[1]);
+                    if (sys.rhs && warp == 0) y_update(X, buf);     // X == p1: the factor warp needs y_{p1} for z(s+1)
+                }
+                if (sys.rhs && warp == NW - 1 && lane >= 8 && lane < 16)      // recycle the rhs window slot p: local block s+T
+                    sm.y[p * TS + lane - 8] = sm.ringRhs[s % kRing][lane - 8];
+                if (warp == T - 1) {
+                    // this warp has no M' block: it streams the finished panel s and [A11^{-1} | z] to HBM (coalesced 16-byte stores)
+                    const double2* src = reinterpret_cast<const double2*>(&sm.raw[buf][0][0][0][0]);
+                    double2* dst = reinterpret_cast<double2*>(panels + (size_t)s * panel_doubles(T));
+                    constexpr int NQ = panel_doubles(T) / 2 / 32;      // 16-byte chunks per lane
+                    constexpr int HQ = (NQ + 1) / 2;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        double2 tmp[HQ];
+#pragma unroll
+                        for (int qq = 0; qq < HQ; ++qq) if (h * HQ + qq < NQ) tmp[qq] = src[lane + 32 * (h * HQ + qq)];
+#pragma unroll
+                        for (int qq = 0; qq < HQ; ++qq) if (h * HQ + qq < NQ) dst[lane + 32 * (h * HQ + qq)] = tmp[qq];
+                    }
+                    cplx* dz = ainvz + (size_t)s * AZ;
+                    for (int qq = lane; qq < AZ; qq += 32) dz[qq] = sm.ainvz[buf][qq];
+                }
+                bar_sync(BAR_M, NW * 32);
+                // recycle the tile touching slot block p: its panel (raw(s)) is already published, and it now holds
+                // entries of local block s+T, whose untouched stencil couplings may already reach the next pivot block.
+#pragma unroll
+                for (int i = 0; i < TPW; ++i) {
+                    if (i != ip) continue;
+                    int dI = tI[i] - p1; if (dI < 0) dI += T;      // position inside the window [s+1, s+T]
+                    int dJ = tJ[i] - p1; if (dJ < 0) dJ += T;
+                    // row/column distance between the entering block (position T-1) and the other block of the tile
+                    const int delta = TS * (T - 1 - min(dI, dJ));
+                    const bool cand = !staged || delta <= TS || (delta + 7 >= nf && delta - 7 <= nf);   // warp-uniform
+                    cre[i][0] = cre[i][1] = cim[i][0] = cim[i][1] = 0.0;
+                    if (cand) {
+                        int gi = (s + 1 + dI) * TS + g;
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            int gj = (s + 1 + dJ) * TS + 2 * t + e;
+                            int hi = max(gi, gj), lo = min(gi, gj);    // hi always lies in the entering block s+T
+                            cplx v = staged ? prov.get_staged(sm.ringRow[s % kRing], hi, lo) : prov.get(hi, lo);
+                            cre[i][e] = v.x;
+                            cim[i][e] = v.y;
+                        }
+                    }
+                }
+                // pass 1: the tile of the next pivot column (and the pivot block after it) first, then publish
+                if (s + 1 < s1) {
+#pragma unroll
+                    for (int i = 0; i < TPW; ++i) {
+                        if (i == ip1) {
+                            if (i != ip) update(i, buf);            // the recycled {p,p1} tile is fresh: no update
+                            dump(i, p1, buf ^ 1);
+                        } else if (i == idg) {
+                            if (i != ip) update(i, buf);            // (T == 2: p2 == p, already recycled)
+                            dump_diag(i, buf);                      // pivot block of panel s+2, updated through panel s
+                        }
+                    }
+                    bar_arrive(BAR_RAW, NTHR);
+                }
+                if (sys.rhs && myX >= 0 && warp != 0) y_update(myX, buf);
+                // pass 2: the rest of the trailing window
+#pragma unroll
+                for (int i = 0; i < TPW; ++i) {
+                    if (i == ip || i == ip1 || i == idg) continue;
+                    update(i, buf);
+                }
+            }
+            if (mode == FM_OWN) {
+                // end of the own lines: export the window (positions relative to the separator start), both triangles
+                cplx* const img = rank == 0 ? wimg0 : wimg1;
+#pragma unroll
+                for (int i = 0; i < TPW; ++i) {
+                    const int aI = rel(tI[i], s1), aJ = rel(tJ[i], s1);
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const cplx v = mk(cre[i][e], cim[i][e]);
+                        img[(size_t)(aI * TS + g) * R + aJ * TS + 2 * t + e] = v;
+                        if (aI != aJ) img[(size_t)(aJ * TS + 2 * t + e) * R + aI * TS + g] = v;
+                    }
+                }
             }
         }
     } else {
@@ -356,7 +493,6 @@ band_factor_kernel(const BandSys* __restrict__ systems, int N, int nf, int b) {
         const int i = g, j0 = 2 * t;
         cplx a0, a1;                                        // A11^{-1}[i][j0], [i][j0+1] of the CURRENT panel
         bool bad = false;
-        // in-register Gauss-Jordan inversion of an 8x8 complex block held as (row i, cols j0, j0+1)
         // Fraction-free Gauss-Jordan (validated in numpy): rows i != k take  row_i <- (p row_i - a_ik row_k) 2^-e
         // with an exact power-of-two rescale, so no reciprocal sits on the 8-pivot dependency chain; every row carries
         // its accumulated scale q_i and the true inverse is  a_ij / q_i, formed with one reciprocal per row at the end.
@@ -396,156 +532,184 @@ band_factor_kernel(const BandSys* __restrict__ systems, int N, int nf, int b) {
             a0 = a0 * qi;
             a1 = a1 * qi;
         };
-        auto publish = [&](int buf) {      // -A11^{-1} as B-fragments, plain A11^{-1} for the TMA store
+        auto publish = [&](int buf) {      // -A11^{-1} as B-fragments, plain A11^{-1} for the store
             // B-fragment layout wants plane[kk][n][tt] = -Ainv[4kk+tt][n]; Ainv is symmetric, so write -Ainv[i][j] at [j>>2][i][j&3]
             *reinterpret_cast<double2*>(&sm.nainv[buf][0][j0 >> 2][i][j0 & 3]) = make_double2(-a0.x, -a1.x);
             *reinterpret_cast<double2*>(&sm.nainv[buf][1][j0 >> 2][i][j0 & 3]) = make_double2(-a0.y, -a1.y);
             sm.ainvz[buf][i * 8 + j0] = a0;
             sm.ainvz[buf][i * 8 + j0 + 1] = a1;
         };
-        // prologue: panel 0
-        bar_sync(BAR_RAW, NTHR);
         {
-            double2 lre = *reinterpret_cast<const double2*>(&sm.raw[0][0][j0 >> 2][i][j0 & 3]);
-            double2 lim = *reinterpret_cast<const double2*>(&sm.raw[0][1][j0 >> 2][i][j0 & 3]);
-            a0 = mk(lre.x, lim.x); a1 = mk(lre.y, lim.y);
-            invert();
-            publish(0);
-        }
-        for (int s = 0; s < S; ++s) {
-            const int p = s % T, p1 = (s + 1) % T, buf = s & 1;
-            const int rp = p * TS;
-            if (bad && lane == 0) { sm.fail = 1; if (sys.status) *sys.status = kErrSingular; }
-            if (sys.rhs) {
-                // z_i = sum_j Ainv[i][j] y_p[j] : two terms per lane, reduced over the 4 lanes of a row
-                cplx acc = a0 * sm.y[rp + j0] + a1 * sm.y[rp + j0 + 1];
-#pragma unroll
-                for (int off = 1; off <= 2; off <<= 1) {
-                    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
-                    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
-                }
-                if (t == 0) sm.ainvz[buf][64 + i] = acc;
-            } else if (t == 0) sm.ainvz[buf][64 + i] = mk(0.0, 0.0);
-            bar_arrive(BAR_INV, NTHR);                      // panel s may be applied (bar.arrive orders the prior smem writes)
-            if (bad) break;
-            // ring prefetch for the block entering the window kPre steps from now (loads stay in flight over the inversion)
-            double rowv; cplx rhsv;
-            ring_fetch(s + kPre + T, lane, rowv, rhsv);
-            if (s + 1 < S) {
-                // ---- early inversion of the next pivot block:  A11(s+1) = D(s+1; through s-1) + M'_{p1} raw_{p1}^T ----
-                double dre[2], dim_[2];
-                {
-                    double2 vre = *reinterpret_cast<const double2*>(&sm.dnext[buf ^ 1][0][i][j0]);
-                    double2 vim = *reinterpret_cast<const double2*>(&sm.dnext[buf ^ 1][1][i][j0]);
-                    dre[0] = vre.x; dre[1] = vre.y; dim_[0] = vim.x; dim_[1] = vim.y;
-                }
-                const int r1 = p1 * TS + g;
-                double mre[2] = {0.0, 0.0}, mim[2] = {0.0, 0.0}, mr2[2] = {0.0, 0.0}, mi2[2] = {0.0, 0.0};
-                double bre[2], bim[2];
-#pragma unroll
-                for (int kk = 0; kk < 2; ++kk) {
-                    bre[kk] = sm.raw[buf][0][kk][r1][t]; bim[kk] = sm.raw[buf][1][kk][r1][t];
-                    double nre = sm.nainv[buf][0][kk][g][t], nim = sm.nainv[buf][1][kk][g][t];
-                    dmma884(mre, bre[kk], nre);
-                    dmma884(mim, bre[kk], nim);
-                    dmma884(mr2, -bim[kk], nim);
-                    dmma884(mi2, bim[kk], nre);
-                }
-                mre[0] += mr2[0]; mre[1] += mr2[1]; mim[0] += mi2[0]; mim[1] += mi2[1];
-                *reinterpret_cast<double2*>(&sm.mscr[0][t >> 1][g][(t & 1) * 2]) = make_double2(mre[0], mre[1]);
-                *reinterpret_cast<double2*>(&sm.mscr[1][t >> 1][g][(t & 1) * 2]) = make_double2(mim[0], mim[1]);
-                __syncwarp();
-                double dr2[2] = {0.0, 0.0}, di2[2] = {0.0, 0.0};
-#pragma unroll
-                for (int kk = 0; kk < 2; ++kk) {
-                    double are = sm.mscr[0][kk][g][t], aim = sm.mscr[1][kk][g][t];
-                    dmma884(dre, are, bre[kk]);
-                    dmma884(dim_, are, bim[kk]);
-                    dmma884(dr2, -aim, bim[kk]);
-                    dmma884(di2, aim, bre[kk]);
-                }
-                a0 = mk(dre[0] + dr2[0], dim_[0] + di2[0]); a1 = mk(dre[1] + dr2[1], dim_[1] + di2[1]);
+            const int s0 = sBeg, s1 = sEnd;
+            // prologue: invert the pivot block of panel s0
+            bar_sync(BAR_RAW, NTHR);
+            {
+                const int rp0 = (s0 % T) * TS;
+                double2 lre = *reinterpret_cast<const double2*>(&sm.raw[s0 & 1][0][j0 >> 2][rp0 + i][j0 & 3]);
+                double2 lim = *reinterpret_cast<const double2*>(&sm.raw[s0 & 1][1][j0 >> 2][rp0 + i][j0 & 3]);
+                a0 = mk(lre.x, lim.x); a1 = mk(lre.y, lim.y);
                 invert();
-                publish(buf ^ 1);
+                publish(s0 & 1);
             }
-            // ring slot of step s+kPre: its previous content (step s+kPre-kRing) was consumed before BAR_M(s+kPre-kRing)
-            sm.ringRow[(s + kPre) % kRing][lane >> 3][lane & 7] = rowv;
-            if (lane < 8) sm.ringRhs[(s + kPre) % kRing][lane] = rhsv;
-            if (s + 1 < S) bar_sync(BAR_RAW, NTHR);         // raw(s+1) complete (y_p(s+1) final as well)
+            for (int s = s0; s < s1; ++s) {
+                const int p = s % T, p1 = (s + 1) % T, buf = s & 1;
+                const int rp = p * TS;
+                bad = __any_sync(0xffffffffu, bad);
+                if (bad && lane == 0) { sm.fail = 1; if (sys.status) *sys.status = kErrSingular; }
+                if (sys.rhs) {
+                    // z_i = sum_j Ainv[i][j] y_p[j] : two terms per lane, reduced over the 4 lanes of a row
+                    cplx acc = a0 * sm.y[rp + j0] + a1 * sm.y[rp + j0 + 1];
+#pragma unroll
+                    for (int off = 1; off <= 2; off <<= 1) {
+                        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
+                        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+                    }
+                    if (t == 0) sm.ainvz[buf][64 + i] = acc;
+                } else if (t == 0) sm.ainvz[buf][64 + i] = mk(0.0, 0.0);
+                bar_arrive(BAR_INV, NTHR);                      // panel s may be applied (bar.arrive orders the prior smem writes)
+                if (bad) break;
+                // ring prefetch for the block entering the window kPre steps from now (loads stay in flight over the inversion)
+                const int gr = (s + kPre + T) * TS + (lane & 7);
+                const double rowv = staged ? prov.plane(gr, lane >> 3) : 0.0;
+                const cplx rhsv = (sys.rhs && lane < 8 && gr < nLoc) ? prov.rhs_at(sys.rhs, gr) : mk(0.0, 0.0);
+                if (s + 1 < s1) {
+                    // ---- early inversion of the next pivot block:  A11(s+1) = D(s+1; through s-1) + M'_{p1} raw_{p1}^T ----
+                    double dre[2], dim_[2];
+                    {
+                        double2 vre = *reinterpret_cast<const double2*>(&sm.dnext[buf ^ 1][0][i][j0]);
+                        double2 vim = *reinterpret_cast<const double2*>(&sm.dnext[buf ^ 1][1][i][j0]);
+                        dre[0] = vre.x; dre[1] = vre.y; dim_[0] = vim.x; dim_[1] = vim.y;
+                    }
+                    const int r1 = p1 * TS + g;
+                    double mre[2] = {0.0, 0.0}, mim[2] = {0.0, 0.0}, mr2[2] = {0.0, 0.0}, mi2[2] = {0.0, 0.0};
+                    double bre[2], bim[2];
+#pragma unroll
+                    for (int kk = 0; kk < 2; ++kk) {
+                        bre[kk] = sm.raw[buf][0][kk][r1][t]; bim[kk] = sm.raw[buf][1][kk][r1][t];
+                        double nre = sm.nainv[buf][0][kk][g][t], nim = sm.nainv[buf][1][kk][g][t];
+                        dmma884(mre, bre[kk], nre);
+                        dmma884(mim, bre[kk], nim);
+                        dmma884(mr2, -bim[kk], nim);
+                        dmma884(mi2, bim[kk], nre);
+                    }
+                    mre[0] += mr2[0]; mre[1] += mr2[1]; mim[0] += mi2[0]; mim[1] += mi2[1];
+                    *reinterpret_cast<double2*>(&sm.mscr[0][t >> 1][g][(t & 1) * 2]) = make_double2(mre[0], mre[1]);
+                    *reinterpret_cast<double2*>(&sm.mscr[1][t >> 1][g][(t & 1) * 2]) = make_double2(mim[0], mim[1]);
+                    __syncwarp();
+                    double dr2[2] = {0.0, 0.0}, di2[2] = {0.0, 0.0};
+#pragma unroll
+                    for (int kk = 0; kk < 2; ++kk) {
+                        double are = sm.mscr[0][kk][g][t], aim = sm.mscr[1][kk][g][t];
+                        dmma884(dre, are, bre[kk]);
+                        dmma884(dim_, are, bim[kk]);
+                        dmma884(dr2, -aim, bim[kk]);
+                        dmma884(di2, aim, bre[kk]);
+                    }
+                    a0 = mk(dre[0] + dr2[0], dim_[0] + di2[0]); a1 = mk(dre[1] + dr2[1], dim_[1] + di2[1]);
+                    invert();
+                    publish(buf ^ 1);
+                }
+                // ring slot of step s+kPre: its previous content (step s+kPre-kRing) was consumed before BAR_M(s+kPre-kRing)
+                sm.ringRow[(s + kPre) % kRing][lane >> 3][lane & 7] = rowv;
+                if (lane < 8) sm.ringRhs[(s + kPre) % kRing][lane] = rhsv;
+                if (s + 1 < s1) bar_sync(BAR_RAW, NTHR);        // raw(s+1) complete (y_p(s+1) final as well)
+            }
         }
     }
+  }   // mode != FM_BACK
     fence_proxy_async_all();                                // the panels are read back below through the async proxy (TMA)
     __threadfence();
-    __syncthreads();
-    if (!sys.rhs || sm.fail) return;
+    cta_sync();
+    if (!sys.rhs) return;
+    if (mode == FM_OWN) {
+        // forward-eliminated rhs window, relative to the separator start
+        cplx* const yimg = rank == 0 ? yimg0 : yimg1;
+        for (int r_b = 0; r_b < R; r_b += NTHR) if (const int r = r_b + tid; r < R) yimg[rel(r >> 3, sEnd) * TS + (r & 7)] = sm.y[r];
+        return;
+    }
+    // NB on a singular pivot block (sm.fail) the status is set; the substitution below then runs on garbage but terminates.
 
     // =============================== fused back-substitution ===============================
-    //   x_p = z_s - A11_s^{-1} (raw_s^T x_rest),  s = S-1 .. 0   (x window circular in smem: reuse sm.y)
-    // The factor is streamed back with TMA bulk loads, kBackStages-1 panels in flight.
+    //   x_p = z_s - A11_s^{-1} (raw_s^T x_rest),  s = last .. first   (x window circular in smem: reuse sm.y)
+    // The factor is streamed back with TMA bulk loads, kBackStages-1 panels in flight.  With a split system FM_SEP
+    // solves the separator steps and publishes the separator solution, FM_BACK finishes the own steps of both halves.
     constexpr int NST = FactorSmem<T>::kBackStages;
-    for (int i = tid; i < R; i += NTHR) sm.y[i] = mk(0.0, 0.0);
+    for (int i_b = 0; i_b < R; i_b += NTHR) if (const int i = i_b + tid; i < R)
+        sm.y[i] = (mode == FM_BACK) ? xsep[rel(i >> 3, L.sOwn) * TS + (i & 7)] : mk(0.0, 0.0);
     if (tid == 0) {
         for (int q = 0; q < NST; ++q) mbar_init(&sm.mbar[q], 1);
         fence_mbar_init();
     }
-    __syncthreads();
+    cta_sync();
     constexpr uint32_t PBYTES = panel_doubles(T) * 8;
-    auto issue = [&](int s) {     // thread 0: prefetch panel s and [A11^{-1}|z]_s into stage (S-1-s) % NST
-        int st = (S - 1 - s) % NST;
-        mbar_arrive_expect_tx(&sm.mbar[st], PBYTES + AZ * 16);
-        bulk_g2s(&sm.stage[st][0][0][0][0], sys.panels + (size_t)s * panel_doubles(T), PBYTES, &sm.mbar[st]);
-        bulk_g2s(&sm.stageAZ[st][0], sys.ainvz + (size_t)s * AZ, AZ * 16, &sm.mbar[st]);
-    };
-    if (tid == 0) {
-        fence_proxy_async();
-        for (int q = 0; q < NST - 1 && S - 1 - q >= 0; ++q) issue(S - 1 - q);
-    }
     constexpr int NRG = NTHR / 8;        // row groups
-    for (int s = S - 1; s >= 0; --s) {
-        const int p = s % T, it = S - 1 - s, st = it % NST;
-        if (tid == 0 && s - (NST - 1) >= 0) issue(s - (NST - 1));      // stage freed at the end of the previous step
-        mbar_wait(&sm.mbar[st], (uint32_t)((it / NST) & 1));
-        const int c = tid & 7, rg = tid >> 3;
-        cplx acc = mk(0.0, 0.0);
-        for (int r = rg; r < R; r += NRG) {
-            if ((r >> 3) == p) continue;
-            cplx rv = mk(sm.stage[st][0][c >> 2][r][c & 3], sm.stage[st][1][c >> 2][r][c & 3]);
-            cfma(acc, rv, sm.y[r]);
+    int itBase = 0;                      // running count of panel visits: stage = visit % NST, parity = (visit / NST) & 1
+    auto back_range = [&](int sHi, int sLo) {        // steps sHi-1 .. sLo
+        const int n = sHi - sLo;
+        auto issue = [&](int k) {        // k-th visit of this range -> panel sHi-1-k
+            const int s = sHi - 1 - k, st = (itBase + k) % NST;
+            mbar_arrive_expect_tx(&sm.mbar[st], PBYTES + AZ * 16);
+            bulk_g2s(&sm.stage[st][0][0][0][0], panels + (size_t)s * panel_doubles(T), PBYTES, &sm.mbar[st]);
+            bulk_g2s(&sm.stageAZ[st][0], ainvz + (size_t)s * AZ, AZ * 16, &sm.mbar[st]);
+        };
+        if (tid == 0) {
+            fence_proxy_async();
+            for (int k = 0; k < NST - 1 && k < n; ++k) issue(k);
         }
-        // reduce the 4 row groups inside a warp (lanes differing in bits 3,4)
-#pragma unroll
-        for (int off = 8; off <= 16; off <<= 1) {
-            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
-            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
-        }
-        if (lane < 8) sm.part[warp][lane] = acc;
-        __syncthreads();
-        if (warp == 0) {
-            // d_k = sum_w part[w][k] (lanes k + 8j hold partial sums), then x_i = z_i - sum_k Ainv[i][k] d_k
-            cplx d = mk(0.0, 0.0);
-            for (int w = (lane >> 3); w < NW + 1; w += 4) d += sm.part[w][lane & 7];
+        for (int k = 0; k < n; ++k) {
+            const int s = sHi - 1 - k, p = s % T, it = itBase + k, st = it % NST;
+            if (tid == 0 && k + NST - 1 < n) issue(k + NST - 1);       // stage freed at the end of the previous step
+            mbar_wait(&sm.mbar[st], (uint32_t)((it / NST) & 1));
+            const int c = tid & 7, rg = tid >> 3;
+            cplx acc = mk(0.0, 0.0);
+            for (int r = rg; r < R; r += NRG) {
+                if ((r >> 3) == p) continue;
+                cplx rv = mk(sm.stage[st][0][c >> 2][r][c & 3], sm.stage[st][1][c >> 2][r][c & 3]);
+                cfma(acc, rv, sm.y[r]);
+            }
+            // reduce the 4 row groups inside a warp (lanes differing in bits 3,4)
 #pragma unroll
             for (int off = 8; off <= 16; off <<= 1) {
-                d.x += __shfl_xor_sync(0xffffffffu, d.x, off);
-                d.y += __shfl_xor_sync(0xffffffffu, d.y, off);
+                acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
+                acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
             }
-            const int ii = lane >> 2, tt = lane & 3;     // lane handles k = 2tt, 2tt+1 of row ii
-            cplx d0 = mk(__shfl_sync(0xffffffffu, d.x, 2 * tt), __shfl_sync(0xffffffffu, d.y, 2 * tt));
-            cplx d1 = mk(__shfl_sync(0xffffffffu, d.x, 2 * tt + 1), __shfl_sync(0xffffffffu, d.y, 2 * tt + 1));
-            cplx xv = sm.stageAZ[st][ii * 8 + 2 * tt] * d0 + sm.stageAZ[st][ii * 8 + 2 * tt + 1] * d1;
+            if (lane < 8) sm.part[warp][lane] = acc;
+            cta_sync();
+            if (warp == 0) {
+                // d_k = sum_w part[w][k] (lanes k + 8j hold partial sums), then x_i = z_i - sum_k Ainv[i][k] d_k
+                cplx d = mk(0.0, 0.0);
+                for (int w = (lane >> 3); w < NW + 1; w += 4) d += sm.part[w][lane & 7];
 #pragma unroll
-            for (int off = 1; off <= 2; off <<= 1) {
-                xv.x += __shfl_xor_sync(0xffffffffu, xv.x, off);
-                xv.y += __shfl_xor_sync(0xffffffffu, xv.y, off);
+                for (int off = 8; off <= 16; off <<= 1) {
+                    d.x += __shfl_xor_sync(0xffffffffu, d.x, off);
+                    d.y += __shfl_xor_sync(0xffffffffu, d.y, off);
+                }
+                const int ii = lane >> 2, tt = lane & 3;     // lane handles k = 2tt, 2tt+1 of row ii
+                cplx d0 = mk(__shfl_sync(0xffffffffu, d.x, 2 * tt), __shfl_sync(0xffffffffu, d.y, 2 * tt));
+                cplx d1 = mk(__shfl_sync(0xffffffffu, d.x, 2 * tt + 1), __shfl_sync(0xffffffffu, d.y, 2 * tt + 1));
+                cplx xv = sm.stageAZ[st][ii * 8 + 2 * tt] * d0 + sm.stageAZ[st][ii * 8 + 2 * tt + 1] * d1;
+#pragma unroll
+                for (int off = 1; off <= 2; off <<= 1) {
+                    xv.x += __shfl_xor_sync(0xffffffffu, xv.x, off);
+                    xv.y += __shfl_xor_sync(0xffffffffu, xv.y, off);
+                }
+                if (tt == 0) {
+                    cplx xo = sm.stageAZ[st][64 + ii] - xv;
+                    sm.y[p * TS + ii] = xo;
+                    prov.x_store(sys.x, s * TS + ii, xo);
+                }
             }
-            if (tt == 0) {
-                cplx xo = sm.stageAZ[st][64 + ii] - xv;
-                sm.y[p * TS + ii] = xo;
-                int gidx = s * TS + ii;
-                if (gidx < N) sys.x[gidx] = xo;
-            }
+            cta_sync();
         }
-        __syncthreads();
+        itBase += n;
+    };
+    if (mode == FM_FULL) {
+        back_range(L.sTot, 0);
+    } else if (mode == FM_SEP) {
+        back_range(L.sTot, L.sOwn);
+        for (int r_b = 0; r_b < R; r_b += NTHR) if (const int r = r_b + tid; r < R) xsep[rel(r >> 3, L.sOwn) * TS + (r & 7)] = sm.y[r];
+    } else {
+        back_range(L.sOwn, 0);
     }
 }
 

@@ -115,11 +115,21 @@ __device__ __forceinline__ void dmma884_p(double (&c)[2], double a, double b, in
 }
 
 // ---- named barriers -------------------------------------------------------------------
+// bar.sync / bar.arrive must be executed by a converged warp: reconverge explicitly first
 __device__ __forceinline__ void bar_sync(int id, int nthreads) {
+    __syncwarp();
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 __device__ __forceinline__ void bar_arrive(int id, int nthreads) {
+    __syncwarp();
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// CTA barrier preceded by an explicit warp reconvergence: bar.sync is an *aligned* barrier, a warp that reaches it
+// in two divergent halves is counted twice and deadlocks the next generation (seen with ncu/trace on B200).
+__device__ __forceinline__ void cta_sync() {
+    __syncwarp();
+    __syncthreads();
 }
 
 // ---- TMA bulk copies (SASS: UBLKCP) + mbarrier ------------------------------------------

@@ -2,6 +2,7 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -43,6 +44,8 @@ struct hmcmt_plan {
     int modeList[2] = {0, 1};
     int nSysPerChain = 0, nSys = 0, nFull = 0;      // nFull = nFreq*nRx*nModes per chain
     int T = 0, S = 0, b = 0, device = 0;
+    BandDom dom{};
+    int steps0 = 0, steps1 = 0;                     // macro-steps of half 0 (own lines + separator) / half 1 (0 when not split)
     double beta = 1.0, lo = 0.0, hi = 0.0;
     MeshDev M{};
     SysMap sm{};
@@ -61,7 +64,7 @@ struct hmcmt_plan {
     DevBuf<double> yLen, zLen, zNode, freqs, fdy1, fdy2, wL, wR, bg, wmVal, wd, m, p, mref, sigma, meanSig, planes;
     DevBuf<double> Gpart, phiPart, phi, gsig, gdata, gtotal, energies, panels, curM, curP, chainScal, zmom;
     DevBuf<int> fid, iL, iR, cell2act, act2cell, wmPtr, wmIdx, status, driftFlag, packed2full, Lsteps;
-    DevBuf<cplx> obs, bc, bcs, rhs, x, F, lam, Lam, srows, qrow, scratch, predFull, ainvz, zadj, vin, predPacked;
+    DevBuf<cplx> obs, bc, bcs, rhs, x, F, lam, Lam, srows, qrow, scratch, predFull, ainvz, zadj, vin, predPacked, wexp;
     DevBuf<BandSys> sysDesc;
     DevBuf<SolveJob> jobs;
     // pinned staging for the host-buffer entry points
@@ -81,26 +84,42 @@ namespace {
         }                                                         \
     } while (0)
 
+// A split system takes three launches in stream order: own lines of both halves, separator, back-substitution of both halves.
 template <int T>
-int launch_factor_T(cudaStream_t st, const BandSys* sys, int nsys, int N, int nf, int b) {
+int launch_factor_T(cudaStream_t st, const BandSys* sys, int nsys, const BandDom& dom) {
     static bool configured = false;
     size_t smem = sizeof(FactorSmem<T>);
     if (!configured) {
         HMCMT_CUDA_TRY(cudaFuncSetAttribute(band_factor_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    band_factor_kernel<T><<<nsys, FactorCfg<T>::NTHREADS, smem, st>>>(sys, N, nf, b);
+    constexpr int NT = FactorCfg<T>::NTHREADS;
+    if (!dom.split) {
+        band_factor_kernel<T><<<nsys, NT, smem, st>>>(sys, dom, FM_FULL);
+    } else {
+        band_factor_kernel<T><<<2 * nsys, NT, smem, st>>>(sys, dom, FM_OWN);
+        band_factor_kernel<T><<<nsys, NT, smem, st>>>(sys, dom, FM_SEP);
+        band_factor_kernel<T><<<2 * nsys, NT, smem, st>>>(sys, dom, FM_BACK);
+    }
+    HMCMT_CUDA_TRY(cudaGetLastError());
     return kOk;
 }
 template <int T>
-int launch_solve_T(cudaStream_t st, const SolveJob* jobs, int njobs, int N) {
+int launch_solve_T(cudaStream_t st, const SolveJob* jobs, int njobs, const BandDom& dom) {
     static bool configured = false;
     size_t smem = sizeof(SolveSmem<T>);
     if (!configured) {
         HMCMT_CUDA_TRY(cudaFuncSetAttribute(band_solve_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    band_solve_kernel<T><<<njobs, kSolveThreads, smem, st>>>(jobs, N);
+    if (!dom.split) {
+        band_solve_kernel<T><<<njobs, kSolveThreads, smem, st>>>(jobs, dom, FM_FULL);
+    } else {
+        band_solve_kernel<T><<<2 * njobs, kSolveThreads, smem, st>>>(jobs, dom, FM_OWN);
+        band_solve_kernel<T><<<njobs, kSolveThreads, smem, st>>>(jobs, dom, FM_SEP);
+        band_solve_kernel<T><<<2 * njobs, kSolveThreads, smem, st>>>(jobs, dom, FM_BACK);
+    }
+    HMCMT_CUDA_TRY(cudaGetLastError());
     return kOk;
 }
 
@@ -114,37 +133,29 @@ int round_T(int b) {
     if (T & 1) ++T;
     return T;
 }
-int launch_factor(cudaStream_t st, int T, const BandSys* sys, int nsys, int N, int nf, int b) {
-    int rc;
+int launch_factor(cudaStream_t st, int T, const BandSys* sys, int nsys, const BandDom& dom) {
     switch (T) {
-        case 2: rc = launch_factor_T<2>(st, sys, nsys, N, nf, b); break;
-        case 4: rc = launch_factor_T<4>(st, sys, nsys, N, nf, b); break;
-        case 6: rc = launch_factor_T<6>(st, sys, nsys, N, nf, b); break;
-        case 8: rc = launch_factor_T<8>(st, sys, nsys, N, nf, b); break;
-        case 10: rc = launch_factor_T<10>(st, sys, nsys, N, nf, b); break;
-        case 12: rc = launch_factor_T<12>(st, sys, nsys, N, nf, b); break;
-        case 14: rc = launch_factor_T<14>(st, sys, nsys, N, nf, b); break;
+        case 2: return launch_factor_T<2>(st, sys, nsys, dom);
+        case 4: return launch_factor_T<4>(st, sys, nsys, dom);
+        case 6: return launch_factor_T<6>(st, sys, nsys, dom);
+        case 8: return launch_factor_T<8>(st, sys, nsys, dom);
+        case 10: return launch_factor_T<10>(st, sys, nsys, dom);
+        case 12: return launch_factor_T<12>(st, sys, nsys, dom);
+        case 14: return launch_factor_T<14>(st, sys, nsys, dom);
         default: return kErrArg;
     }
-    if (rc) return rc;
-    if (cudaGetLastError() != cudaSuccess) return kErrCuda;
-    return kOk;
 }
-int launch_solve(cudaStream_t st, int T, const SolveJob* jobs, int njobs, int N) {
-    int rc;
+int launch_solve(cudaStream_t st, int T, const SolveJob* jobs, int njobs, const BandDom& dom) {
     switch (T) {
-        case 2: rc = launch_solve_T<2>(st, jobs, njobs, N); break;
-        case 4: rc = launch_solve_T<4>(st, jobs, njobs, N); break;
-        case 6: rc = launch_solve_T<6>(st, jobs, njobs, N); break;
-        case 8: rc = launch_solve_T<8>(st, jobs, njobs, N); break;
-        case 10: rc = launch_solve_T<10>(st, jobs, njobs, N); break;
-        case 12: rc = launch_solve_T<12>(st, jobs, njobs, N); break;
-        case 14: rc = launch_solve_T<14>(st, jobs, njobs, N); break;
+        case 2: return launch_solve_T<2>(st, jobs, njobs, dom);
+        case 4: return launch_solve_T<4>(st, jobs, njobs, dom);
+        case 6: return launch_solve_T<6>(st, jobs, njobs, dom);
+        case 8: return launch_solve_T<8>(st, jobs, njobs, dom);
+        case 10: return launch_solve_T<10>(st, jobs, njobs, dom);
+        case 12: return launch_solve_T<12>(st, jobs, njobs, dom);
+        case 14: return launch_solve_T<14>(st, jobs, njobs, dom);
         default: return kErrArg;
     }
-    if (rc) return rc;
-    if (cudaGetLastError() != cudaSuccess) return kErrCuda;
-    return kOk;
 }
 int max_band_T() { return 14; }
 }  // namespace hmcmt
@@ -288,9 +299,9 @@ int compute_step(hmcmt_plan* pl, bool wantAdjoint, const cplx* vin) {
         }
         auto& ev = pl->factorEvents[pl->factorEventsUsed++];
         HMCMT_CUDA_TRY(cudaEventRecord(ev.first, st));
-        int rc = launch_factor(st, pl->T, pl->sysDesc.p, nSys, M.N, M.nf, pl->b);
+        int rc = launch_factor(st, pl->T, pl->sysDesc.p, nSys, pl->dom);
         if (rc) return rc;
-        ++pl->launches;
+        pl->launches += pl->dom.split ? 3 : 1;
         ++pl->factorLaunches;
         HMCMT_CUDA_TRY(cudaEventRecord(ev.second, st));
     }
@@ -304,9 +315,9 @@ int compute_step(hmcmt_plan* pl, bool wantAdjoint, const cplx* vin) {
     LAUNCH_CHECK(pl);
     pl->haveForward = true;
     if (!wantAdjoint) return kOk;
-    int rc = launch_solve(st, pl->T, pl->jobs.p, nSys, M.N);      // lam <- A^{-1} s[ii]  (in place)
+    int rc = launch_solve(st, pl->T, pl->jobs.p, nSys, pl->dom);      // lam <- A^{-1} s[ii]  (in place)
     if (rc) return rc;
-    ++pl->launches;
+    pl->launches += pl->dom.split ? 3 : 1;
     k_node_field<<<dim3((M.nNode + 255) / 256, nSys), 256, 0, st>>>(M, pl->lam.p, nullptr, pl->Lam.p);
     LAUNCH_CHECK(pl);
     HMCMT_CUDA_TRY(cudaStreamWaitEvent(st, pl->evJoin, 0));
@@ -368,7 +379,16 @@ int hmcmt_plan_create(const hmcmt_problem* pr, hmcmt_plan** out) {
     M.nCell = ny * nz; M.nNode = (ny + 1) * (nz + 1); M.nb = 2 * (ny + nz);
     pl->b = M.nf;
     pl->T = round_T(pl->b);
-    pl->S = (M.N + TS - 1) / TS;
+    {
+        // two CTAs per system when there are enough lines: halves the sequential pivot chain
+        const char* env = std::getenv("HMCMT_SPLIT");
+        int want = env ? std::atoi(env) : 1;
+        pl->dom = BandDom{M.N, M.nf, pl->b, M.nl, (want && M.nl >= 9) ? 1 : 0, M.nl / 2};
+        LocalDom L0 = LocalDom::make(pl->dom, 0);
+        pl->steps0 = L0.sTot;
+        pl->steps1 = pl->dom.split ? LocalDom::make(pl->dom, 1).sOwn : 0;
+        pl->S = pl->steps0 + pl->steps1;
+    }
     if (M.nf < 2) { delete pl; return kErrArg; }
     if (pl->T > max_band_T()) {
         fprintf(stderr, "[hmcmt_b200] half-bandwidth %d needs a tile window T=%d > %d: not supported by the register-window kernel yet\n",
@@ -459,6 +479,8 @@ int hmcmt_plan_create(const hmcmt_problem* pr, hmcmt_plan** out) {
     ok(pl->predFull.alloc(nCh * pl->nFull)); ok(pl->vin.alloc(nCh * pl->nFull)); ok(pl->predPacked.alloc(nCh * pr->nData));
     ok(pl->panels.alloc(nSys * (size_t)pl->S * panel_doubles(pl->T)));
     ok(pl->ainvz.alloc(nSys * (size_t)pl->S * AZ)); ok(pl->zadj.alloc(nSys * (size_t)pl->S * 8));
+    const size_t wexpN = split_scratch_entries(TS * pl->T);
+    ok(pl->wexp.alloc(pl->dom.split ? nSys * wexpN : 0));
     ok(pl->status.alloc(nSys)); ok(pl->driftFlag.alloc(1)); ok(pl->Lsteps.alloc(nCh));
     ok(pl->sysDesc.alloc(nSys)); ok(pl->jobs.alloc(nSys));
     if (rc) { hmcmt_destroy(pl); return rc; }
@@ -482,14 +504,20 @@ int hmcmt_plan_create(const hmcmt_problem* pr, hmcmt_plan** out) {
         d.omega = 2.0 * kPi * pr->freqs[f];
         d.band = nullptr;
         d.rhs = pl->rhs.p + s * N;
-        d.panels = pl->panels.p + s * (size_t)pl->S * panel_doubles(pl->T);
-        d.ainvz = pl->ainvz.p + s * (size_t)pl->S * AZ;
+        d.panels[0] = pl->panels.p + s * (size_t)pl->S * panel_doubles(pl->T);
+        d.panels[1] = d.panels[0] + (size_t)pl->steps0 * panel_doubles(pl->T);
+        d.ainvz[0] = pl->ainvz.p + s * (size_t)pl->S * AZ;
+        d.ainvz[1] = d.ainvz[0] + (size_t)pl->steps0 * AZ;
+        d.wexp = pl->dom.split ? pl->wexp.p + s * wexpN : nullptr;
         d.x = pl->x.p + s * N;
         d.status = pl->status.p + s;
         SolveJob& j = jb[s];
-        j.panels = d.panels; j.ainvz = d.ainvz;
+        j.panels[0] = d.panels[0]; j.panels[1] = d.panels[1];
+        j.ainvz[0] = d.ainvz[0]; j.ainvz[1] = d.ainvz[1];
         j.rhs = pl->lam.p + s * N; j.x = pl->lam.p + s * N;
-        j.zbuf = pl->zadj.p + s * (size_t)pl->S * 8;
+        j.zbuf[0] = pl->zadj.p + s * (size_t)pl->S * 8;
+        j.zbuf[1] = j.zbuf[0] + (size_t)pl->steps0 * 8;
+        j.wexp = d.wexp;
     }
     if (cudaMemcpy(pl->sysDesc.p, sd.data(), sizeof(BandSys) * nSys, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(pl->jobs.p, jb.data(), sizeof(SolveJob) * nSys, cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -527,7 +555,7 @@ void hmcmt_destroy(hmcmt_plan* pl) {
     pl->driftFlag.release(); pl->packed2full.release(); pl->Lsteps.release(); pl->obs.release(); pl->bc.release(); pl->bcs.release();
     pl->rhs.release(); pl->x.release(); pl->F.release(); pl->lam.release(); pl->Lam.release(); pl->srows.release(); pl->qrow.release();
     pl->scratch.release(); pl->predFull.release(); pl->ainvz.release(); pl->zadj.release(); pl->vin.release();
-    pl->predPacked.release(); pl->sysDesc.release(); pl->jobs.release();
+    pl->predPacked.release(); pl->wexp.release(); pl->sysDesc.release(); pl->jobs.release();
     if (pl->pin) cudaFreeHost(pl->pin);
     delete pl;
 }

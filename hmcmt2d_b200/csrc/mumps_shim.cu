@@ -15,8 +15,8 @@
 
 namespace hmcmt {
 int round_T(int b);
-int launch_factor(cudaStream_t st, int T, const BandSys* sys, int nsys, int N, int nf, int b);
-int launch_solve(cudaStream_t st, int T, const SolveJob* jobs, int njobs, int N);
+int launch_factor(cudaStream_t st, int T, const BandSys* sys, int nsys, const BandDom& dom);
+int launch_solve(cudaStream_t st, int T, const SolveJob* jobs, int njobs, const BandDom& dom);
 int max_band_T();
 }  // namespace hmcmt
 using namespace hmcmt;
@@ -91,9 +91,10 @@ int64_t factor_common(int64_t n, int64_t sym, const double* nzval, const int64_t
     cudaMemcpy(dband, band.data(), band.size() * sizeof(cplx), cudaMemcpyHostToDevice);
     cudaMemset(dstatus, 0, sizeof(int));
     BandSys s{};
-    s.band = dband; s.omega = 0.0; s.rhs = nullptr; s.panels = f->panels; s.ainvz = f->ainvz; s.x = nullptr; s.status = dstatus;
+    s.band = dband; s.omega = 0.0; s.rhs = nullptr; s.panels[0] = f->panels; s.panels[1] = nullptr; s.ainvz[0] = f->ainvz; s.ainvz[1] = nullptr; s.wexp = nullptr; s.x = nullptr; s.status = dstatus;
     cudaMemcpy(dsys, &s, sizeof(BandSys), cudaMemcpyHostToDevice);
-    int rc = launch_factor(nullptr, T, dsys, 1, (int)n, (int)b, (int)b);
+    BandDom dom{(int)n, (int)b, (int)b, 0, 0, 0};
+    int rc = launch_factor(nullptr, T, dsys, 1, dom);
     int hst = 0;
     if (rc == kOk && cudaDeviceSynchronize() != cudaSuccess) rc = kErrCuda;
     if (rc == kOk) cudaMemcpy(&hst, dstatus, sizeof(int), cudaMemcpyDeviceToHost);
@@ -129,11 +130,13 @@ int64_t solve_common(int64_t h, int64_t nrhs, const double* rhs, double* x, bool
     cudaMemcpy(dx, hb.data(), hb.size() * sizeof(cplx), cudaMemcpyHostToDevice);
     std::vector<SolveJob> jobs(nrhs);
     for (int64_t r = 0; r < nrhs; ++r) {
-        jobs[r].panels = f->panels; jobs[r].ainvz = f->ainvz;
-        jobs[r].rhs = dx + r * n; jobs[r].x = dx + r * n; jobs[r].zbuf = dz + (size_t)r * f->S * 8;
+        jobs[r].panels[0] = f->panels; jobs[r].panels[1] = nullptr; jobs[r].ainvz[0] = f->ainvz; jobs[r].ainvz[1] = nullptr;
+        jobs[r].rhs = dx + r * n; jobs[r].x = dx + r * n; jobs[r].zbuf[0] = dz + (size_t)r * f->S * 8; jobs[r].zbuf[1] = nullptr;
+        jobs[r].wexp = nullptr;
     }
     cudaMemcpy(djobs, jobs.data(), sizeof(SolveJob) * nrhs, cudaMemcpyHostToDevice);
-    int rc = launch_solve(nullptr, f->T, djobs, (int)nrhs, f->n);
+    BandDom dom{f->n, f->b, f->b, 0, 0, 0};
+    int rc = launch_solve(nullptr, f->T, djobs, (int)nrhs, dom);
     if (rc == kOk && cudaDeviceSynchronize() != cudaSuccess) rc = kErrCuda;
     if (rc == kOk) {
         cudaMemcpy(hb.data(), dx, hb.size() * sizeof(cplx), cudaMemcpyDeviceToHost);
