@@ -302,6 +302,112 @@ class Plan:
         return colptr, rowval, nzval, rhs, bc
 
 
+    # -- frequency-sharded step (include/hmcmt_b200.h) --
+    def step_partial(self, dt):
+        _lib.check(self.L.hmcmt_step_partial(self.h, float(dt)), "hmcmt_step_partial")
+
+    def step_finish(self, dt):
+        _lib.check(self.L.hmcmt_step_finish(self.h, float(dt)), "hmcmt_step_finish")
+
+    def exchange_buffer(self):
+        """(device pointer, number of doubles) of the per-step exchange buffer [gdata(nAC) | phi_d] x nChains."""
+        ptr, n = C.c_void_p(), C.c_int64(0)
+        _lib.check(self.L.hmcmt_exchange_buffer(self.h, C.byref(ptr), C.byref(n)), "hmcmt_exchange_buffer")
+        return int(ptr.value), int(n.value)
+
+
+# ---------------------------------------------------------------------------------------------------
+# frequency sharding (SURVEY.md 8e, BASELINE.json configs[3]): the (frequency, mode) systems are independent given sigma
+
+
+def shard_frequencies(mtData: MTData, invParam: InvDataModel, rank: int, world: int):
+    """Frequencies rank, rank+world, ... (round-robin: every frequency costs the same, identical sparsity pattern).
+    -> (MTData restricted to those frequencies with freqID renumbered 1..n, InvDataModel with the matching observation
+    rows, `rows` = positions of those observations in the full data vector)."""
+    nF = len(mtData.freqs)
+    mine = np.arange(rank, nF, world)
+    if len(mine) == 0:
+        raise ValueError(f"rank {rank} of {world} owns no frequency (nFreq = {nF})")
+    newid = np.zeros(nF + 1, dtype=np.int64)
+    newid[mine + 1] = np.arange(1, len(mine) + 1)
+    fid = np.asarray(mtData.freqID)
+    rows = np.nonzero(newid[fid] > 0)[0]
+    # dataID is the (comp, rx, freq) presence mask of readMT2DData.jl:165-172: keep the frequency planes this rank owns
+    nRx, nDt = np.asarray(mtData.rxLoc).shape[0], len(mtData.dataComp)
+    mask = np.asarray(mtData.dataID, dtype=bool).reshape(nF, nRx, nDt)[mine].reshape(-1)
+    sub = MTData(np.array(mtData.rxLoc), np.array(mtData.freqs)[mine], mtData.dataType, list(mtData.dataComp),
+                 np.asarray(mtData.rxID)[rows], newid[fid[rows]], np.asarray(mtData.dtID)[rows], mask, mtData.compTE, mtData.compTM)
+    dataW = np.asarray(invParam.dataW)[rows]
+    inv = InvDataModel(np.asarray(invParam.obsData)[rows], dataW, np.array(invParam.strModel), np.array(invParam.refModel),
+                       invParam.activeCell, np.array(invParam.bgModel), invParam.Wm, 1.0 / dataW)
+    return sub, inv, rows
+
+
+class FreqShardedPlan:
+    """One rank's share of a frequency-sharded problem.  `group` is a torch.distributed process group (NCCL on GPUs); the
+    only data-path collective is one sum-all-reduce of [gdata | phi_d] per evaluation."""
+
+    def __init__(self, mtMesh, mtData, invParam, hmcprior, rank: int, world: int, device: int = 0, group=None):
+        self.rank, self.world, self.group = int(rank), int(world), group
+        self.nDataFull = len(np.asarray(invParam.obsData))
+        sub, inv, self.rows = shard_frequencies(mtData, invParam, rank, world)
+        self.plan = Plan(mtMesh, sub, inv, hmcprior, nChains=1, device=device)
+        self.nAC, self.device = self.plan.nAC, int(device)
+        self._xt = None
+
+    # host-buffer evaluation: compDataGradient over all frequencies
+    def forward_gradient(self, m):
+        import torch
+        import torch.distributed as dist
+        pred, phi, g = self.plan.forward_gradient(m)
+        full = np.zeros(self.nDataFull, dtype=np.complex128)
+        full[self.rows] = pred[0]
+        packed = np.concatenate([g[0], phi, full.view(np.float64)])
+        if self.world > 1:
+            t = torch.from_numpy(packed)
+            if dist.get_backend(self.group) == "nccl":
+                t = t.cuda(self.device)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            packed = t.cpu().numpy()
+        nAC = self.nAC
+        return packed[nAC + 1:].view(np.complex128), float(packed[nAC]), packed[:nAC]
+
+    # device-resident leapfrog steps with one NCCL all-reduce per step
+    def _exchange_tensor(self):
+        import torch
+        if self._xt is None:
+            ptr, n = self.plan.exchange_buffer()
+
+            class _View:
+                __cuda_array_interface__ = dict(shape=(n,), typestr="<f8", data=(ptr, False), version=2)
+            self._xt = torch.as_tensor(_View(), device=f"cuda:{self.device}")
+        return self._xt
+
+    def leapfrog_steps_device(self, dt, nsteps):
+        import torch
+        import torch.distributed as dist
+        xt = self._exchange_tensor() if self.world > 1 else None
+        for _ in range(int(nsteps)):
+            self.plan.step_partial(dt)
+            if self.world > 1:
+                self.plan.sync()                                   # the plan's stream is not torch's
+                dist.all_reduce(xt, op=dist.ReduceOp.SUM, group=self.group)
+                torch.cuda.current_stream(self.device).synchronize()
+            self.plan.step_finish(dt)
+
+    def set_state(self, m=None, p=None, mref=None):
+        self.plan.set_state(m, p, mref)
+
+    def get_state(self):
+        return self.plan.get_state()
+
+    def sync(self):
+        self.plan.sync()
+
+    def close(self):
+        self.plan.close()
+
+
 def _plan_for(mtMesh, mtData, invParam, hmcprior, nChains=1, device=0) -> Plan:
     """One plan per (invParam, nChains, device), cached on the invParam object like the reference caches
     operators on the mesh (`mtMesh.setup`)."""

@@ -1,0 +1,264 @@
+// Large-bandwidth path of the batched complex-symmetric block-LDL^T factorisation (half-bandwidth 105 .. 320,
+// e.g. the 800 x 300-cell mesh of BASELINE.json configs[3], b = 299).
+//
+// Same algorithm and the SAME stored factor as band_factor.cuh — 8x8 pivot blocks, per macro-step
+// { raw panel image, A11^{-1}, z } — so the solve kernel (band_solve.cuh) serves both paths.  What changes is where
+// the sliding window lives: T x T tiles no longer fit one SM's register file, so the window is a circular R x R
+// array in global memory (L2-resident: 1.6 MB per system at b = 299) and the elimination advances kBigNBK = 4
+// macro-steps (32 columns) per pair of stream-ordered launches:
+//   bigband_panel_kernel   one CTA per system: loads the 32 panel columns into shared memory, eliminates the four
+//                          8x8 pivot blocks one after the other (same in-register Gauss-Jordan as the register
+//                          kernel), forms M' = -raw A11^{-1}, forward-eliminates the fused right-hand side and writes
+//                          the four factor panels;
+//   bigband_update_kernel  many CTAs per system: rank-32 update of the trailing window with FP64 tensor-core MMAs
+//                          (DMMA.8x8x4), one warp per 8-row block, operands straight from L2/L1; four extra CTAs
+//                          refill the recycled window rows from the stencil (assembly stays fused, the matrix is
+//                          never stored).
+// No cross-CTA synchronisation inside a kernel.  Replaces factorMUMPS / lu for the systems of mt2DTE.jl:47-55,
+// mt2DTM.jl:46-54 when the mesh is too wide for the register-window kernel.
+#pragma once
+#include "band_factor.cuh"
+
+namespace hmcmt {
+
+constexpr int kBigNBK = 4;          // 8-column blocks per panel launch
+constexpr int kBigPanStride = 9;    // complex entries per shared-memory panel row (8 + 1 pad: conflict-free 16-byte accesses)
+constexpr int kBigMaxT = 44;        // window of 44 tiles: b <= 8 * (44 - kBigNBK) = 320
+
+__host__ __device__ constexpr int big_T_for(int b) { return ((b + 7) / 8 + kBigNBK + 3) / 4 * 4; }
+// per-system workspace (complex entries): window R*R | M' [NBK][R][8] | raw [NBK][R][8] | rhs window [R]
+__host__ __device__ constexpr size_t big_work_entries(int T) {
+    return (size_t)(TS * T) * (TS * T) + 2 * (size_t)kBigNBK * (TS * T) * 8 + (size_t)(TS * T);
+}
+__host__ __device__ constexpr size_t big_panel_smem_bytes(int T) {
+    return ((size_t)kBigNBK * (TS * T) * kBigPanStride + (size_t)(TS * T) + 64 + 8) * sizeof(cplx) + 16;
+}
+
+struct BigView {
+    cplx *win, *mscr, *rscr, *ywin;
+    __device__ __forceinline__ BigView(cplx* base, int R) {
+        win = base;
+        mscr = win + (size_t)R * R;
+        rscr = mscr + (size_t)kBigNBK * R * 8;
+        ywin = rscr + (size_t)kBigNBK * R * 8;
+    }
+};
+
+// global block held by window slot `slot` when the window covers blocks s0 .. s0+T-1
+__device__ __forceinline__ int big_block_of_slot(int slot, int s0, int T) {
+    int a = slot - s0 % T;
+    if (a < 0) a += T;
+    return s0 + a;
+}
+
+// Pristine matrix entries for the 8 window rows of block `beta` (slot beta % T); the window covers blocks s0w .. s0w+T-1.
+// Cell convention: entry (row block bi >= column block bj) lives at win[(slot(bi)*8 + i) * R + slot(bj)*8 + j].
+__device__ __forceinline__ void big_fill_rows(const EntryProvider& prov, cplx* win, int T, int s0w, int beta, int tid, int nthr) {
+    const int R = TS * T, slot = beta % T;
+    for (int e = tid; e < TS * R; e += nthr) {
+        const int i = e / R, col = e - i * R;
+        const int bj = big_block_of_slot(col >> 3, s0w, T);
+        if (bj > beta) continue;
+        const int gi = beta * TS + i, gj = bj * TS + (col & 7);
+        win[(size_t)(slot * TS + i) * R + col] = prov.get(max(gi, gj), min(gi, gj));
+    }
+}
+
+// grid (T, nsys), 256 threads: initial window (blocks 0 .. T-1) and rhs window
+__global__ void __launch_bounds__(256)
+bigband_init_kernel(const BandSys* __restrict__ systems, BandDom dom, int T) {
+    const BandSys sys = systems[blockIdx.y];
+    const LocalDom L = LocalDom::make(dom, 0);
+    EntryProvider prov{sys.dr, sys.dm, sys.e1, sys.e2, sys.band, sys.omega, dom.b, L};
+    const int R = TS * T;
+    BigView v(sys.big, R);
+    big_fill_rows(prov, v.win, T, 0, (int)blockIdx.x, threadIdx.x, blockDim.x);
+    if (blockIdx.x == 0)
+        for (int r = threadIdx.x; r < R; r += blockDim.x)
+            v.ywin[r] = (sys.rhs && r < L.nLoc) ? prov.rhs_at(sys.rhs, r) : mk(0.0, 0.0);
+}
+
+// grid nsys, 2R threads (thread = window row r, column half h), dynamic smem = big_panel_smem_bytes(T)
+__global__ void __launch_bounds__(2 * TS * kBigMaxT, 1)
+bigband_panel_kernel(const BandSys* __restrict__ systems, BandDom dom, int T, int k) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int R = TS * T;
+    cplx* const pan = reinterpret_cast<cplx*>(smem_raw);                  // [NBK][R][kBigPanStride]
+    cplx* const ysh = pan + (size_t)kBigNBK * R * kBigPanStride;          // [R]
+    cplx* const ainv = ysh + R;                                           // [64] row-major A11^{-1}
+    cplx* const zsh = ainv + 64;                                          // [8]
+    int* const failp = reinterpret_cast<int*>(zsh + 8);
+
+    const BandSys sys = systems[blockIdx.x];
+    const LocalDom L = LocalDom::make(dom, 0);
+    EntryProvider prov{sys.dr, sys.dm, sys.e1, sys.e2, sys.band, sys.omega, dom.b, L};
+    BigView v(sys.big, R);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int r = tid >> 1, h = tid & 1;
+    const int s0 = k * kBigNBK;
+    const int nsub = min(kBigNBK, L.sTot - s0);
+    const int beta = big_block_of_slot(r >> 3, s0, T);
+    auto P = [&](int c, int row, int col) -> cplx& { return pan[((size_t)c * R + row) * kBigPanStride + col]; };
+
+    for (int c = 0; c < kBigNBK; ++c) {
+        const int pc = (s0 + c) % T;
+        const bool live = c < nsub && beta >= s0 + c;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) P(c, r, 4 * h + j) = live ? v.win[(size_t)r * R + pc * TS + 4 * h + j] : mk(0.0, 0.0);
+    }
+    if (h == 0) ysh[r] = v.ywin[r];
+    if (tid == 0) *failp = 0;
+    __syncthreads();
+
+    for (int c = 0; c < nsub; ++c) {
+        const int pc = (s0 + c) % T;
+        if (warp == 0) {
+            const int i = lane >> 2, t = lane & 3;
+            cplx a0 = P(c, pc * TS + i, 2 * t), a1 = P(c, pc * TS + i, 2 * t + 1);
+            bool bad = false;
+            gj_invert8(a0, a1, bad, i, t);
+            bad = __any_sync(0xffffffffu, bad);
+            if (bad && lane == 0) { *failp = 1; if (sys.status) *sys.status = kErrSingular; }
+            ainv[i * 8 + 2 * t] = a0;
+            ainv[i * 8 + 2 * t + 1] = a1;
+            cplx acc = a0 * ysh[pc * TS + 2 * t] + a1 * ysh[pc * TS + 2 * t + 1];
+#pragma unroll
+            for (int off = 1; off <= 2; off <<= 1) {
+                acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
+                acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+            }
+            if (!sys.rhs) acc = mk(0.0, 0.0);
+            if (t == 0) zsh[i] = acc;
+            cplx* dz = sys.ainvz[0] + (size_t)(s0 + c) * AZ;
+            dz[i * 8 + 2 * t] = a0;
+            dz[i * 8 + 2 * t + 1] = a1;
+            if (t == 0) dz[64 + i] = acc;
+        }
+        __syncthreads();
+        // M'[r][4h..4h+3] = -sum_k raw[r][k] A11^{-1}[k][4h+j]   (all rows: the partner exchange below must be warp-converged)
+        cplx raw[8], m[4], mf[8];
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) raw[kk] = P(c, r, kk);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            cplx acc = mk(0.0, 0.0);
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) cfma(acc, -raw[kk], ainv[kk * 8 + 4 * h + j]);
+            m[j] = acc;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const cplx o = mk(__shfl_xor_sync(0xffffffffu, m[j].x, 1), __shfl_xor_sync(0xffffffffu, m[j].y, 1));
+            mf[4 * h + j] = m[j];
+            mf[4 * (h ^ 1) + j] = o;
+        }
+        const bool below = beta > s0 + c;
+        if (below) {
+            for (int c2 = c + 1; c2 < nsub; ++c2) {
+                if (beta < s0 + c2) continue;
+                const int p2 = (s0 + c2) % T;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    cplx acc = P(c2, r, 4 * h + j);
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk) cfma(acc, mf[kk], P(c, p2 * TS + 4 * h + j, kk));
+                    P(c2, r, 4 * h + j) = acc;
+                }
+            }
+            if (h == 0 && sys.rhs) {
+                cplx acc = ysh[r];
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) cfma(acc, -raw[kk], zsh[kk]);
+                ysh[r] = acc;
+            }
+        }
+        // operands of the trailing update (plain [c][r][8] layout, L2-resident)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            v.mscr[((size_t)c * R + r) * 8 + 4 * h + j] = below ? m[j] : mk(0.0, 0.0);
+            v.rscr[((size_t)c * R + r) * 8 + 4 * h + j] = below ? raw[4 * h + j] : mk(0.0, 0.0);
+        }
+        // factor panel of macro-step s0+c in the solve kernels' image layout [re/im][kk][R][4]; rows of blocks already
+        // eliminated in this launch are outside the band of this panel: zero
+        {
+            double* img = sys.panels[0] + (size_t)(s0 + c) * panel_doubles(T);
+            const bool keep = beta >= s0 + c;
+            double2 re01 = make_double2(0.0, 0.0), re23 = re01, im01 = re01, im23 = re01;
+            if (keep) {
+                re01 = make_double2(raw[4 * h].x, raw[4 * h + 1].x); re23 = make_double2(raw[4 * h + 2].x, raw[4 * h + 3].x);
+                im01 = make_double2(raw[4 * h].y, raw[4 * h + 1].y); im23 = make_double2(raw[4 * h + 2].y, raw[4 * h + 3].y);
+            }
+            double2* pre = reinterpret_cast<double2*>(img + ((size_t)(0 * 2 + h) * R + r) * 4);
+            double2* pim = reinterpret_cast<double2*>(img + ((size_t)(1 * 2 + h) * R + r) * 4);
+            pre[0] = re01; pre[1] = re23;
+            pim[0] = im01; pim[1] = im23;
+        }
+        __syncthreads();
+    }
+    // rhs window: the slots of the eliminated blocks now hold blocks +T
+    if (h == 0) {
+        cplx yv = ysh[r];
+        if (beta < s0 + nsub) {
+            const int gr = (beta + T) * TS + (r & 7);
+            yv = (sys.rhs && gr < L.nLoc) ? prov.rhs_at(sys.rhs, gr) : mk(0.0, 0.0);
+        }
+        v.ywin[r] = yv;
+    }
+}
+
+// grid (nStrips + kBigNBK, nsys), 256 threads.  CTAs x < nStrips: warp w owns trailing-window position 8*x + w (one 8-row block)
+// and sweeps the column blocks up to its own; CTAs x >= nStrips refill one recycled 8-row block from the stencil.
+__global__ void __launch_bounds__(256)
+bigband_update_kernel(const BandSys* __restrict__ systems, BandDom dom, int T, int k, int nStrips) {
+    const BandSys sys = systems[blockIdx.y];
+    const int R = TS * T;
+    BigView v(sys.big, R);
+    const int s0 = k * kBigNBK, w0 = s0 + kBigNBK;      // first block of the trailing window
+    if ((int)blockIdx.x >= nStrips) {
+        const LocalDom L = LocalDom::make(dom, 0);
+        EntryProvider prov{sys.dr, sys.dm, sys.e1, sys.e2, sys.band, sys.omega, dom.b, L};
+        big_fill_rows(prov, v.win, T, w0, s0 + ((int)blockIdx.x - nStrips) + T, threadIdx.x, blockDim.x);
+        return;
+    }
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int warp = __shfl_sync(0xffffffffu, (int)threadIdx.x >> 5, 0);
+    const int aX = (int)blockIdx.x * 8 + warp;
+    if (aX >= T - kBigNBK) return;
+    const int slotX = (w0 + aX) % T;
+    double are[kBigNBK][2], aim[kBigNBK][2];
+#pragma unroll
+    for (int c = 0; c < kBigNBK; ++c)
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+            const cplx a = __ldg(&v.mscr[((size_t)c * R + slotX * TS + g) * 8 + 4 * kk + t]);
+            are[c][kk] = a.x; aim[c][kk] = a.y;
+        }
+    for (int aY = 0; aY <= aX; ++aY) {
+        const int slotY = (w0 + aY) % T;
+        double bre[kBigNBK][2], bim[kBigNBK][2];
+#pragma unroll
+        for (int c = 0; c < kBigNBK; ++c)
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+                const cplx bv = __ldg(&v.rscr[((size_t)c * R + slotY * TS + g) * 8 + 4 * kk + t]);
+                bre[c][kk] = bv.x; bim[c][kk] = bv.y;
+            }
+        cplx* cp = v.win + (size_t)(slotX * TS + g) * R + slotY * TS + 2 * t;
+        const cplx c0 = cp[0], c1 = cp[1];
+        double cre[2] = {c0.x, c1.x}, cim[2] = {c0.y, c1.y}, t1[2] = {0.0, 0.0}, t2[2] = {0.0, 0.0};
+#pragma unroll
+        for (int c = 0; c < kBigNBK; ++c)
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+                dmma884(cre, are[c][kk], bre[c][kk]);
+                dmma884(cim, are[c][kk], bim[c][kk]);
+                dmma884(t1, -aim[c][kk], bim[c][kk]);
+                dmma884(t2, aim[c][kk], bre[c][kk]);
+            }
+        cp[0] = mk(cre[0] + t1[0], cim[0] + t2[0]);
+        cp[1] = mk(cre[1] + t1[1], cim[1] + t2[1]);
+    }
+}
+
+}  // namespace hmcmt

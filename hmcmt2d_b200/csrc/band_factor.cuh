@@ -56,6 +56,7 @@ struct BandSys {
     double* panels[2];   // per half (rank): [steps][16*R] doubles: re/im x kk x R x 4 (exactly the smem operand layout)
     cplx* ainvz[2];      // per half (rank): [steps][72]: A11^{-1} row-major, then z = A11^{-1} * (forward-eliminated rhs block)
     cplx* wexp;          // split only: hand-over scratch [2][R*R] window images, [2][R] rhs windows, [R] separator solution
+    cplx* big;           // large-bandwidth path only (band_big.cuh): per-system workspace of big_work_entries(T) entries
     int* status;         // 0 ok, -10 zero/NaN pivot block
 };
 
@@ -208,6 +209,49 @@ struct EntryProvider {
         if (q >= 0 && !(kind == 1 && L.rank == 1)) x[q] = v;
     }
 };
+
+// In-register inversion of an 8x8 complex-symmetric block by one warp, pivot-free.  Lane 4*i + t holds A[i][2t], A[i][2t+1]
+// on entry and A^{-1}[i][2t], A^{-1}[i][2t+1] on return.
+// Fraction-free Gauss-Jordan (validated in numpy): rows i != k take  row_i <- (p row_i - a_ik row_k) 2^-e
+// with an exact power-of-two rescale, so no reciprocal sits on the 8-pivot dependency chain; every row carries
+// its accumulated scale q_i and the true inverse is  a_ij / q_i, formed with one reciprocal per row at the end.
+__device__ __forceinline__ void gj_invert8(cplx& a0, cplx& a1, bool& bad, const int i, const int t) {
+    const int j0 = 2 * t;
+    cplx q = mk(1.0, 0.0);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int srcRow = 4 * k + t, srcCol = 4 * i + (k >> 1), srcPiv = 4 * k + (k >> 1);
+        const cplx mine = (k & 1) ? a1 : a0;
+        const cplx pk = mk(__shfl_sync(0xffffffffu, mine.x, srcPiv), __shfl_sync(0xffffffffu, mine.y, srcPiv));
+        const cplx f = mk(__shfl_sync(0xffffffffu, mine.x, srcCol), __shfl_sync(0xffffffffu, mine.y, srcCol));
+        const cplx ck = mk(__shfl_sync(0xffffffffu, q.x, 4 * k), __shfl_sync(0xffffffffu, q.y, 4 * k));
+        cplx r0 = mk(__shfl_sync(0xffffffffu, a0.x, srcRow), __shfl_sync(0xffffffffu, a0.y, srcRow));
+        cplx r1 = mk(__shfl_sync(0xffffffffu, a1.x, srcRow), __shfl_sync(0xffffffffu, a1.y, srcRow));
+        if (j0 == k) r0 = ck;                       // slot (k,k) switches to the right-hand block: value c_k
+        if (j0 + 1 == k) r1 = ck;
+        const double mag = fmax(fabs(pk.x), fabs(pk.y));
+        if (!(mag > 1e-290) || !(mag < 1e290)) bad = true;
+        const int eb = (__double2hiint(mag) >> 20) & 0x7ff;
+        const double sc = __hiloint2double((2046 - eb) << 20, 0);          // 2^-(exponent of the pivot), exact
+        const cplx ps = mk(pk.x * sc, pk.y * sc), fs = mk(f.x * sc, f.y * sc);
+        if (i == k) {
+            a0 = r0; a1 = r1; q = pk;
+        } else {
+            const cplx b0 = (j0 == k) ? mk(0.0, 0.0) : a0, b1 = (j0 + 1 == k) ? mk(0.0, 0.0) : a1;
+            cplx n0 = ps * b0, n1 = ps * b1;
+            cfma(n0, -fs, r0);
+            cfma(n1, -fs, r1);
+            a0 = n0; a1 = n1;
+            q = ps * q;
+        }
+    }
+    const double den = fma(q.x, q.x, q.y * q.y);
+    if (!(den > 0.0) || isinf(den)) bad = true;
+    const double iden = __drcp_rn(den);
+    const cplx qi = mk(q.x * iden, -q.y * iden);
+    a0 = a0 * qi;
+    a1 = a1 * qi;
+}
 
 // grid = nsys CTAs (FM_FULL, FM_SEP) or 2*nsys CTAs (FM_OWN, FM_BACK: CTA = 2*system + rank), block = FactorCfg<T>::NTHREADS,
 // dynamic smem = sizeof(FactorSmem<T>)
@@ -493,45 +537,7 @@ band_factor_kernel(const BandSys* __restrict__ systems, BandDom dom, int mode) {
         const int i = g, j0 = 2 * t;
         cplx a0, a1;                                        // A11^{-1}[i][j0], [i][j0+1] of the CURRENT panel
         bool bad = false;
-        // Fraction-free Gauss-Jordan (validated in numpy): rows i != k take  row_i <- (p row_i - a_ik row_k) 2^-e
-        // with an exact power-of-two rescale, so no reciprocal sits on the 8-pivot dependency chain; every row carries
-        // its accumulated scale q_i and the true inverse is  a_ij / q_i, formed with one reciprocal per row at the end.
-        auto invert = [&]() {
-            cplx q = mk(1.0, 0.0);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int srcRow = 4 * k + t, srcCol = 4 * i + (k >> 1), srcPiv = 4 * k + (k >> 1);
-                const cplx mine = (k & 1) ? a1 : a0;
-                const cplx pk = mk(__shfl_sync(0xffffffffu, mine.x, srcPiv), __shfl_sync(0xffffffffu, mine.y, srcPiv));
-                const cplx f = mk(__shfl_sync(0xffffffffu, mine.x, srcCol), __shfl_sync(0xffffffffu, mine.y, srcCol));
-                const cplx ck = mk(__shfl_sync(0xffffffffu, q.x, 4 * k), __shfl_sync(0xffffffffu, q.y, 4 * k));
-                cplx r0 = mk(__shfl_sync(0xffffffffu, a0.x, srcRow), __shfl_sync(0xffffffffu, a0.y, srcRow));
-                cplx r1 = mk(__shfl_sync(0xffffffffu, a1.x, srcRow), __shfl_sync(0xffffffffu, a1.y, srcRow));
-                if (j0 == k) r0 = ck;                       // slot (k,k) switches to the right-hand block: value c_k
-                if (j0 + 1 == k) r1 = ck;
-                const double mag = fmax(fabs(pk.x), fabs(pk.y));
-                if (!(mag > 1e-290) || !(mag < 1e290)) bad = true;
-                const int eb = (__double2hiint(mag) >> 20) & 0x7ff;
-                const double sc = __hiloint2double((2046 - eb) << 20, 0);          // 2^-(exponent of the pivot), exact
-                const cplx ps = mk(pk.x * sc, pk.y * sc), fs = mk(f.x * sc, f.y * sc);
-                if (i == k) {
-                    a0 = r0; a1 = r1; q = pk;
-                } else {
-                    const cplx b0 = (j0 == k) ? mk(0.0, 0.0) : a0, b1 = (j0 + 1 == k) ? mk(0.0, 0.0) : a1;
-                    cplx n0 = ps * b0, n1 = ps * b1;
-                    cfma(n0, -fs, r0);
-                    cfma(n1, -fs, r1);
-                    a0 = n0; a1 = n1;
-                    q = ps * q;
-                }
-            }
-            const double den = fma(q.x, q.x, q.y * q.y);
-            if (!(den > 0.0) || isinf(den)) bad = true;
-            const double iden = __drcp_rn(den);
-            const cplx qi = mk(q.x * iden, -q.y * iden);
-            a0 = a0 * qi;
-            a1 = a1 * qi;
-        };
+        auto invert = [&]() { gj_invert8(a0, a1, bad, g, t); };
         auto publish = [&](int buf) {      // -A11^{-1} as B-fragments, plain A11^{-1} for the store
             // B-fragment layout wants plane[kk][n][tt] = -Ainv[4kk+tt][n]; Ainv is symmetric, so write -Ainv[i][j] at [j>>2][i][j&3]
             *reinterpret_cast<double2*>(&sm.nainv[buf][0][j0 >> 2][i][j0 & 3]) = make_double2(-a0.x, -a1.x);

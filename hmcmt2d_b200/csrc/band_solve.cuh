@@ -1,7 +1,7 @@
 // Forward + backward substitution with the block-LDL^T factor written by band_factor_kernel.
 // Replaces `applyMUMPS(Ainv, rhs)` / `Ainv \ rhs` for the adjoint solve (compJacTMatVec.jl:220-224,
 // 291-295) and `solve_mumps_cmplx_` (MUMPSfuncs.jl:123-132).  HBM-bound: streams the 16*8T*8-byte
-// panel images with TMA bulk loads (kSolveStages panels in flight on mbarriers) — 2 reads of the
+// panel images with TMA bulk loads (solve_stages(T) panels in flight on mbarriers) — 2 reads of the
 // factor per right-hand side.  Split systems use the same launch sequence as the factorisation
 // (FM_OWN: forward sweep of both halves, FM_SEP: separator forward + backward, FM_BACK: backward
 // sweep of both halves), hand-over through global scratch in stream order.
@@ -19,20 +19,25 @@ struct SolveJob {
     cplx* wexp;                // split only: hand-over scratch (the [2][R] rhs windows and [R] separator solution after the window images)
 };
 
-constexpr int kSolveStages = 8;
+// TMA stages in flight: 8 for the register-window sizes (14 KB panels), fewer for the large-bandwidth windows (up to 45 KB)
+__host__ __device__ constexpr int solve_stages(int T) { return T <= 14 ? 8 : (T <= 28 ? 5 : 4); }
 constexpr int kSolveThreads = 256;
+// extra launch mode of the solve kernel: backward sweep only, z read from the factor's [A11^{-1} | z] stream (the fused
+// forward system of the large-bandwidth factorisation, band_big.cuh)
+constexpr int SM_BACKZ = 4;
 
 template <int T>
 struct SolveSmem {
     static constexpr int R = TS * T;
-    double stage[kSolveStages][2][2][R][4];
-    cplx ainv[kSolveStages][64];
+    static constexpr int NST = solve_stages(T);
+    double stage[NST][2][2][R][4];
+    cplx ainv[NST][64];
     cplx y[R];
     cplx zv[8];
     cplx part[kSolveThreads / 32][8];
     cplx ringRhs[kRing][8];     // rhs rows entering the window (forward sweep), prefetched kPre steps ahead
     cplx ringZ[kRing][8];       // z of upcoming panels (backward sweep)
-    uint64_t mbar[kSolveStages];
+    uint64_t mbar[NST];
 };
 
 __device__ __forceinline__ cplx local_rhs(const LocalDom& L, const cplx* rhs, int g) {
@@ -50,7 +55,7 @@ __device__ __forceinline__ void local_store(const LocalDom& L, cplx* x, int g, c
 template <int T>
 __global__ void __launch_bounds__(kSolveThreads, 1)
 band_solve_kernel(const SolveJob* __restrict__ jobs, BandDom dom, int mode) {
-    constexpr int R = TS * T, NTHR = kSolveThreads, NST = kSolveStages;
+    constexpr int R = TS * T, NTHR = kSolveThreads, NST = solve_stages(T);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SolveSmem<T>& sm = *reinterpret_cast<SolveSmem<T>*>(smem_raw);
     const bool paired = (mode == FM_OWN || mode == FM_BACK);
@@ -72,7 +77,7 @@ band_solve_kernel(const SolveJob* __restrict__ jobs, BandDom dom, int mode) {
 
     // rhs may alias x: all rhs reads happen in the FM_OWN / FM_FULL forward sweep (and, for the separator rows, come through
     // the exported windows), all x writes of a split system in the later FM_SEP / FM_BACK launches.
-    if (mode != FM_BACK)
+    if (mode != FM_BACK && mode != SM_BACKZ)
         for (int i_b = 0; i_b < R; i_b += NTHR) if (const int i = i_b + tid; i < R) {
             cplx v = mk(0.0, 0.0);
             if (mode == FM_SEP) {
@@ -85,7 +90,7 @@ band_solve_kernel(const SolveJob* __restrict__ jobs, BandDom dom, int mode) {
         for (int q = 0; q < NST; ++q) mbar_init(&sm.mbar[q], 1);
         fence_mbar_init();
     }
-    if (tid >= 32 && tid < 40)
+    if (tid >= 32 && tid < 40 && mode != FM_BACK && mode != SM_BACKZ)
         for (int q = 0; q < kPre; ++q) {
             int gnew = (sBeg + q + T) * TS + (tid - 32);
             sm.ringRhs[(sBeg + q) % kRing][tid - 32] = (gnew < nLoc) ? local_rhs(L, job.rhs, gnew) : mk(0.0, 0.0);
@@ -144,18 +149,19 @@ band_solve_kernel(const SolveJob* __restrict__ jobs, BandDom dom, int mode) {
     };
     // ---------------- backward over steps sHi-1 .. sLo:  x_p = z_s - A11^{-1} raw_s^T x_rest ----------------
     constexpr int NRG = NTHR / 8;
+    auto zsrc = [&](int s, int i) { return mode == SM_BACKZ ? ainvz[(size_t)s * AZ + 64 + i] : zbuf[(size_t)s * 8 + i]; };
     auto backward_range = [&](int sHi, int sLo) {
         const int n = sHi - sLo;
         if (tid == 0)
             for (int k = 0; k < NST - 1 && k < n; ++k) issue(sHi - 1 - k, itBase + k);
         if (tid >= 32 && tid < 40)
-            for (int q = 0; q < kPre && q < n; ++q) sm.ringZ[q % kRing][tid - 32] = zbuf[(size_t)(sHi - 1 - q) * 8 + (tid - 32)];
+            for (int q = 0; q < kPre && q < n; ++q) sm.ringZ[q % kRing][tid - 32] = zsrc(sHi - 1 - q, tid - 32);
         cta_sync();
         for (int k = 0; k < n; ++k) {
             const int s = sHi - 1 - k, p = s % T, it = itBase + k, st = it % NST;
             if (tid == 0 && k + NST - 1 < n) issue(s - (NST - 1), it + NST - 1);
             cplx prez = mk(0.0, 0.0);
-            if (tid >= 32 && tid < 40 && k + kPre < n) prez = zbuf[(size_t)(s - kPre) * 8 + (tid - 32)];
+            if (tid >= 32 && tid < 40 && k + kPre < n) prez = zsrc(s - kPre, tid - 32);
             mbar_wait(&sm.mbar[st], (uint32_t)((it / NST) & 1));
             const int c = tid & 7, rg = tid >> 3;
             cplx acc = mk(0.0, 0.0);
@@ -213,7 +219,7 @@ band_solve_kernel(const SolveJob* __restrict__ jobs, BandDom dom, int mode) {
     for (int i_b = 0; i_b < R; i_b += NTHR) if (const int i = i_b + tid; i < R)
         sm.y[i] = (mode == FM_BACK) ? xsep[rel(i >> 3, L.sOwn) * TS + (i & 7)] : mk(0.0, 0.0);
     cta_sync();
-    if (mode == FM_FULL) {
+    if (mode == FM_FULL || mode == SM_BACKZ) {
         backward_range(L.sTot, 0);
     } else if (mode == FM_SEP) {
         backward_range(L.sTot, L.sOwn);

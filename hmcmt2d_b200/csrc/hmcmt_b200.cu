@@ -10,6 +10,7 @@
 #include "../../include/hmcmt_b200.h"
 #include "band_factor.cuh"
 #include "band_solve.cuh"
+#include "band_big.cuh"
 #include "mt_kernels.cuh"
 
 using namespace hmcmt;
@@ -62,11 +63,11 @@ struct hmcmt_plan {
     std::vector<int> h_packed2full;      // [nData] full index (without chain) of each packed datum
     // device buffers
     DevBuf<double> yLen, zLen, zNode, freqs, fdy1, fdy2, wL, wR, bg, wmVal, wd, m, p, mref, sigma, meanSig, planes;
-    DevBuf<double> Gpart, phiPart, phi, gsig, gdata, gtotal, energies, panels, curM, curP, chainScal, zmom;
+    DevBuf<double> xbuf, Gpart, phiPart, phi, gsig, gdata, gtotal, energies, panels, curM, curP, chainScal, zmom;
     DevBuf<int> fid, iL, iR, cell2act, act2cell, wmPtr, wmIdx, status, driftFlag, packed2full, Lsteps;
-    DevBuf<cplx> obs, bc, bcs, rhs, x, F, lam, Lam, srows, qrow, scratch, predFull, ainvz, zadj, vin, predPacked, wexp;
+    DevBuf<cplx> obs, bc, bcs, rhs, x, F, lam, Lam, srows, qrow, scratch, predFull, ainvz, zadj, vin, predPacked, wexp, bigWork;
     DevBuf<BandSys> sysDesc;
-    DevBuf<SolveJob> jobs;
+    DevBuf<SolveJob> jobs, fwdJobs;                 // fwdJobs: backward sweeps of the fused forward systems (large-bandwidth path)
     // pinned staging for the host-buffer entry points
     double* pin = nullptr;
     size_t pinBytes = 0;
@@ -125,15 +126,75 @@ int launch_solve_T(cudaStream_t st, const SolveJob* jobs, int njobs, const BandD
 
 }  // namespace
 
+namespace {
+template <int T>
+int launch_solve_mode_T(cudaStream_t st, const SolveJob* jobs, int njobs, const BandDom& dom, int mode) {
+    static bool configured = false;
+    size_t smem = sizeof(SolveSmem<T>);
+    if (!configured) {
+        HMCMT_CUDA_TRY(cudaFuncSetAttribute(band_solve_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    band_solve_kernel<T><<<njobs, kSolveThreads, smem, st>>>(jobs, dom, mode);
+    HMCMT_CUDA_TRY(cudaGetLastError());
+    return kOk;
+}
+// large-bandwidth windows (band_big.cuh): one unsplit sweep per system
+int launch_solve_big(cudaStream_t st, int T, const SolveJob* jobs, int njobs, const BandDom& dom, int mode) {
+    switch (T) {
+        case 16: return launch_solve_mode_T<16>(st, jobs, njobs, dom, mode);
+        case 20: return launch_solve_mode_T<20>(st, jobs, njobs, dom, mode);
+        case 24: return launch_solve_mode_T<24>(st, jobs, njobs, dom, mode);
+        case 28: return launch_solve_mode_T<28>(st, jobs, njobs, dom, mode);
+        case 32: return launch_solve_mode_T<32>(st, jobs, njobs, dom, mode);
+        case 36: return launch_solve_mode_T<36>(st, jobs, njobs, dom, mode);
+        case 40: return launch_solve_mode_T<40>(st, jobs, njobs, dom, mode);
+        case 44: return launch_solve_mode_T<44>(st, jobs, njobs, dom, mode);
+        default: return kErrArg;
+    }
+}
+// Large-bandwidth factorisation: init, then one panel launch + one trailing-update launch per 32 columns, then the
+// backward sweep of the fused forward system (fwdJobs, optional).
+int launch_factor_big(cudaStream_t st, int T, const BandSys* sys, int nsys, const BandDom& dom, const SolveJob* fwdJobs, int* nLaunches) {
+    static bool configured = false;
+    if (!configured) {
+        HMCMT_CUDA_TRY(cudaFuncSetAttribute(bigband_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)big_panel_smem_bytes(kBigMaxT)));
+        configured = true;
+    }
+    const int R = TS * T, sTot = (dom.N + TS - 1) / TS, nPanels = (sTot + kBigNBK - 1) / kBigNBK;
+    const int nStrips = (T - kBigNBK + 7) / 8;
+    const size_t smem = big_panel_smem_bytes(T);
+    bigband_init_kernel<<<dim3(T, nsys), 256, 0, st>>>(sys, dom, T);
+    for (int k = 0; k < nPanels; ++k) {
+        bigband_panel_kernel<<<nsys, 2 * R, smem, st>>>(sys, dom, T, k);
+        if (k + 1 < nPanels) bigband_update_kernel<<<dim3(nStrips + kBigNBK, nsys), 256, 0, st>>>(sys, dom, T, k, nStrips);
+    }
+    HMCMT_CUDA_TRY(cudaGetLastError());
+    int n = 2 * nPanels;
+    if (fwdJobs) {
+        int rc = launch_solve_big(st, T, fwdJobs, nsys, dom, SM_BACKZ);
+        if (rc) return rc;
+        ++n;
+    }
+    if (nLaunches) *nLaunches = n;
+    return kOk;
+}
+}  // namespace
+
 namespace hmcmt {
 // shared with mumps_shim.cu
 int round_T(int b) {
+    if (b > 8 * 14 - 8) return big_T_for(b);      // window in global memory (band_big.cuh)
     int T = band_T_for(b);
     if (T < 2) T = 2;
     if (T & 1) ++T;
     return T;
 }
-int launch_factor(cudaStream_t st, int T, const BandSys* sys, int nsys, const BandDom& dom) {
+// fwdJobs: backward-sweep jobs of the fused forward systems, needed by the large-bandwidth path only (the register-window
+// kernel back-substitutes inside the factor launch).  nLaunches (optional) receives the number of kernels launched.
+int launch_factor(cudaStream_t st, int T, const BandSys* sys, int nsys, const BandDom& dom, const SolveJob* fwdJobs, int* nLaunches) {
+    if (nLaunches) *nLaunches = dom.split ? 3 : 1;
     switch (T) {
         case 2: return launch_factor_T<2>(st, sys, nsys, dom);
         case 4: return launch_factor_T<4>(st, sys, nsys, dom);
@@ -142,7 +203,9 @@ int launch_factor(cudaStream_t st, int T, const BandSys* sys, int nsys, const Ba
         case 10: return launch_factor_T<10>(st, sys, nsys, dom);
         case 12: return launch_factor_T<12>(st, sys, nsys, dom);
         case 14: return launch_factor_T<14>(st, sys, nsys, dom);
-        default: return kErrArg;
+        default:
+            if (T > 14 && T <= kBigMaxT && T % 4 == 0 && !dom.split) return launch_factor_big(st, T, sys, nsys, dom, fwdJobs, nLaunches);
+            return kErrArg;
     }
 }
 int launch_solve(cudaStream_t st, int T, const SolveJob* jobs, int njobs, const BandDom& dom) {
@@ -154,10 +217,13 @@ int launch_solve(cudaStream_t st, int T, const SolveJob* jobs, int njobs, const 
         case 10: return launch_solve_T<10>(st, jobs, njobs, dom);
         case 12: return launch_solve_T<12>(st, jobs, njobs, dom);
         case 14: return launch_solve_T<14>(st, jobs, njobs, dom);
-        default: return kErrArg;
+        default:
+            if (T > 14 && !dom.split) return launch_solve_big(st, T, jobs, njobs, dom, FM_FULL);
+            return kErrArg;
     }
 }
-int max_band_T() { return 14; }
+int max_band_T() { return kBigMaxT; }
+size_t big_work_bytes(int T) { return T > 14 ? big_work_entries(T) * sizeof(cplx) : 0; }
 }  // namespace hmcmt
 
 namespace {
@@ -252,6 +318,29 @@ k_accept(int nAC, int nData, int it, int nsamples, const double* __restrict__ ua
     }
 }
 
+// Frequency-sharded evaluation: every rank holds a subset of the frequencies.  The data gradient and the
+// data misfit are sums over frequencies, so each rank packs its partial [gdata(nAC) | phi_d] per chain into one exchange
+// buffer, the host all-reduces it (NCCL over NVLink), and the prior gradient — which must be counted once — is added after.
+__global__ void k_pack_exchange(int nAC, const double* __restrict__ gdata, const double* __restrict__ phi, double* __restrict__ xbuf) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x, ch = blockIdx.y;
+    if (a < nAC) xbuf[(size_t)ch * (nAC + 1) + a] = gdata[(size_t)ch * nAC + a];
+    if (a == nAC) xbuf[(size_t)ch * (nAC + 1) + nAC] = phi[ch];
+}
+__global__ void k_unpack_exchange(int nAC, const double* __restrict__ xbuf, const double* __restrict__ m, const double* __restrict__ mref,
+                                  const int* __restrict__ wmPtr, const int* __restrict__ wmIdx, const double* __restrict__ wmVal,
+                                  double beta, double* __restrict__ gdata, double* __restrict__ gtotal, double* __restrict__ phi) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x, ch = blockIdx.y;
+    if (a == nAC) phi[ch] = xbuf[(size_t)ch * (nAC + 1) + nAC];
+    if (a >= nAC) return;
+    const double* mm = m + (size_t)ch * nAC;
+    const double* mr = mref + (size_t)ch * nAC;
+    double pr = 0.0;
+    for (int k = wmPtr[a]; k < wmPtr[a + 1]; ++k) { int j = wmIdx[k]; pr += wmVal[k] * (mm[j] - mr[j]); }
+    const double gd = xbuf[(size_t)ch * (nAC + 1) + a];
+    gdata[(size_t)ch * nAC + a] = gd;
+    gtotal[(size_t)ch * nAC + a] = gd + beta * pr;
+}
+
 int ensure_pin(hmcmt_plan* pl, size_t bytes) {
     if (pl->pinBytes >= bytes) return kOk;
     if (pl->pin) cudaFreeHost(pl->pin);
@@ -299,9 +388,10 @@ int compute_step(hmcmt_plan* pl, bool wantAdjoint, const cplx* vin) {
         }
         auto& ev = pl->factorEvents[pl->factorEventsUsed++];
         HMCMT_CUDA_TRY(cudaEventRecord(ev.first, st));
-        int rc = launch_factor(st, pl->T, pl->sysDesc.p, nSys, pl->dom);
+        int nl = 0;
+        int rc = launch_factor(st, pl->T, pl->sysDesc.p, nSys, pl->dom, pl->fwdJobs.p, &nl);
         if (rc) return rc;
-        pl->launches += pl->dom.split ? 3 : 1;
+        pl->launches += nl;
         ++pl->factorLaunches;
         HMCMT_CUDA_TRY(cudaEventRecord(ev.second, st));
     }
@@ -383,7 +473,7 @@ int hmcmt_plan_create(const hmcmt_problem* pr, hmcmt_plan** out) {
         // two CTAs per system when there are enough lines: halves the sequential pivot chain
         const char* env = std::getenv("HMCMT_SPLIT");
         int want = env ? std::atoi(env) : 1;
-        pl->dom = BandDom{M.N, M.nf, pl->b, M.nl, (want && M.nl >= 9) ? 1 : 0, M.nl / 2};
+        pl->dom = BandDom{M.N, M.nf, pl->b, M.nl, (want && M.nl >= 9 && pl->T <= 14) ? 1 : 0, M.nl / 2};
         LocalDom L0 = LocalDom::make(pl->dom, 0);
         pl->steps0 = L0.sTot;
         pl->steps1 = pl->dom.split ? LocalDom::make(pl->dom, 1).sOwn : 0;
@@ -391,7 +481,7 @@ int hmcmt_plan_create(const hmcmt_problem* pr, hmcmt_plan** out) {
     }
     if (M.nf < 2) { delete pl; return kErrArg; }
     if (pl->T > max_band_T()) {
-        fprintf(stderr, "[hmcmt_b200] half-bandwidth %d needs a tile window T=%d > %d: not supported by the register-window kernel yet\n",
+        fprintf(stderr, "[hmcmt_b200] half-bandwidth %d needs a tile window T=%d > %d: not supported\n",
                 pl->b, pl->T, max_band_T());
         delete pl;
         return kErrArg;
@@ -474,13 +564,16 @@ int hmcmt_plan_create(const hmcmt_problem* pr, hmcmt_plan** out) {
     ok(pl->srows.alloc(nSys * 2 * (ny + 1))); ok(pl->qrow.alloc(nSys * ny));
     ok(pl->scratch.alloc(nSys * 3 * prof_stride(nz)));
     ok(pl->Gpart.alloc(nSys * M.nCell)); ok(pl->phiPart.alloc(nSys)); ok(pl->phi.alloc(nCh));
-    ok(pl->gsig.alloc(nCh * pr->nAC)); ok(pl->gdata.alloc(nCh * pr->nAC)); ok(pl->gtotal.alloc(nCh * pr->nAC)); ok(pl->energies.alloc(nCh * 2));
+    ok(pl->gsig.alloc(nCh * pr->nAC)); ok(pl->gdata.alloc(nCh * pr->nAC)); ok(pl->gtotal.alloc(nCh * pr->nAC)); ok(pl->xbuf.alloc((size_t)nCh * (pl->nAC + 1))); ok(pl->energies.alloc(nCh * 2));
     ok(pl->chainScal.alloc(nCh * 4));
     ok(pl->predFull.alloc(nCh * pl->nFull)); ok(pl->vin.alloc(nCh * pl->nFull)); ok(pl->predPacked.alloc(nCh * pr->nData));
     ok(pl->panels.alloc(nSys * (size_t)pl->S * panel_doubles(pl->T)));
     ok(pl->ainvz.alloc(nSys * (size_t)pl->S * AZ)); ok(pl->zadj.alloc(nSys * (size_t)pl->S * 8));
     const size_t wexpN = split_scratch_entries(TS * pl->T);
     ok(pl->wexp.alloc(pl->dom.split ? nSys * wexpN : 0));
+    const size_t bigN = pl->T > 14 ? big_work_entries(pl->T) : 0;
+    ok(pl->bigWork.alloc(nSys * bigN));
+    ok(pl->fwdJobs.alloc(bigN ? nSys : 0));
     ok(pl->status.alloc(nSys)); ok(pl->driftFlag.alloc(1)); ok(pl->Lsteps.alloc(nCh));
     ok(pl->sysDesc.alloc(nSys)); ok(pl->jobs.alloc(nSys));
     if (rc) { hmcmt_destroy(pl); return rc; }
@@ -493,7 +586,7 @@ int hmcmt_plan_create(const hmcmt_problem* pr, hmcmt_plan** out) {
     pl->rx = RxDev{pr->nRx, pl->fid.p, pl->fdy1.p, pl->fdy2.p, pl->iL.p, pl->iR.p, pl->wL.p, pl->wR.p};
     // per-system descriptors
     std::vector<BandSys> sd(nSys);
-    std::vector<SolveJob> jb(nSys);
+    std::vector<SolveJob> jb(nSys), jfw(nSys);
     for (size_t s = 0; s < nSys; ++s) {
         int f = (int)(s % pl->nFreq);
         int t = (int)(s / pl->nFreq);
@@ -509,6 +602,7 @@ int hmcmt_plan_create(const hmcmt_problem* pr, hmcmt_plan** out) {
         d.ainvz[0] = pl->ainvz.p + s * (size_t)pl->S * AZ;
         d.ainvz[1] = d.ainvz[0] + (size_t)pl->steps0 * AZ;
         d.wexp = pl->dom.split ? pl->wexp.p + s * wexpN : nullptr;
+        d.big = bigN ? pl->bigWork.p + s * bigN : nullptr;
         d.x = pl->x.p + s * N;
         d.status = pl->status.p + s;
         SolveJob& j = jb[s];
@@ -518,11 +612,25 @@ int hmcmt_plan_create(const hmcmt_problem* pr, hmcmt_plan** out) {
         j.zbuf[0] = pl->zadj.p + s * (size_t)pl->S * 8;
         j.zbuf[1] = j.zbuf[0] + (size_t)pl->steps0 * 8;
         j.wexp = d.wexp;
+        SolveJob& jf = jfw[s];
+        jf = j;
+        jf.rhs = nullptr; jf.x = d.x;
     }
     if (cudaMemcpy(pl->sysDesc.p, sd.data(), sizeof(BandSys) * nSys, cudaMemcpyHostToDevice) != cudaSuccess ||
-        cudaMemcpy(pl->jobs.p, jb.data(), sizeof(SolveJob) * nSys, cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaMemcpy(pl->jobs.p, jb.data(), sizeof(SolveJob) * nSys, cudaMemcpyHostToDevice) != cudaSuccess ||
+        (pl->fwdJobs.p && cudaMemcpy(pl->fwdJobs.p, jfw.data(), sizeof(SolveJob) * nSys, cudaMemcpyHostToDevice) != cudaSuccess)) {
         hmcmt_destroy(pl);
         return kErrCuda;
+    }
+    {
+        // wide meshes: the receiver / contraction kernels stage whole node rows in shared memory
+        const size_t rxSmem = (size_t)(6 * (M.ny + 1) + 3 * M.ny) * sizeof(cplx);
+        const size_t cSmem = (size_t)(5 * M.nz + (M.ny - 1) + M.ny) * sizeof(cplx);
+        if ((rxSmem > 48 * 1024 && cudaFuncSetAttribute(k_rx_adjoint, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rxSmem) != cudaSuccess) ||
+            (cSmem > 48 * 1024 && cudaFuncSetAttribute(k_contract, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cSmem) != cudaSuccess)) {
+            hmcmt_destroy(pl);
+            return kErrArg;
+        }
     }
     if (cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&pl->side, cudaStreamNonBlocking) != cudaSuccess ||
@@ -555,7 +663,7 @@ void hmcmt_destroy(hmcmt_plan* pl) {
     pl->driftFlag.release(); pl->packed2full.release(); pl->Lsteps.release(); pl->obs.release(); pl->bc.release(); pl->bcs.release();
     pl->rhs.release(); pl->x.release(); pl->F.release(); pl->lam.release(); pl->Lam.release(); pl->srows.release(); pl->qrow.release();
     pl->scratch.release(); pl->predFull.release(); pl->ainvz.release(); pl->zadj.release(); pl->vin.release();
-    pl->predPacked.release(); pl->wexp.release(); pl->sysDesc.release(); pl->jobs.release();
+    pl->predPacked.release(); pl->xbuf.release(); pl->wexp.release(); pl->bigWork.release(); pl->fwdJobs.release(); pl->sysDesc.release(); pl->jobs.release();
     if (pl->pin) cudaFreeHost(pl->pin);
     delete pl;
 }
@@ -783,6 +891,36 @@ int hmcmt_leapfrog_steps_device(hmcmt_plan* pl, double dt, int32_t nsteps) {
         k_kick<<<pl->nChains, 1024, 0, pl->stream>>>(pl->nAC, dt, pl->gtotal.p, pl->p.p);
         LAUNCH_CHECK(pl);
     }
+    return kOk;
+}
+
+int hmcmt_step_partial(hmcmt_plan* pl, double dt) {
+    if (!pl) return kErrArg;
+    HMCMT_CUDA_TRY(cudaSetDevice(pl->device));
+    int rc = drift(pl, dt);
+    if (rc) return rc;
+    rc = compute_step(pl, true, nullptr);
+    if (rc) return rc;
+    k_pack_exchange<<<dim3((pl->nAC + 1 + 255) / 256, pl->nChains), 256, 0, pl->stream>>>(pl->nAC, pl->gdata.p, pl->phi.p, pl->xbuf.p);
+    LAUNCH_CHECK(pl);
+    return kOk;
+}
+
+int hmcmt_exchange_buffer(hmcmt_plan* pl, void** dptr, int64_t* count) {
+    if (!pl || !dptr || !count) return kErrArg;
+    *dptr = pl->xbuf.p;
+    *count = (int64_t)pl->nChains * (pl->nAC + 1);
+    return kOk;
+}
+
+int hmcmt_step_finish(hmcmt_plan* pl, double dt) {
+    if (!pl) return kErrArg;
+    HMCMT_CUDA_TRY(cudaSetDevice(pl->device));
+    k_unpack_exchange<<<dim3((pl->nAC + 1 + 255) / 256, pl->nChains), 256, 0, pl->stream>>>(
+        pl->nAC, pl->xbuf.p, pl->m.p, pl->mref.p, pl->wmPtr.p, pl->wmIdx.p, pl->wmVal.p, pl->beta, pl->gdata.p, pl->gtotal.p, pl->phi.p);
+    LAUNCH_CHECK(pl);
+    k_kick<<<pl->nChains, 1024, 0, pl->stream>>>(pl->nAC, dt, pl->gtotal.p, pl->p.p);
+    LAUNCH_CHECK(pl);
     return kOk;
 }
 

@@ -15,7 +15,8 @@
 
 namespace hmcmt {
 int round_T(int b);
-int launch_factor(cudaStream_t st, int T, const BandSys* sys, int nsys, const BandDom& dom);
+int launch_factor(cudaStream_t st, int T, const BandSys* sys, int nsys, const BandDom& dom, const SolveJob* fwdJobs, int* nLaunches);
+size_t big_work_bytes(int T);
 int launch_solve(cudaStream_t st, int T, const SolveJob* jobs, int njobs, const BandDom& dom);
 int max_band_T();
 }  // namespace hmcmt
@@ -62,8 +63,8 @@ int64_t factor_common(int64_t n, int64_t sym, const double* nzval, const int64_t
     if (b < 1) b = 1;
     int T = round_T((int)b);
     if (T > max_band_T()) {
-        fprintf(stderr, "[hmcmt_b200] factor_mumps: half-bandwidth %lld exceeds the register-window kernel (max %d)\n",
-                (long long)b, 8 * max_band_T() - 8);
+        fprintf(stderr, "[hmcmt_b200] factor_mumps: half-bandwidth %lld exceeds the supported maximum %d\n",
+                (long long)b, 8 * max_band_T() - 32);
         return fail(kErrArg);
     }
     // lower band image: band[g*(b+1)+d] = A[g][g-d]   (the lower triangle is what LDL^T reads)
@@ -78,23 +79,24 @@ int64_t factor_common(int64_t n, int64_t sym, const double* nzval, const int64_t
     Factor* f = new Factor();
     f->n = (int)n; f->b = (int)b; f->T = T; f->S = (int)((n + TS - 1) / TS); f->isReal = isReal;
     cplx* dband = nullptr;
+    cplx* dbig = nullptr;
     BandSys* dsys = nullptr;
     int* dstatus = nullptr;
-    auto cleanup = [&]() { if (dband) cudaFree(dband); if (dsys) cudaFree(dsys); if (dstatus) cudaFree(dstatus); };
+    auto cleanup = [&]() { if (dband) cudaFree(dband); if (dbig) cudaFree(dbig); if (dsys) cudaFree(dsys); if (dstatus) cudaFree(dstatus); };
     if (cudaMalloc(&dband, band.size() * sizeof(cplx)) != cudaSuccess ||
         cudaMalloc(&f->panels, (size_t)f->S * panel_doubles(T) * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&f->ainvz, (size_t)f->S * AZ * sizeof(cplx)) != cudaSuccess || cudaMalloc(&dsys, sizeof(BandSys)) != cudaSuccess ||
-        cudaMalloc(&dstatus, sizeof(int)) != cudaSuccess) {
+        cudaMalloc(&dstatus, sizeof(int)) != cudaSuccess || (big_work_bytes(T) && cudaMalloc(&dbig, big_work_bytes(T)) != cudaSuccess)) {
         cleanup(); free_factor(f);
         return fail(kErrAlloc);
     }
     cudaMemcpy(dband, band.data(), band.size() * sizeof(cplx), cudaMemcpyHostToDevice);
     cudaMemset(dstatus, 0, sizeof(int));
     BandSys s{};
-    s.band = dband; s.omega = 0.0; s.rhs = nullptr; s.panels[0] = f->panels; s.panels[1] = nullptr; s.ainvz[0] = f->ainvz; s.ainvz[1] = nullptr; s.wexp = nullptr; s.x = nullptr; s.status = dstatus;
+    s.band = dband; s.omega = 0.0; s.rhs = nullptr; s.panels[0] = f->panels; s.panels[1] = nullptr; s.ainvz[0] = f->ainvz; s.ainvz[1] = nullptr; s.wexp = nullptr; s.big = dbig; s.x = nullptr; s.status = dstatus;
     cudaMemcpy(dsys, &s, sizeof(BandSys), cudaMemcpyHostToDevice);
     BandDom dom{(int)n, (int)b, (int)b, 0, 0, 0};
-    int rc = launch_factor(nullptr, T, dsys, 1, dom);
+    int rc = launch_factor(nullptr, T, dsys, 1, dom, nullptr, nullptr);
     int hst = 0;
     if (rc == kOk && cudaDeviceSynchronize() != cudaSuccess) rc = kErrCuda;
     if (rc == kOk) cudaMemcpy(&hst, dstatus, sizeof(int), cudaMemcpyDeviceToHost);

@@ -65,6 +65,9 @@ def load() -> C.CDLL:
     lib.hmcmt_get_state.argtypes = [vp, _f64p, _f64p]
     lib.hmcmt_leapfrog_trajectory.argtypes = [vp, C.c_double, _i32p, _f64p, _f64p]
     lib.hmcmt_leapfrog_steps_device.argtypes = [vp, C.c_double, C.c_int32]
+    lib.hmcmt_step_partial.argtypes = [vp, C.c_double]
+    lib.hmcmt_exchange_buffer.argtypes = [vp, C.POINTER(vp), _i64p]
+    lib.hmcmt_step_finish.argtypes = [vp, C.c_double]
     lib.hmcmt_sync.argtypes = [vp]
     lib.hmcmt_timer_start.argtypes = [vp]
     lib.hmcmt_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
@@ -97,6 +100,7 @@ EXPORTED_SYMBOLS = [
     "solve_mumps_cmplx_sparse_rhs_", "destroy_mumps_", "destroy_mumps_cmplx_",
     "hmcmt_plan_create", "hmcmt_destroy", "hmcmt_plan_info", "hmcmt_forward", "hmcmt_jtvec", "hmcmt_forward_gradient",
     "hmcmt_set_state", "hmcmt_get_state", "hmcmt_leapfrog_trajectory", "hmcmt_leapfrog_steps_device", "hmcmt_sync",
+    "hmcmt_step_partial", "hmcmt_exchange_buffer", "hmcmt_step_finish",
     "hmcmt_timer_start", "hmcmt_timer_stop", "hmcmt_kernel_time", "hmcmt_run_chain", "hmcmt_export_system", "hmcmt_version",
 ]
 

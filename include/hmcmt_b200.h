@@ -138,6 +138,18 @@ int hmcmt_leapfrog_trajectory(hmcmt_plan* plan, double dt, const int32_t* intste
 /* `nsteps` leapfrog steps (drift, reflect, forward+adjoint gradient, prior gradient, kick) with no host
  * transfer at all — the timed region of bench.py's `value`. */
 int hmcmt_leapfrog_steps_device(hmcmt_plan* plan, double dt, int32_t nsteps);
+
+/* Frequency-sharded leapfrog step (BASELINE.json configs[3]): every rank's plan holds a subset of the
+ * frequencies and the full model.  compDataGradient is a sum over frequencies (the loop of MT2DFwdSolver.jl:163-191 and
+ * compJacTMatVec.jl:200-324), so one step is
+ *   hmcmt_step_partial   drift + reflect, forward + adjoint over THIS rank's frequencies, partial [gdata | phi_d] per chain
+ *                        packed into the exchange buffer (device memory, nChains*(nAC+1) doubles);
+ *   <caller>             sum-all-reduce of the exchange buffer across ranks (ncclAllReduce / torch.distributed);
+ *   hmcmt_step_finish    prior gradient beta*Wm*(m-m_ref) added once, kick (HMCSampler.jl:255-265).
+ * All of it is enqueued on the plan's stream: call hmcmt_sync before the caller's collective reads the buffer. */
+int hmcmt_step_partial(hmcmt_plan* plan, double dt);
+int hmcmt_exchange_buffer(hmcmt_plan* plan, void** device_ptr, int64_t* count);
+int hmcmt_step_finish(hmcmt_plan* plan, double dt);
 /* blocks until all work queued on the plan's stream has finished */
 int hmcmt_sync(hmcmt_plan* plan);
 /* CUDA-event bracket on the plan's stream: start / stop (returns elapsed ms through *ms) */

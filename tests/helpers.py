@@ -50,3 +50,16 @@ def to_product(mesh, data, inv, prior):
     pp = fileio.HMCPrior(burninsamples=prior.burninsamples, totalsamples=prior.totalsamples, sigBounds=list(prior.sigBounds),
                          sigmastd=prior.sigmastd, dt=prior.dt, timestep=list(prior.timestep), regParam=prior.regParam)
     return pm, pd, pi, pp
+
+
+def to_oracle(mesh, data, inv, prior):
+    """Oracle-side objects from product-side ones (hmcmt2d_b200.synthetic / fileio), same arrays."""
+    omesh = ofio.TensorMesh2D(np.array(mesh.yLen), np.array(mesh.zLen), np.array(mesh.airLayer), tuple(mesh.gridSize),
+                              np.array(mesh.origin), np.array(mesh.sigma))
+    od = ofio.MTData(np.array(data.rxLoc), np.array(data.freqs), data.dataType, list(data.dataComp), np.array(data.rxID),
+                     np.array(data.freqID), np.array(data.dtID), np.array(data.dataID), data.compTE, data.compTM)
+    oinv = osamp.setupInverseDataModel(omesh, [1e-8], np.array(inv.obsData), np.array(inv.dataErr))
+    oinv.strModel = np.array(inv.strModel)
+    oprior = ofio.HMCPrior(burninsamples=prior.burninsamples, totalsamples=prior.totalsamples, sigBounds=list(prior.sigBounds),
+                           sigmastd=prior.sigmastd, dt=prior.dt, timestep=list(prior.timestep), regParam=prior.regParam)
+    return omesh, od, oinv, oprior

@@ -1,7 +1,7 @@
 """Level-1 ABI (MUMPS shim) on the GPU — mirrors the reference's own solver-boundary tests
 MUMPS/test/testDivGrad.jl (:19,32-33,45-46,58-59) and testTwoSystem.jl (:35,43): relative residual
 < 1e-14, result eltype, several live factorisations.  The div-grad grid is sized so that its
-half-bandwidth fits the register-window kernel (b = n1*n2 <= 104)."""
+half-bandwidth fits the register-window kernel (b = n1*n2 <= 104); larger bandwidths: test_gpu_bigband.py."""
 import numpy as np
 import pytest
 import scipy.sparse as sp
@@ -95,9 +95,9 @@ def test_error_codes():
     with pytest.raises(lib.HmcmtError) as e:
         lib.factorMUMPS(zero, 1)
     assert e.value.code == -10                     # "Numerically singular matrix" (MUMPSfuncs.jl:62-63)
-    wide = sp.diags([np.full(300, 4.0), np.full(100, -1.0), np.full(100, -1.0)], [0, 200, -200], format="csc")
+    wide = sp.diags([np.full(500, 4.0), np.full(100, -1.0), np.full(100, -1.0)], [0, 400, -400], format="csc")
     with pytest.raises(lib.HmcmtError) as e:
-        lib.factorMUMPS(wide, 1)                   # half-bandwidth 200 > 104: refused, never a CPU fallback
+        lib.factorMUMPS(wide, 1)                   # half-bandwidth 400 > 320: refused, never a CPU fallback
     assert e.value.code == -3
     with pytest.raises(ValueError):
         lib.factorMUMPS(sp.csc_matrix(np.ones((3, 4))), 1)
