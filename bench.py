@@ -10,6 +10,10 @@ frequencies x TE/TM), prior gradient, momentum kick.  Workload = BASELINE.json c
 200x100-cell mesh, 30 frequencies, TE+TM, one independent chain per GPU (weak scaling, no data-path
 collective: "replicas only", as parallelHMC.jl).
 
+    python bench.py --config cfg4 --gpus N [--nfreq F]       (BASELINE.json configs[3]; not the driver's default line)
+the 800x300-cell mesh with 60 frequencies, frequency-sharded over N >= 2 GPUs (strong scaling; the 120 factors need
+154 GB, so N = 1 only runs with a reduced --nfreq), one NCCL all-reduce of [gradient | misfit] per leapfrog step.
+
 `value` : steps/s with the chain state resident in HBM (hmcmt_leapfrog_steps_device), CUDA events on the
           library's stream, max over ranks.
 `e2e`   : the same step through the reference-facing call (compDataGradient-equivalent through the C ABI)
@@ -31,6 +35,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+CFG4 = dict(workload="cfg4: synthetic 800x300-cell mesh, 60 frequencies, TE+TM, 1 HMC chain, frequencies sharded over the GPUs "
+                     "(one NCCL sum-all-reduce of [gradient | misfit] per step)",
+            ny=800, nz=300, nfreq=60, nrx=40, modes="TE+TM", chains_per_gpu=1)
 METRIC = "leapfrog_steps_per_sec"
 UNIT = "steps/s"
 WORKLOAD = dict(workload="cfg2: synthetic 200x100-cell mesh, 30 frequencies, TE+TM, 1 HMC chain per GPU",
@@ -89,9 +96,10 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_problem():
+def build_problem(cfg=None):
     from hmcmt2d_b200 import synthetic
-    mesh, data, inv, prior = synthetic.make_problem(WORKLOAD["ny"], WORKLOAD["nz"], WORKLOAD["nfreq"], WORKLOAD["nrx"])
+    cfg = cfg or WORKLOAD
+    mesh, data, inv, prior = synthetic.make_problem(cfg["ny"], cfg["nz"], cfg["nfreq"], cfg["nrx"])
     return mesh, data, inv, prior
 
 
@@ -100,12 +108,12 @@ def build_problem():
 
 def _cpu_freq_job(args):
     """forward + adjoint for ONE frequency (TE+TM) of the workload — the unit the host cores are farmed over."""
-    fidx, seed = args
+    fidx, seed, cfg = args
     sys.path.insert(0, ROOT)
     from hmcmt2d_b200 import synthetic
     from oracle import fileio as ofio
     from oracle import sampler as osamp
-    mesh, data, inv, prior = build_problem()
+    mesh, data, inv, prior = build_problem(cfg)
     keep = data.freqID == fidx + 1
     omesh = ofio.TensorMesh2D(mesh.yLen, mesh.zLen, mesh.airLayer, mesh.gridSize, mesh.origin, mesh.sigma)
     od = ofio.MTData(data.rxLoc, data.freqs[fidx:fidx + 1], data.dataType, data.dataComp, data.rxID[keep],
@@ -117,21 +125,23 @@ def _cpu_freq_job(args):
     return time.perf_counter() - t0
 
 
-def cpu_steps_per_sec(nworkers: int, nfreq_sample: int, repeats: int = 1):
+def cpu_steps_per_sec(nworkers: int, nfreq_sample: int, repeats: int = 1, cfg=None):
     """Times `nfreq_sample` of the 30 frequencies farmed over `nworkers` processes and extrapolates to the full
     step (frequencies are independent and cost the same: identical sparsity pattern)."""
     import multiprocessing as mp
-    freqs = list(np.linspace(0, WORKLOAD["nfreq"] - 1, nfreq_sample).astype(int))
+    cfg = cfg or WORKLOAD
+    freqs = list(np.linspace(0, cfg["nfreq"] - 1, nfreq_sample).astype(int))
     ctx = mp.get_context("spawn")
     times = []
     with ctx.Pool(nworkers) as pool:
-        pool.map(_cpu_freq_job, [(freqs[0], 1)] * nworkers)            # warm the workers (imports, operator setup)
+        if cfg["ny"] * cfg["nz"] < 100000:
+            pool.map(_cpu_freq_job, [(freqs[0], 1, cfg)] * nworkers)   # warm the workers (imports, operator setup)
         for r in range(repeats):
             t0 = time.perf_counter()
-            pool.map(_cpu_freq_job, [(int(f), 1) for f in freqs])
+            pool.map(_cpu_freq_job, [(int(f), 1, cfg) for f in freqs])
             times.append(time.perf_counter() - t0)
     t = min(times)
-    step_time = t * WORKLOAD["nfreq"] / nfreq_sample
+    step_time = t * cfg["nfreq"] / nfreq_sample
     return 1.0 / step_time, t
 
 
@@ -284,6 +294,123 @@ def run_gpu(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------------
+# cfg4: one chain, frequencies sharded over the ranks, one NCCL all-reduce per step (strong scaling)
+
+def run_gpu_cfg4(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from hmcmt2d_b200 import api, synthetic
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — hmcmt2d_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    cfg = dict(CFG4)
+    if args.nfreq:
+        cfg["nfreq"] = args.nfreq
+        cfg["workload"] += f" [reduced to {args.nfreq} frequencies]"
+    if world == 1 and cfg["nfreq"] > 48:
+        raise SystemExit("bench.py --config cfg4: the 120 factors (1.28 GB each) do not fit one GPU; use --gpus >= 2 or --nfreq <= 48")
+    mesh, data, inv, prior = build_problem(cfg)
+    sp = api.FreqShardedPlan(mesh, data, inv, prior, rank, world, device=local_rank)
+    pl = sp.plan
+    m0 = synthetic.stress_model(inv, seed=1)                                   # the same chain state on every rank
+    p0 = np.clip(np.random.default_rng(100).standard_normal(len(m0)), -2.5, 2.5)
+    dt = prior.dt
+    K, W = args.steps, max(3, args.warmup)
+
+    sp.set_state(m0, p0, m0)
+    sp.leapfrog_steps_device(dt, W)
+    sp.sync()
+    pl.kernel_time(reset=True)
+    launches0 = pl.info(10)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    pl.timer_start()
+    sp.leapfrog_steps_device(dt, K)
+    ms = pl.timer_stop()
+    barrier()
+    clocks = sampler.stop()
+    launches = pl.info(10) - launches0
+    factor_ms, factor_n = pl.kernel_time(reset=True)
+    ms = max_over_ranks(ms)
+    value = K / (ms * 1e-3)
+    m_end, _ = sp.get_state()
+    drift_between_ranks = max_over_ranks(float(np.abs(m_end).sum())) - (-max_over_ranks(-float(np.abs(m_end).sum())))
+
+    # end to end: compDataGradient through host buffers (H2D model, D2H data / misfit / gradient, all-reduce) + host leapfrog
+    lo, hi = np.log(prior.sigBounds[0]), np.log(prior.sigBounds[1])
+    Wm, beta = inv.Wm, prior.regParam
+
+    def host_step(m, p):
+        dm = dt * p
+        mx = np.abs(dm).max()
+        if mx > 3.0:
+            dm = dm / mx * 3.0
+        m = np.clip(m + dm, lo, hi)
+        pred, phi, g = sp.forward_gradient(m)
+        return m, p - dt * (g + beta * (Wm @ (m - m0))), phi
+
+    Ke = max(1, min(K, 5))
+    m, p = m0.copy(), p0.copy()
+    m, p, _ = host_step(m, p)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        m, p, phi = host_step(m, p)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+
+    N, b, nsys = pl.info(0), pl.info(4), pl.info(7)
+    flops_launch = (4.0 * N * b * b + 16.0 * N * b) * nsys
+    bytes_launch = 2.0 * 16.0 * N * (b + 1) * nsys
+    fac_ms = factor_ms / max(1, factor_n)
+    achieved = flops_launch / (fac_ms * 1e-3) / 1e12
+    peaks, peak_src = load_peaks()
+    roofline = dict(bound="tensor", kernel="large-bandwidth factorisation of this rank's systems: bigband_panel_kernel + "
+                    "bigband_update_kernel (DMMA.8x8x4) per 32 columns + backward sweep (band_big.cuh)",
+                    achieved=achieved, peak=FP64_DMMA_PEAK_TFLOPS, unit="TFLOP/s", frac=achieved / FP64_DMMA_PEAK_TFLOPS,
+                    peak_source="measured FP64 DMMA m8n8k4 rate on this pool's B200 (profiles/r01_fp64_peak_ubench.txt); " + peak_src,
+                    traffic=None, algorithmic_flops_per_launch=flops_launch, algorithmic_bytes_per_launch=bytes_launch,
+                    hbm_achieved_gbs=bytes_launch / (fac_ms * 1e-3) / 1e9, hbm_peak_gbs=peaks.get("hbm_gbs"),
+                    avg_launch_ms=fac_ms, launches_timed=factor_n, share_of_step=fac_ms / (ms / K),
+                    note="latency-bound: ~7.5k stream-ordered panel/update launch pairs per factorisation")
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=ms / K, higher_is_better=True,
+                scaling="strong", vs_baseline=None, dtype="f64 (complex128)", data="synthetic",
+                config=dict(cfg, systems_per_gpu=int(nsys), l2_policy="inputs larger than L2: each rank streams its 1.28 GB-per-system factors",
+                            parallelism=f"frequencies x{world} (NCCL sum-all-reduce of [gdata | phi_d], {8 * (pl.nAC + 1)} B per step)",
+                            state_spread_between_ranks=drift_between_ranks),
+                e2e=dict(value=Ke / e2e_s, unit=UNIT, h2d_bytes_per_step=pl.nAC * 8, d2h_bytes_per_step=pl.nData * 16 + 8 + pl.nAC * 8,
+                         ms_per_step=1000 * e2e_s / Ke, steps=Ke),
+                gpu_launches=int(launches), clocks=clocks, roofline=roofline)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v1, wall1 = cpu_steps_per_sec(1, 1, cfg=cfg)
+        line["cpu_baseline"] = dict(value=v1, unit=UNIT, cores=1, kind="port",
+                                    sample=f"1 of {cfg['nfreq']} frequencies (TE+TM forward+adjoint, {wall1:.1f} s) on one host core, extrapolated; "
+                                           "matrix-free restatement (the reference's dense dBC needs 8.4 GB per system at this size)")
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    sp.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -291,6 +418,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg4"])
+    ap.add_argument("--nfreq", type=int, default=0, help="cfg4 only: reduced number of frequencies (testing)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -302,8 +431,11 @@ def main():
         # convenience: re-launch under torchrun when called directly with --gpus N
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                "--master-port", "29511", os.path.abspath(__file__), "--gpus", str(args.gpus), "--steps", str(args.steps),
-               "--warmup", str(args.warmup)]
+               "--warmup", str(args.warmup), "--config", args.config, "--nfreq", str(args.nfreq)]
         raise SystemExit(subprocess.call(cmd))
+    if args.config == "cfg4":
+        run_gpu_cfg4(args, rank, world, local_rank)
+        return
     run_gpu(args, rank, world, local_rank)
 
 

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhmcmt_b200.so")
 SOURCES = ["hmcmt_b200.cu", "mumps_shim.cu"]
-HEADERS = ["common.cuh", "band_factor.cuh", "band_solve.cuh", "mt_kernels.cuh", os.path.join("..", "..", "include", "hmcmt_b200.h")]
+HEADERS = ["common.cuh", "band_factor.cuh", "band_solve.cuh", "band_big.cuh", "mt_kernels.cuh", os.path.join("..", "..", "include", "hmcmt_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC"]
 

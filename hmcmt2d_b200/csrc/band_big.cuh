@@ -11,7 +11,7 @@
 //                          kernel), forms M' = -raw A11^{-1}, forward-eliminates the fused right-hand side and writes
 //                          the four factor panels;
 //   bigband_update_kernel  many CTAs per system: rank-32 update of the trailing window with FP64 tensor-core MMAs
-//                          (DMMA.8x8x4), one warp per 8-row block, operands straight from L2/L1; four extra CTAs
+//                          (DMMA.8x8x4), one warp per 8x8 tile, operands straight from L2/L1; four extra CTAs
 //                          refill the recycled window rows from the stencil (assembly stays fused, the matrix is
 //                          never stored).
 // No cross-CTA synchronisation inside a kernel.  Replaces factorMUMPS / lu for the systems of mt2DTE.jl:47-55,
@@ -136,27 +136,33 @@ bigband_panel_kernel(const BandSys* __restrict__ systems, BandDom dom, int T, in
             if (t == 0) dz[64 + i] = acc;
         }
         __syncthreads();
-        // M'[r][4h..4h+3] = -sum_k raw[r][k] A11^{-1}[k][4h+j]   (all rows: the partner exchange below must be warp-converged)
-        cplx raw[8], m[4], mf[8];
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) raw[kk] = P(c, r, kk);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            cplx acc = mk(0.0, 0.0);
-#pragma unroll
-            for (int kk = 0; kk < 8; ++kk) cfma(acc, -raw[kk], ainv[kk * 8 + 4 * h + j]);
-            m[j] = acc;
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const cplx o = mk(__shfl_xor_sync(0xffffffffu, m[j].x, 1), __shfl_xor_sync(0xffffffffu, m[j].y, 1));
-            mf[4 * h + j] = m[j];
-            mf[4 * (h ^ 1) + j] = o;
-        }
+        // M'[r][4h..4h+3] = -sum_k raw[r][k] A11^{-1}[k][4h+j]   (all rows: the partner exchange below must be warp-converged).
+        // Register budget (704 threads -> 88 registers): raw is streamed from shared memory, never held as an array.
         const bool below = beta > s0 + c;
-        if (below) {
-            for (int c2 = c + 1; c2 < nsub; ++c2) {
-                if (beta < s0 + c2) continue;
+        cplx m[4] = {mk(0.0, 0.0), mk(0.0, 0.0), mk(0.0, 0.0), mk(0.0, 0.0)};
+        cplx yacc = mk(0.0, 0.0);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+            const cplx rv = P(c, r, kk);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) cfma(m[j], -rv, ainv[kk * 8 + 4 * h + j]);
+            cfma(yacc, -rv, zsh[kk]);
+        }
+        if (below && h == 0 && sys.rhs) ysh[r] = ysh[r] + yacc;
+        // operands of the trailing update (plain [c][r][8] layout, L2-resident)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v.mscr[((size_t)c * R + r) * 8 + 4 * h + j] = below ? m[j] : mk(0.0, 0.0);
+        {
+            cplx mf[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {      // static indices only: the array must stay in registers
+                const cplx o = mk(__shfl_xor_sync(0xffffffffu, m[j].x, 1), __shfl_xor_sync(0xffffffffu, m[j].y, 1));
+                mf[j] = h ? o : m[j];
+                mf[4 + j] = h ? m[j] : o;
+            }
+#pragma unroll
+            for (int c2 = 1; c2 < kBigNBK; ++c2) {
+                if (c2 <= c || c2 >= nsub || !below || beta < s0 + c2) continue;
                 const int p2 = (s0 + c2) % T;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -166,19 +172,12 @@ bigband_panel_kernel(const BandSys* __restrict__ systems, BandDom dom, int T, in
                     P(c2, r, 4 * h + j) = acc;
                 }
             }
-            if (h == 0 && sys.rhs) {
-                cplx acc = ysh[r];
-#pragma unroll
-                for (int kk = 0; kk < 8; ++kk) cfma(acc, -raw[kk], zsh[kk]);
-                ysh[r] = acc;
-            }
         }
-        // operands of the trailing update (plain [c][r][8] layout, L2-resident)
+        cplx rawh[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            v.mscr[((size_t)c * R + r) * 8 + 4 * h + j] = below ? m[j] : mk(0.0, 0.0);
-            v.rscr[((size_t)c * R + r) * 8 + 4 * h + j] = below ? raw[4 * h + j] : mk(0.0, 0.0);
-        }
+        for (int j = 0; j < 4; ++j) rawh[j] = P(c, r, 4 * h + j);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v.rscr[((size_t)c * R + r) * 8 + 4 * h + j] = below ? rawh[j] : mk(0.0, 0.0);
         // factor panel of macro-step s0+c in the solve kernels' image layout [re/im][kk][R][4]; rows of blocks already
         // eliminated in this launch are outside the band of this panel: zero
         {
@@ -186,8 +185,8 @@ bigband_panel_kernel(const BandSys* __restrict__ systems, BandDom dom, int T, in
             const bool keep = beta >= s0 + c;
             double2 re01 = make_double2(0.0, 0.0), re23 = re01, im01 = re01, im23 = re01;
             if (keep) {
-                re01 = make_double2(raw[4 * h].x, raw[4 * h + 1].x); re23 = make_double2(raw[4 * h + 2].x, raw[4 * h + 3].x);
-                im01 = make_double2(raw[4 * h].y, raw[4 * h + 1].y); im23 = make_double2(raw[4 * h + 2].y, raw[4 * h + 3].y);
+                re01 = make_double2(rawh[0].x, rawh[1].x); re23 = make_double2(rawh[2].x, rawh[3].x);
+                im01 = make_double2(rawh[0].y, rawh[1].y); im23 = make_double2(rawh[2].y, rawh[3].y);
             }
             double2* pre = reinterpret_cast<double2*>(img + ((size_t)(0 * 2 + h) * R + r) * 4);
             double2* pim = reinterpret_cast<double2*>(img + ((size_t)(1 * 2 + h) * R + r) * 4);
@@ -207,58 +206,51 @@ bigband_panel_kernel(const BandSys* __restrict__ systems, BandDom dom, int T, in
     }
 }
 
-// grid (nStrips + kBigNBK, nsys), 256 threads.  CTAs x < nStrips: warp w owns trailing-window position 8*x + w (one 8-row block)
-// and sweeps the column blocks up to its own; CTAs x >= nStrips refill one recycled 8-row block from the stencil.
+// grid (nXp * nYq + kBigNBK, nsys), 256 threads.  CTAs x < nXp*nYq: a 2 x 4 block of 8x8 tiles of the trailing window, one
+// tile per warp (the two M' row blocks and four raw row blocks of a CTA are shared through L1); CTAs beyond refill one
+// recycled 8-row block from the stencil.  nXp = ceil(npos/2), nYq = ceil(npos/4), npos = T - kBigNBK window positions.
 __global__ void __launch_bounds__(256)
-bigband_update_kernel(const BandSys* __restrict__ systems, BandDom dom, int T, int k, int nStrips) {
+bigband_update_kernel(const BandSys* __restrict__ systems, BandDom dom, int T, int k, int nYq, int nBlocks) {
     const BandSys sys = systems[blockIdx.y];
     const int R = TS * T;
     BigView v(sys.big, R);
     const int s0 = k * kBigNBK, w0 = s0 + kBigNBK;      // first block of the trailing window
-    if ((int)blockIdx.x >= nStrips) {
+    if ((int)blockIdx.x >= nBlocks) {
         const LocalDom L = LocalDom::make(dom, 0);
         EntryProvider prov{sys.dr, sys.dm, sys.e1, sys.e2, sys.band, sys.omega, dom.b, L};
-        big_fill_rows(prov, v.win, T, w0, s0 + ((int)blockIdx.x - nStrips) + T, threadIdx.x, blockDim.x);
+        big_fill_rows(prov, v.win, T, w0, s0 + ((int)blockIdx.x - nBlocks) + T, threadIdx.x, blockDim.x);
         return;
     }
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int warp = __shfl_sync(0xffffffffu, (int)threadIdx.x >> 5, 0);
-    const int aX = (int)blockIdx.x * 8 + warp;
-    if (aX >= T - kBigNBK) return;
-    const int slotX = (w0 + aX) % T;
-    double are[kBigNBK][2], aim[kBigNBK][2];
+    const int xb = (int)blockIdx.x / nYq, yb = (int)blockIdx.x - xb * nYq;
+    const int aX = 2 * xb + (warp >> 2), aY = 4 * yb + (warp & 3);
+    if (aX >= T - kBigNBK || aY > aX) return;
+    const int slotX = (w0 + aX) % T, slotY = (w0 + aY) % T;
+    double are[kBigNBK][2], aim[kBigNBK][2], bre[kBigNBK][2], bim[kBigNBK][2];
 #pragma unroll
     for (int c = 0; c < kBigNBK; ++c)
 #pragma unroll
         for (int kk = 0; kk < 2; ++kk) {
             const cplx a = __ldg(&v.mscr[((size_t)c * R + slotX * TS + g) * 8 + 4 * kk + t]);
+            const cplx bv = __ldg(&v.rscr[((size_t)c * R + slotY * TS + g) * 8 + 4 * kk + t]);
             are[c][kk] = a.x; aim[c][kk] = a.y;
+            bre[c][kk] = bv.x; bim[c][kk] = bv.y;
         }
-    for (int aY = 0; aY <= aX; ++aY) {
-        const int slotY = (w0 + aY) % T;
-        double bre[kBigNBK][2], bim[kBigNBK][2];
+    cplx* cp = v.win + (size_t)(slotX * TS + g) * R + slotY * TS + 2 * t;
+    const cplx c0 = cp[0], c1 = cp[1];
+    double cre[2] = {c0.x, c1.x}, cim[2] = {c0.y, c1.y}, t1[2] = {0.0, 0.0}, t2[2] = {0.0, 0.0};
 #pragma unroll
-        for (int c = 0; c < kBigNBK; ++c)
+    for (int c = 0; c < kBigNBK; ++c)
 #pragma unroll
-            for (int kk = 0; kk < 2; ++kk) {
-                const cplx bv = __ldg(&v.rscr[((size_t)c * R + slotY * TS + g) * 8 + 4 * kk + t]);
-                bre[c][kk] = bv.x; bim[c][kk] = bv.y;
-            }
-        cplx* cp = v.win + (size_t)(slotX * TS + g) * R + slotY * TS + 2 * t;
-        const cplx c0 = cp[0], c1 = cp[1];
-        double cre[2] = {c0.x, c1.x}, cim[2] = {c0.y, c1.y}, t1[2] = {0.0, 0.0}, t2[2] = {0.0, 0.0};
-#pragma unroll
-        for (int c = 0; c < kBigNBK; ++c)
-#pragma unroll
-            for (int kk = 0; kk < 2; ++kk) {
-                dmma884(cre, are[c][kk], bre[c][kk]);
-                dmma884(cim, are[c][kk], bim[c][kk]);
-                dmma884(t1, -aim[c][kk], bim[c][kk]);
-                dmma884(t2, aim[c][kk], bre[c][kk]);
-            }
-        cp[0] = mk(cre[0] + t1[0], cim[0] + t2[0]);
-        cp[1] = mk(cre[1] + t1[1], cim[1] + t2[1]);
-    }
+        for (int kk = 0; kk < 2; ++kk) {
+            dmma884(cre, are[c][kk], bre[c][kk]);
+            dmma884(cim, are[c][kk], bim[c][kk]);
+            dmma884(t1, -aim[c][kk], bim[c][kk]);
+            dmma884(t2, aim[c][kk], bre[c][kk]);
+        }
+    cp[0] = mk(cre[0] + t1[0], cim[0] + t2[0]);
+    cp[1] = mk(cre[1] + t1[1], cim[1] + t2[1]);
 }
 
 }  // namespace hmcmt

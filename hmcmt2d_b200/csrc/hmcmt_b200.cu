@@ -163,12 +163,12 @@ int launch_factor_big(cudaStream_t st, int T, const BandSys* sys, int nsys, cons
         configured = true;
     }
     const int R = TS * T, sTot = (dom.N + TS - 1) / TS, nPanels = (sTot + kBigNBK - 1) / kBigNBK;
-    const int nStrips = (T - kBigNBK + 7) / 8;
+    const int npos = T - kBigNBK, nYq = (npos + 3) / 4, nBlocks = ((npos + 1) / 2) * nYq;
     const size_t smem = big_panel_smem_bytes(T);
     bigband_init_kernel<<<dim3(T, nsys), 256, 0, st>>>(sys, dom, T);
     for (int k = 0; k < nPanels; ++k) {
         bigband_panel_kernel<<<nsys, 2 * R, smem, st>>>(sys, dom, T, k);
-        if (k + 1 < nPanels) bigband_update_kernel<<<dim3(nStrips + kBigNBK, nsys), 256, 0, st>>>(sys, dom, T, k, nStrips);
+        if (k + 1 < nPanels) bigband_update_kernel<<<dim3(nBlocks + kBigNBK, nsys), 256, 0, st>>>(sys, dom, T, k, nYq, nBlocks);
     }
     HMCMT_CUDA_TRY(cudaGetLastError());
     int n = 2 * nPanels;
