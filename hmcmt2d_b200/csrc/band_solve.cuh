@@ -22,6 +22,8 @@ struct SolveJob {
 // TMA stages in flight: 8 for the register-window sizes (14 KB panels), fewer for the large-bandwidth windows (up to 45 KB)
 __host__ __device__ constexpr int solve_stages(int T) { return T <= 14 ? 8 : (T <= 28 ? 5 : 4); }
 constexpr int kSolveThreads = 256;
+constexpr int kSolveRing = 8, kRhsAhead = 5;   // rhs ring of the forward sweep: depth and prefetch distance (steps)
+enum { SB_X0 = 1, SB_X1 = 2, SB_F0 = 3, SB_F1 = 4 };      // named barriers of the sweep pipeline
 // extra launch mode of the solve kernel: backward sweep only, z read from the factor's [A11^{-1} | z] stream (the fused
 // forward system of the large-bandwidth factorisation, band_big.cuh)
 constexpr int SM_BACKZ = 4;
@@ -31,12 +33,11 @@ struct SolveSmem {
     static constexpr int R = TS * T;
     static constexpr int NST = solve_stages(T);
     double stage[NST][2][2][R][4];
-    cplx ainv[NST][64];
+    cplx az[NST][AZ];                           // per stage: A11^{-1} (64) and, for the backward sweep, z (8)
     cplx y[R];
-    cplx zv[8];
-    cplx part[kSolveThreads / 32][8];
-    cplx ringRhs[kRing][8];     // rhs rows entering the window (forward sweep), prefetched kPre steps ahead
-    cplx ringZ[kRing][8];       // z of upcoming panels (backward sweep)
+    cplx zv[2][8];                              // z of the current step, double-buffered by step parity
+    cplx part[2][kSolveThreads / 32][8];        // far warps' partial dot products, double-buffered by step parity
+    cplx ringRhs[kSolveRing][8];                // rhs rows entering the window (forward sweep), cp.async'ed kRhsAhead steps ahead
     uint64_t mbar[NST];
 };
 
@@ -90,119 +91,198 @@ band_solve_kernel(const SolveJob* __restrict__ jobs, BandDom dom, int mode) {
         for (int q = 0; q < NST; ++q) mbar_init(&sm.mbar[q], 1);
         fence_mbar_init();
     }
-    if (tid >= 32 && tid < 40 && mode != FM_BACK && mode != SM_BACKZ)
-        for (int q = 0; q < kPre; ++q) {
-            int gnew = (sBeg + q + T) * TS + (tid - 32);
-            sm.ringRhs[(sBeg + q) % kRing][tid - 32] = (gnew < nLoc) ? local_rhs(L, job.rhs, gnew) : mk(0.0, 0.0);
-        }
     cta_sync();
     int itBase = 0;        // running count of panel visits: stage = visit % NST, parity = (visit / NST) & 1
-    auto issue = [&](int s, int visit) {
+    auto issue = [&](int s, int visit, int dir) {      // dir: +1 forward sweep, -1 backward sweep
         const int st = visit % NST;
-        mbar_arrive_expect_tx(&sm.mbar[st], PBYTES + 64 * 16);
+        // backward sweep: z_s travels with its panel (from the factor's [A11^{-1} | z] stream, or from this solve's zbuf)
+        const bool zFromFactor = (mode == SM_BACKZ);
+        const uint32_t azBytes = (dir < 0 && zFromFactor) ? AZ * 16 : 64 * 16;
+        mbar_arrive_expect_tx(&sm.mbar[st], PBYTES + azBytes + ((dir < 0 && !zFromFactor) ? 8 * 16 : 0));
         bulk_g2s(&sm.stage[st][0][0][0][0], panels + (size_t)s * panel_doubles(T), PBYTES, &sm.mbar[st]);
-        bulk_g2s(&sm.ainv[st][0], ainvz + (size_t)s * AZ, 64 * 16, &sm.mbar[st]);
+        bulk_g2s(&sm.az[st][0], ainvz + (size_t)s * AZ, azBytes, &sm.mbar[st]);
+        if (dir < 0 && !zFromFactor) bulk_g2s(&sm.az[st][64], zbuf + (size_t)s * 8, 8 * 16, &sm.mbar[st]);
+    };
+
+    // Both sweeps are software-pipelined across two warp roles so that the serial dependency between consecutive 8-column
+    // steps runs inside ONE warp (no CTA-wide barrier on the chain):
+    //   near warp (warp 0)  : the 8x8 work that links step s to step s+1 (pivot block and the neighbouring block);
+    //   far warps (1..6)    : the remaining rows of the panel, one step out of phase with the near warp;
+    //   service warp (7)    : global stores, ring prefetches and TMA issue.
+    // Named barriers, two per direction alternating with the step parity: SB_X* near -> far, SB_F* far -> near.
+    constexpr int NFAR = NTHR - 32;
+    auto reduce_rows_in_warp = [&](cplx& acc) {      // lanes differing in bits 3,4 hold partial sums of the same column
+#pragma unroll
+        for (int off = 8; off <= 16; off <<= 1) {
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
+            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+        }
+    };
+    auto reduce_quad = [&](cplx& acc) {               // the 4 lanes of a row
+#pragma unroll
+        for (int off = 1; off <= 2; off <<= 1) {
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
+            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+        }
     };
 
     // ---------------- forward over steps [sLo, sHi):  z_s = A11^{-1} y_p ;  y_rest -= raw_s z_s ----------------
     auto forward_range = [&](int sLo, int sHi) {
         const int n = sHi - sLo;
+        if (n <= 0) return;
         if (tid == 0)
-            for (int k = 0; k < NST - 1 && k < n; ++k) issue(sLo + k, itBase + k);
-        for (int k = 0; k < n; ++k) {
-            const int s = sLo + k, p = s % T, it = itBase + k, st = it % NST, rp = p * TS;
-            if (tid == 0 && k + NST - 1 < n) issue(s + NST - 1, it + NST - 1);
-            cplx pre = mk(0.0, 0.0);
-            if (tid >= 32 && tid < 40) {          // rhs rows of the block entering kPre steps from now (load in flight over the step)
-                int gnew = (s + kPre + T) * TS + (tid - 32);
-                if (gnew < nLoc) pre = local_rhs(L, job.rhs, gnew);
-            }
-            mbar_wait(&sm.mbar[st], (uint32_t)((it / NST) & 1));
-            if (warp == 0) {
-                const int ii = lane >> 2, tt = lane & 3;
-                cplx acc = sm.ainv[st][ii * 8 + 2 * tt] * sm.y[rp + 2 * tt] + sm.ainv[st][ii * 8 + 2 * tt + 1] * sm.y[rp + 2 * tt + 1];
+            for (int k = 0; k < NST && k < n; ++k) issue(sLo + k, itBase + k, +1);
+        if (warp == 0) {
+            // the near warp touches shared memory only: global stores, ring prefetches and TMA issue belong to the far warps
+            const int ii = lane >> 2, tt = lane & 3;
+            for (int k = 0; k < n; ++k) {
+                const int s = sLo + k, p = s % T, p1 = (s + 1) % T, it = itBase + k, st = it % NST, rp = p * TS;
+                mbar_wait(&sm.mbar[st], (uint32_t)((it / NST) & 1));
+                // z_s = A11^{-1} y_p  (y_p is final: far(s-2) was joined in the previous iteration, the block update of s-1 is ours)
+                cplx z = sm.az[st][ii * 8 + 2 * tt] * sm.y[rp + 2 * tt] + sm.az[st][ii * 8 + 2 * tt + 1] * sm.y[rp + 2 * tt + 1];
+                reduce_quad(z);
+                if (tt == 0) sm.zv[k & 1][ii] = z;
+                bar_arrive(SB_X0 + (k & 1), NTHR);                       // z_s published: far(s) may start (bar.arrive orders the smem writes)
+                // block s+1:  y_{p1} -= raw_s[p1 rows] z_s   — after far(s-1) has finished with those rows
+                const int r1 = p1 * TS + ii;
+                cplx u = mk(0.0, 0.0);
 #pragma unroll
-                for (int off = 1; off <= 2; off <<= 1) {
-                    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
-                    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+                for (int e = 0; e < 2; ++e) {
+                    const int c = 2 * tt + e;
+                    const cplx rv = mk(sm.stage[st][0][c >> 2][r1][c & 3], sm.stage[st][1][c >> 2][r1][c & 3]);
+                    const cplx zc = mk(__shfl_sync(0xffffffffu, z.x, 4 * c), __shfl_sync(0xffffffffu, z.y, 4 * c));
+                    cfma(u, rv, zc);
                 }
-                if (tt == 0) { sm.zv[ii] = acc; zbuf[(size_t)s * 8 + ii] = acc; }
+                reduce_quad(u);
+                if (k >= 1) bar_sync(SB_F0 + ((k - 1) & 1), NTHR);
+                if (tt == 0 && T > 1) sm.y[r1] = sm.y[r1] - u;
+                __syncwarp();
             }
-            cta_sync();
-            for (int r_b = 0; r_b < R; r_b += NTHR) if (const int r = r_b + tid; r < R) {
-                if ((r >> 3) == p) {      // recycle: slot block p now holds local block s+T
-                    sm.y[r] = sm.ringRhs[s % kRing][r & 7];
-                    continue;
+            bar_sync(SB_F0 + ((n - 1) & 1), NTHR);
+        } else if (warp == NTHR / 32 - 1) {
+            // service warp: everything that touches global memory, kept off both the near chain and the far arithmetic.
+            // lanes 0..7 store z_s, lane 8 refills the TMA stage of step s-1, lanes 16..23 feed the rhs ring with cp.async
+            // issued kRhsAhead steps before the rows are needed, so the warp never waits on a load
+            const int rl = lane - 16;
+            auto rhs_fetch = [&](int step) {     // rhs rows of the block entering the window at `step` -> ring, asynchronously
+                if (rl >= 0 && rl < 8) {
+                    int kind, lrel;
+                    const int gnew = (step + T) * TS + rl;
+                    const int qg = (step < sHi && gnew < nLoc) ? L.map(gnew, kind, lrel) : -1;
+                    const bool ok = qg >= 0 && !(kind == 1 && L.rank == 1);
+                    cp_async16(&sm.ringRhs[step % kSolveRing][rl], job.rhs + (ok ? qg : 0), ok ? 16u : 0u);
                 }
-                cplx acc = sm.y[r];
+                cp_async_commit();
+            };
+            for (int q = 0; q < kRhsAhead; ++q) rhs_fetch(sLo + q);
+            cp_async_wait<kRhsAhead - 1>();
+            for (int k = 0; k < n; ++k) {
+                const int s = sLo + k, it = itBase + k;
+                bar_sync(SB_X0 + (k & 1), NTHR);                         // z_s ready
+                if (lane < 8) zbuf[(size_t)s * 8 + lane] = sm.zv[k & 1][lane];
+                // the stage of step s-1 is free: near is past it and far(s-1) arrived on SB_F before this warp's previous arrive
+                if (lane == 8 && k >= 1 && k - 1 + NST < n) issue(s - 1 + NST, it - 1 + NST, +1);
+                rhs_fetch(s + kRhsAhead);
+                cp_async_wait<kRhsAhead - 1>();                           // the rows of step s+1 have landed
+                bar_arrive(SB_F0 + (k & 1), NTHR);
+            }
+        } else {
+            const int ft = tid - 32;
+            constexpr int NFC = NTHR - 64;         // far compute threads: one per window row
+            for (int k = 0; k < n; ++k) {
+                const int s = sLo + k, p = s % T, p1 = (s + 1) % T, it = itBase + k, st = it % NST;
+                mbar_wait(&sm.mbar[st], (uint32_t)((it / NST) & 1));
+                bar_sync(SB_X0 + (k & 1), NTHR);                         // z_s ready
 #pragma unroll
-                for (int kk = 0; kk < 8; ++kk) {
-                    cplx rv = mk(sm.stage[st][0][kk >> 2][r][kk & 3], sm.stage[st][1][kk >> 2][r][kk & 3]);
-                    cfma(acc, -rv, sm.zv[kk]);
+                for (int r_b = 0; r_b < R; r_b += NFC) {
+                    const int r = r_b + ft;
+                    if (r >= R) continue;
+                    const int slot = r >> 3;
+                    if (slot == p) { sm.y[r] = sm.ringRhs[s % kSolveRing][r & 7]; continue; }      // recycle: slot p now holds local block s+T
+                    if (slot == p1) continue;                                                     // the near warp's block
+                    cplx a0 = sm.y[r], a1 = mk(0.0, 0.0);
+#pragma unroll
+                    for (int c = 0; c < 8; c += 2) {
+                        cfma(a0, -mk(sm.stage[st][0][c >> 2][r][c & 3], sm.stage[st][1][c >> 2][r][c & 3]), sm.zv[k & 1][c]);
+                        cfma(a1, -mk(sm.stage[st][0][c >> 2][r][(c & 3) + 1], sm.stage[st][1][c >> 2][r][(c & 3) + 1]), sm.zv[k & 1][c + 1]);
+                    }
+                    sm.y[r] = a0 + a1;
                 }
-                sm.y[r] = acc;
+                bar_arrive(SB_F0 + (k & 1), NTHR);
             }
-            if (tid >= 32 && tid < 40) sm.ringRhs[(s + kPre) % kRing][tid - 32] = pre;
-            cta_sync();
         }
+        cta_sync();
         itBase += n;
     };
     // ---------------- backward over steps sHi-1 .. sLo:  x_p = z_s - A11^{-1} raw_s^T x_rest ----------------
-    constexpr int NRG = NTHR / 8;
-    auto zsrc = [&](int s, int i) { return mode == SM_BACKZ ? ainvz[(size_t)s * AZ + 64 + i] : zbuf[(size_t)s * 8 + i]; };
     auto backward_range = [&](int sHi, int sLo) {
         const int n = sHi - sLo;
+        if (n <= 0) return;
         if (tid == 0)
-            for (int k = 0; k < NST - 1 && k < n; ++k) issue(sHi - 1 - k, itBase + k);
-        if (tid >= 32 && tid < 40)
-            for (int q = 0; q < kPre && q < n; ++q) sm.ringZ[q % kRing][tid - 32] = zsrc(sHi - 1 - q, tid - 32);
+            for (int k = 0; k < NST && k < n; ++k) issue(sHi - 1 - k, itBase + k, -1);
         cta_sync();
-        for (int k = 0; k < n; ++k) {
-            const int s = sHi - 1 - k, p = s % T, it = itBase + k, st = it % NST;
-            if (tid == 0 && k + NST - 1 < n) issue(s - (NST - 1), it + NST - 1);
-            cplx prez = mk(0.0, 0.0);
-            if (tid >= 32 && tid < 40 && k + kPre < n) prez = zsrc(s - kPre, tid - 32);
-            mbar_wait(&sm.mbar[st], (uint32_t)((it / NST) & 1));
-            const int c = tid & 7, rg = tid >> 3;
-            cplx acc = mk(0.0, 0.0);
-            for (int r = rg; r < R; r += NRG) {
-                if ((r >> 3) == p) continue;
-                cplx rv = mk(sm.stage[st][0][c >> 2][r][c & 3], sm.stage[st][1][c >> 2][r][c & 3]);
-                cfma(acc, rv, sm.y[r]);
-            }
+        if (warp == 0) {
+            bar_arrive(SB_X0, NTHR);        // the first two far jobs need no new x
+            bar_arrive(SB_X1, NTHR);
+            const int c = lane & 7, q = lane >> 3;
+            for (int k = 0; k < n; ++k) {
+                const int s = sHi - 1 - k, p = s % T, p1 = (s + 1) % T, it = itBase + k, st = it % NST;
+                mbar_wait(&sm.mbar[st], (uint32_t)((it / NST) & 1));
+                // contribution of block s+1 (x written by this warp one iteration ago): rows 2q, 2q+1 of slot p1, column c
+                cplx acc = mk(0.0, 0.0);
+                if (T > 1) {
 #pragma unroll
-            for (int off = 8; off <= 16; off <<= 1) {
-                acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
-                acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+                    for (int e = 0; e < 2; ++e) {
+                        const int r = p1 * TS + 2 * q + e;
+                        cfma(acc, mk(sm.stage[st][0][c >> 2][r][c & 3], sm.stage[st][1][c >> 2][r][c & 3]), sm.y[r]);
+                    }
+                }
+                bar_sync(SB_F0 + (k & 1), NTHR);                         // far(s): the rows of blocks s+2 .. s+T-1
+                for (int w = q; w < NTHR / 32 - 2; w += 4) acc += sm.part[k & 1][w][c];
+                reduce_rows_in_warp(acc);                                 // d_c in every lane with this c
+                const int ii = lane >> 2, tt = lane & 3;     // lane handles columns 2tt, 2tt+1 of row ii
+                const cplx d0 = mk(__shfl_sync(0xffffffffu, acc.x, 2 * tt), __shfl_sync(0xffffffffu, acc.y, 2 * tt));
+                const cplx d1 = mk(__shfl_sync(0xffffffffu, acc.x, 2 * tt + 1), __shfl_sync(0xffffffffu, acc.y, 2 * tt + 1));
+                cplx xv = sm.az[st][ii * 8 + 2 * tt] * d0 + sm.az[st][ii * 8 + 2 * tt + 1] * d1;
+                reduce_quad(xv);
+                const cplx xo = sm.az[st][64 + ii] - xv;
+                if (tt == 0) sm.y[p * TS + ii] = xo;
+                bar_arrive(SB_X0 + (k & 1), NTHR);                       // x_s published: far(s-2) may start, and stores x_s
             }
-            if (lane < 8) sm.part[warp][lane] = acc;
-            cta_sync();
-            if (warp == 0) {
-                cplx d = mk(0.0, 0.0);
-                for (int w = (lane >> 3); w < NTHR / 32; w += 4) d += sm.part[w][lane & 7];
-#pragma unroll
-                for (int off = 8; off <= 16; off <<= 1) {
-                    d.x += __shfl_xor_sync(0xffffffffu, d.x, off);
-                    d.y += __shfl_xor_sync(0xffffffffu, d.y, off);
-                }
-                const int ii = lane >> 2, tt = lane & 3;
-                cplx d0 = mk(__shfl_sync(0xffffffffu, d.x, 2 * tt), __shfl_sync(0xffffffffu, d.y, 2 * tt));
-                cplx d1 = mk(__shfl_sync(0xffffffffu, d.x, 2 * tt + 1), __shfl_sync(0xffffffffu, d.y, 2 * tt + 1));
-                cplx xv = sm.ainv[st][ii * 8 + 2 * tt] * d0 + sm.ainv[st][ii * 8 + 2 * tt + 1] * d1;
-#pragma unroll
-                for (int off = 1; off <= 2; off <<= 1) {
-                    xv.x += __shfl_xor_sync(0xffffffffu, xv.x, off);
-                    xv.y += __shfl_xor_sync(0xffffffffu, xv.y, off);
-                }
-                if (tt == 0) {
-                    cplx xo = sm.ringZ[k % kRing][ii] - xv;
-                    sm.y[p * TS + ii] = xo;
-                    local_store(L, job.x, s * TS + ii, xo);
-                }
+        } else if (warp == NTHR / 32 - 1) {
+            // service warp: lanes 0..7 store x of step k-2, lane 8 refills its TMA stage (z_s travels with the panel)
+            for (int k = 0; k < n + 2; ++k) {
+                bar_sync(SB_X0 + (k & 1), NTHR);                          // x of step k-2 published (the last two iterations only drain)
+                const int s = sHi - 1 - k, it = itBase + k;
+                if (k >= 2 && lane < 8) local_store(L, job.x, (s + 2) * TS + lane, sm.y[((s + 2) % T) * TS + lane]);
+                if (k >= 2 && lane == 8 && k - 2 + NST < n) issue(s + 2 - NST, it - 2 + NST, -1);
+                if (k >= n) continue;
+                bar_arrive(SB_F0 + (k & 1), NTHR);
             }
-            if (tid >= 32 && tid < 40) sm.ringZ[(k + kPre) % kRing][tid - 32] = prez;
-            cta_sync();
+        } else {
+            const int ft = tid - 32, c = ft & 7, rg = ft >> 3;
+            constexpr int NRG = (NTHR - 64) / 8;          // row groups of the far compute warps
+            for (int k = 0; k < n + 2; ++k) {
+                bar_sync(SB_X0 + (k & 1), NTHR);                          // x of step k-2 published (the last two iterations only drain)
+                if (k >= n) continue;
+                const int s = sHi - 1 - k, p = s % T, p1 = (s + 1) % T, it = itBase + k, st = it % NST;
+                mbar_wait(&sm.mbar[st], (uint32_t)((it / NST) & 1));
+                cplx a0 = mk(0.0, 0.0), a1 = mk(0.0, 0.0);
+#pragma unroll
+                for (int r_b = 0; r_b < R; r_b += 2 * NRG) {
+                    const int r0 = r_b + rg, r1 = r0 + NRG;
+                    if (r0 < R && (r0 >> 3) != p && (r0 >> 3) != p1)
+                        cfma(a0, mk(sm.stage[st][0][c >> 2][r0][c & 3], sm.stage[st][1][c >> 2][r0][c & 3]), sm.y[r0]);
+                    if (r1 < R && (r1 >> 3) != p && (r1 >> 3) != p1)
+                        cfma(a1, mk(sm.stage[st][0][c >> 2][r1][c & 3], sm.stage[st][1][c >> 2][r1][c & 3]), sm.y[r1]);
+                }
+                cplx acc = a0 + a1;
+                reduce_rows_in_warp(acc);
+                if (lane < 8) sm.part[k & 1][warp - 1][lane] = acc;
+                bar_arrive(SB_F0 + (k & 1), NTHR);
+            }
         }
+        cta_sync();
         itBase += n;
     };
 
@@ -214,7 +294,8 @@ band_solve_kernel(const SolveJob* __restrict__ jobs, BandDom dom, int mode) {
     }
     if (mode == FM_FULL) forward_range(0, L.sTot);
     if (mode == FM_SEP) forward_range(L.sOwn, L.sTot);
-    __threadfence();              // zbuf was written by this CTA during the forward sweep (earlier launches are ordered by the stream)
+    fence_proxy_async_all();      // zbuf was written by this CTA during the forward sweep and is read back through TMA
+    __threadfence();              // (earlier launches are ordered by the stream)
     cta_sync();
     for (int i_b = 0; i_b < R; i_b += NTHR) if (const int i = i_b + tid; i < R)
         sm.y[i] = (mode == FM_BACK) ? xsep[rel(i >> 3, L.sOwn) * TS + (i & 7)] : mk(0.0, 0.0);
