@@ -27,6 +27,8 @@ enum { SB_X0 = 1, SB_X1 = 2, SB_F0 = 3, SB_F1 = 4 };      // named barriers of t
 // extra launch mode of the solve kernel: backward sweep only, z read from the factor's [A11^{-1} | z] stream (the fused
 // forward system of the large-bandwidth factorisation, band_big.cuh)
 constexpr int SM_BACKZ = 4;
+// the same for the two halves of a split system (2 CTAs per system, window initialised with the separator solution)
+constexpr int SM_BACKZ_OWN = 5;
 
 template <int T>
 struct SolveSmem {
@@ -59,7 +61,7 @@ band_solve_kernel(const SolveJob* __restrict__ jobs, BandDom dom, int mode) {
     constexpr int R = TS * T, NTHR = kSolveThreads, NST = solve_stages(T);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SolveSmem<T>& sm = *reinterpret_cast<SolveSmem<T>*>(smem_raw);
-    const bool paired = (mode == FM_OWN || mode == FM_BACK);
+    const bool paired = (mode == FM_OWN || mode == FM_BACK || mode == SM_BACKZ_OWN);
     const int rank = paired ? (int)(blockIdx.x & 1) : 0;
     const SolveJob job = jobs[paired ? (blockIdx.x >> 1) : blockIdx.x];
     const LocalDom L = LocalDom::make(dom, rank);
@@ -78,7 +80,7 @@ band_solve_kernel(const SolveJob* __restrict__ jobs, BandDom dom, int mode) {
 
     // rhs may alias x: all rhs reads happen in the FM_OWN / FM_FULL forward sweep (and, for the separator rows, come through
     // the exported windows), all x writes of a split system in the later FM_SEP / FM_BACK launches.
-    if (mode != FM_BACK && mode != SM_BACKZ)
+    if (mode != FM_BACK && mode != SM_BACKZ && mode != SM_BACKZ_OWN)
         for (int i_b = 0; i_b < R; i_b += NTHR) if (const int i = i_b + tid; i < R) {
             cplx v = mk(0.0, 0.0);
             if (mode == FM_SEP) {
@@ -96,7 +98,7 @@ band_solve_kernel(const SolveJob* __restrict__ jobs, BandDom dom, int mode) {
     auto issue = [&](int s, int visit, int dir) {      // dir: +1 forward sweep, -1 backward sweep
         const int st = visit % NST;
         // backward sweep: z_s travels with its panel (from the factor's [A11^{-1} | z] stream, or from this solve's zbuf)
-        const bool zFromFactor = (mode == SM_BACKZ);
+        const bool zFromFactor = (mode == SM_BACKZ || mode == SM_BACKZ_OWN);
         const uint32_t azBytes = (dir < 0 && zFromFactor) ? AZ * 16 : 64 * 16;
         mbar_arrive_expect_tx(&sm.mbar[st], PBYTES + azBytes + ((dir < 0 && !zFromFactor) ? 8 * 16 : 0));
         bulk_g2s(&sm.stage[st][0][0][0][0], panels + (size_t)s * panel_doubles(T), PBYTES, &sm.mbar[st]);
@@ -298,7 +300,7 @@ band_solve_kernel(const SolveJob* __restrict__ jobs, BandDom dom, int mode) {
     __threadfence();              // (earlier launches are ordered by the stream)
     cta_sync();
     for (int i_b = 0; i_b < R; i_b += NTHR) if (const int i = i_b + tid; i < R)
-        sm.y[i] = (mode == FM_BACK) ? xsep[rel(i >> 3, L.sOwn) * TS + (i & 7)] : mk(0.0, 0.0);
+        sm.y[i] = (mode == FM_BACK || mode == SM_BACKZ_OWN) ? xsep[rel(i >> 3, L.sOwn) * TS + (i & 7)] : mk(0.0, 0.0);
     cta_sync();
     if (mode == FM_FULL || mode == SM_BACKZ) {
         backward_range(L.sTot, 0);

@@ -87,11 +87,12 @@ namespace {
 
 // A split system takes three launches in stream order: own lines of both halves, separator, back-substitution of both halves.
 template <int T>
-int launch_factor_T(cudaStream_t st, const BandSys* sys, int nsys, const BandDom& dom) {
+int launch_factor_T(cudaStream_t st, const BandSys* sys, int nsys, const BandDom& dom, const SolveJob* fwdJobs) {
     static bool configured = false;
-    size_t smem = sizeof(FactorSmem<T>);
+    size_t smem = sizeof(FactorSmem<T>), smemSolve = sizeof(SolveSmem<T>);
     if (!configured) {
         HMCMT_CUDA_TRY(cudaFuncSetAttribute(band_factor_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HMCMT_CUDA_TRY(cudaFuncSetAttribute(band_solve_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemSolve));
         configured = true;
     }
     constexpr int NT = FactorCfg<T>::NTHREADS;
@@ -100,7 +101,9 @@ int launch_factor_T(cudaStream_t st, const BandSys* sys, int nsys, const BandDom
     } else {
         band_factor_kernel<T><<<2 * nsys, NT, smem, st>>>(sys, dom, FM_OWN);
         band_factor_kernel<T><<<nsys, NT, smem, st>>>(sys, dom, FM_SEP);
-        band_factor_kernel<T><<<2 * nsys, NT, smem, st>>>(sys, dom, FM_BACK);
+        // back-substitution of the two halves: the pipelined sweep of band_solve.cuh, z read from the factor stream
+        if (fwdJobs) band_solve_kernel<T><<<2 * nsys, kSolveThreads, smemSolve, st>>>(fwdJobs, dom, SM_BACKZ_OWN);
+        else band_factor_kernel<T><<<2 * nsys, NT, smem, st>>>(sys, dom, FM_BACK);
     }
     HMCMT_CUDA_TRY(cudaGetLastError());
     return kOk;
@@ -196,13 +199,13 @@ int round_T(int b) {
 int launch_factor(cudaStream_t st, int T, const BandSys* sys, int nsys, const BandDom& dom, const SolveJob* fwdJobs, int* nLaunches) {
     if (nLaunches) *nLaunches = dom.split ? 3 : 1;
     switch (T) {
-        case 2: return launch_factor_T<2>(st, sys, nsys, dom);
-        case 4: return launch_factor_T<4>(st, sys, nsys, dom);
-        case 6: return launch_factor_T<6>(st, sys, nsys, dom);
-        case 8: return launch_factor_T<8>(st, sys, nsys, dom);
-        case 10: return launch_factor_T<10>(st, sys, nsys, dom);
-        case 12: return launch_factor_T<12>(st, sys, nsys, dom);
-        case 14: return launch_factor_T<14>(st, sys, nsys, dom);
+        case 2: return launch_factor_T<2>(st, sys, nsys, dom, fwdJobs);
+        case 4: return launch_factor_T<4>(st, sys, nsys, dom, fwdJobs);
+        case 6: return launch_factor_T<6>(st, sys, nsys, dom, fwdJobs);
+        case 8: return launch_factor_T<8>(st, sys, nsys, dom, fwdJobs);
+        case 10: return launch_factor_T<10>(st, sys, nsys, dom, fwdJobs);
+        case 12: return launch_factor_T<12>(st, sys, nsys, dom, fwdJobs);
+        case 14: return launch_factor_T<14>(st, sys, nsys, dom, fwdJobs);
         default:
             if (T > 14 && T <= kBigMaxT && T % 4 == 0 && !dom.split) return launch_factor_big(st, T, sys, nsys, dom, fwdJobs, nLaunches);
             return kErrArg;
@@ -573,7 +576,7 @@ int hmcmt_plan_create(const hmcmt_problem* pr, hmcmt_plan** out) {
     ok(pl->wexp.alloc(pl->dom.split ? nSys * wexpN : 0));
     const size_t bigN = pl->T > 14 ? big_work_entries(pl->T) : 0;
     ok(pl->bigWork.alloc(nSys * bigN));
-    ok(pl->fwdJobs.alloc(bigN ? nSys : 0));
+    ok(pl->fwdJobs.alloc(nSys));
     ok(pl->status.alloc(nSys)); ok(pl->driftFlag.alloc(1)); ok(pl->Lsteps.alloc(nCh));
     ok(pl->sysDesc.alloc(nSys)); ok(pl->jobs.alloc(nSys));
     if (rc) { hmcmt_destroy(pl); return rc; }
