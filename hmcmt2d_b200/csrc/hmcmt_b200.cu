@@ -366,7 +366,11 @@ int compute_step(hmcmt_plan* pl, bool wantAdjoint, const cplx* vin) {
     }
     k_stencil_planes<<<dim3((M.N + 255) / 256, nCh * pl->nModes), 256, 0, st>>>(M, pl->sm, pl->sigma.p, pl->planes.p);
     LAUNCH_CHECK(pl);
-    k_boundary<<<dim3((M.ny + 1 + 63) / 64, nSys), 64, 0, st>>>(M, pl->sm, pl->freqs.p, pl->sigma.p, pl->bc.p);
+    {
+        const int PB = boundary_profiles_per_block(M.nz);
+        k_boundary<<<dim3((M.ny + 1 + PB - 1) / PB, nCh * pl->sm.nFreq), kBcThreads, (size_t)PB * M.nz * 6 * sizeof(cplx), st>>>(
+            M, pl->sm, pl->freqs.p, pl->sigma.p, pl->bc.p, PB);
+    }
     LAUNCH_CHECK(pl);
     k_rhs<<<dim3((M.N + 255) / 256, nSys), 256, 0, st>>>(M, pl->sm, pl->sigma.p, pl->bc.p, pl->rhs.p);
     LAUNCH_CHECK(pl);

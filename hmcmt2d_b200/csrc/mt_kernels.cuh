@@ -115,44 +115,73 @@ __device__ __forceinline__ double prof_sigma(const MeshDev& M, const double* __r
 __device__ __forceinline__ cplx wavenumber(double omega, double s) {
     return csqrt_(mk(kMu0 * kEps0 * omega * omega, -kMu0 * s * omega));
 }
-// systems: sys = (ch*2+mode)*nFreq + f.   grid: (ceil((ny+1)/64), nSys), block 64
-__global__ void k_boundary(MeshDev M, SysMap sm, const double* __restrict__ freqs, const double* __restrict__ sigma,
-                           cplx* __restrict__ bc) {
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    const int sys = blockIdx.y;
-    const int ny = M.ny, nz = M.nz;
-    if (p > ny) return;                         // ny+1 profiles (2 + ny-1) and ny+1 top-row entries
-    cplx* out = bc + (size_t)sys * M.nb;
-    out[p] = mk(1.0, 0.0);                      // top row
-    int ch, mi, mode, f;
-    sys_decode(sm, sys, ch, mi, mode, f);
+// The layered-earth recursion depends on (chain, frequency, profile) only: it is computed once and written to every mode
+// (TE: E = eu+ed, TM: H = (ed-eu) k / (omega mu)).  The expensive per-layer terms (wavenumber, tanh, exponentials, ratios)
+// do not depend on the recursion state: phase A evaluates them for all layers of the block's PB profiles in parallel into
+// shared memory, phase B runs the two serial recursions (a few complex multiplies / divisions per layer) one thread per profile.
+// systems: sys = (ch*nModes+mi)*nFreq + f.   grid: (ceil((ny+1)/PB), nChains*nFreq), block kBcThreads, smem PB*nz*6 complex
+constexpr int kBcThreads = 128;
+__host__ __device__ inline int boundary_profiles_per_block(int nz) {
+    int pb = (int)((44 * 1024) / (6 * sizeof(cplx) * (size_t)nz));
+    return pb < 1 ? 1 : (pb > 8 ? 8 : pb);
+}
+__global__ void __launch_bounds__(kBcThreads)
+k_boundary(MeshDev M, SysMap sm, const double* __restrict__ freqs, const double* __restrict__ sigma, cplx* __restrict__ bc, int PB) {
+    extern __shared__ __align__(16) unsigned char bcraw[];
+    cplx* const sh = reinterpret_cast<cplx*>(bcraw);          // [PB][6][nz]: k, tanh(ikh), exp(ikh), exp(-ikh), omu/k, k_j/k_{j+1}
+    const int ch = blockIdx.y / sm.nFreq, f = blockIdx.y - ch * sm.nFreq;
+    const int ny = M.ny, nz = M.nz, p0 = blockIdx.x * PB;
     const double* sig = sigma + (size_t)ch * M.nCell;
     const double omega = 2.0 * kPi * freqs[f], omu = omega * kMu0;
+    auto A = [&](int pl, int which) { return sh + ((size_t)pl * 6 + which) * nz; };
+    for (int item = threadIdx.x; item < PB * nz; item += kBcThreads) {
+        const int pl = item / nz, j = item - pl * nz, p = p0 + pl;
+        if (p > ny) continue;
+        const cplx k = wavenumber(omega, prof_sigma(M, sig, p, j));
+        const cplx kh = k * M.zLen[j];
+        A(pl, 0)[j] = k;
+        A(pl, 1)[j] = ctanh_(mk(-kh.y, kh.x));          // tanh(i k h)
+        A(pl, 2)[j] = cexp_(mk(-kh.y, kh.x));
+        A(pl, 3)[j] = cexp_(mk(kh.y, -kh.x));
+        A(pl, 4)[j] = omu / k;
+    }
+    __syncthreads();
+    for (int item = threadIdx.x; item < PB * nz; item += kBcThreads) {
+        const int pl = item / nz, j = item - pl * nz;
+        if (p0 + pl > ny) continue;
+        A(pl, 5)[j] = A(pl, 0)[j] / A(pl, 0)[(j + 1 < nz) ? j + 1 : nz - 1];
+    }
+    __syncthreads();
+    const int p = p0 + threadIdx.x;
+    if ((int)threadIdx.x >= PB || p > ny) return;               // ny+1 profiles (2 + ny-1) and ny+1 top-row entries
+    const cplx *K = A(threadIdx.x, 0), *TH = A(threadIdx.x, 1), *EP = A(threadIdx.x, 2), *EM = A(threadIdx.x, 3),
+               *ZP = A(threadIdx.x, 4), *KR = A(threadIdx.x, 5);
+    cplx* out[2];
+    int modes[2];
+    const int nM = sm.nModes;
+    for (int mi = 0; mi < nM; ++mi) {
+        out[mi] = bc + (size_t)((ch * sm.nModes + mi) * sm.nFreq + f) * M.nb;
+        modes[mi] = mi == 0 ? sm.mode0 : sm.mode1;
+        out[mi][p] = mk(1.0, 0.0);              // top row
+    }
     // bottom-up impedance recursion
-    cplx k = wavenumber(omega, prof_sigma(M, sig, p, nz - 1));
-    cplx zt = omu / k;
+    cplx zt = ZP[nz - 1];
     for (int j = nz - 1; j >= 0; --j) {
-        k = wavenumber(omega, prof_sigma(M, sig, p, j));
-        cplx zp = omu / k;
-        cplx kh = k * M.zLen[j];
-        cplx th = ctanh_(mk(-kh.y, kh.x));          // tanh(i k h)
+        const cplx zp = ZP[j], th = TH[j];
         zt = zp * (zt + zp * th) / (zp + zt * th);
     }
-    cplx r0 = omu / (zt * k);                       // k == k of the top layer here
+    const cplx k = K[0];
+    cplx r0 = omu / (zt * k);
     cplx eu = 0.5 * (mk(1.0, 0.0) - r0), ed = 0.5 * (mk(1.0, 0.0) + r0);
-    cplx top;                                        // E[0] or H[0]
-    if (mode == 0) top = eu + ed;
-    else top = (ed * k - eu * k) / omu;
-    cplx* col = (p == 0) ? out + ny + 1 : (p == 1) ? out + ny + 1 + nz : nullptr;
-    cplx ki = k, last = top;
+    auto field = [&](int mode, cplx kk) { return (mode == 0) ? eu + ed : (ed * kk - eu * kk) / omu; };   // E or H
+    cplx top[2], last[2];
+    for (int mi = 0; mi < nM; ++mi) { top[mi] = field(modes[mi], k); last[mi] = top[mi]; }
+    const int colOff = (p == 0) ? ny + 1 : (p == 1) ? ny + 1 + nz : -1;
     bool dead = false;
     for (int i = 0; i < nz; ++i) {
-        cplx val = mk(0.0, 0.0);
+        bool live = false;
         if (!dead) {
-            cplx kn = wavenumber(omega, prof_sigma(M, sig, p, (i + 1 < nz) ? i + 1 : nz - 1));
-            cplx kr = ki / kn;
-            cplx kh = ki * M.zLen[i];
-            cplx ep = cexp_(mk(-kh.y, kh.x)), em = cexp_(mk(kh.y, -kh.x));
+            const cplx kr = KR[i], ep = EP[i], em = EM[i];
             cplx one = mk(1.0, 0.0);
             cplx a = 0.5 * (one + kr), bq = 0.5 * (one - kr);
             cplx nu = (a * ep) * eu + (bq * em) * ed;
@@ -161,14 +190,19 @@ __global__ void k_boundary(MeshDev M, SysMap sm, const double* __restrict__ freq
             if (e2 - e1 > 0.0 || isnan(e2)) {
                 dead = true;                       // mt1DField.jl:77-81: zero all deeper entries
             } else {
-                eu = nu; ed = nd; ki = kn;
-                val = (mode == 0) ? eu + ed : (ed * ki - eu * ki) / omu;
+                eu = nu; ed = nd;
+                live = true;
             }
         }
-        last = val;
-        if (col) col[i] = val / top;
+        const cplx ki = K[(i + 1 < nz) ? i + 1 : nz - 1];
+        for (int mi = 0; mi < nM; ++mi) {
+            const cplx val = live ? field(modes[mi], ki) : mk(0.0, 0.0);
+            last[mi] = val;
+            if (colOff >= 0) out[mi][colOff + i] = val / top[mi];
+        }
     }
-    if (p >= 2) out[ny + 1 + 2 * nz + (p - 2)] = last / top;
+    if (p >= 2)
+        for (int mi = 0; mi < nM; ++mi) out[mi][ny + 1 + 2 * nz + (p - 2)] = last[mi] / top[mi];
 }
 
 // rhs = -Aio*bc in internal ordering (mt2DTE.jl:44).  grid: (ceil(N/256), nSys)
@@ -437,6 +471,9 @@ struct ProfScalars {         // per (system, profile), arrays of length nz+1 (la
     cplx* dz1;               // d Z_top / d sigma_layer   (zimpDeri)
     cplx* z1;                // [1]
     int* jbreak;             // [1] index j at which the overflow guard fired (nz if never)
+    cplx* kr;                // [nz] ka[j]/ka[j+1]            } layer transfer factors of the top-down propagation, shared by
+    cplx* expt;              // [nz] exp(i ka[j] h_j)          } every column of the sensitivity recursion (sens_column)
+    cplx* expr;              // [nz] 1/expt
 };
 __device__ __forceinline__ double sens_sigma(const MeshDev& M, const double* __restrict__ sig, int prof, int k, const double* meanSig) {
     if (prof == 0) return sig[k * M.ny];
@@ -460,13 +497,14 @@ __global__ void k_row_mean(int ny, int nz, const double* __restrict__ sigma, dou
     if (threadIdx.x == 0) meanSig[(size_t)ch * nz + k] = sh[0] / ny;
 }
 
-// scratch layout per (sys,prof): 5*(nz+1) cplx + 1 cplx + pad ; see prof_ptrs
-__host__ __device__ inline size_t prof_stride(int nz) { return 5 * (size_t)(nz + 1) + 2; }
+// scratch layout per (sys,prof): 5*(nz+1) cplx + 1 cplx + pad + 3*nz cplx ; see prof_ptrs
+__host__ __device__ inline size_t prof_stride(int nz) { return 5 * (size_t)(nz + 1) + 2 + 3 * (size_t)nz; }
 __device__ __forceinline__ ProfScalars prof_ptrs(cplx* base, int nz) {
     ProfScalars P;
     P.ka = base; P.dka = base + (nz + 1); P.eu = base + 2 * (nz + 1); P.ed = base + 3 * (nz + 1);
     P.dz1 = base + 4 * (nz + 1); P.z1 = base + 5 * (nz + 1);
     P.jbreak = reinterpret_cast<int*>(base + 5 * (nz + 1) + 1);
+    P.kr = base + 5 * (nz + 1) + 2; P.expt = P.kr + nz; P.expr = P.expt + nz;
     return P;
 }
 // serial part: one thread per (sys, prof).  grid: ceil(nSys*3/64), block 64
@@ -535,6 +573,7 @@ __global__ void k_sens_scalars(MeshDev M, SysMap sm, int nSys, const double* __r
         cplx kh = P.ka[j] * M.zLen[j];
         cplx expt = cexp_(mk(-kh.y, kh.x));
         cplx expr = 1.0 / expt;
+        P.kr[j] = kr; P.expt[j] = expt; P.expr[j] = expr;      // reused (bit-identical) by every sens_column
         cplx one = mk(1.0, 0.0);
         cplx nu = (0.5 * (one + kr) * expt) * eu + (0.5 * (one - kr) * expr) * ed;
         cplx nd = (0.5 * (one - kr) * expt) * eu + (0.5 * (one + kr) * expr) * ed;
@@ -591,10 +630,7 @@ __device__ inline cplx sens_column(const MeshDev& M, const ProfScalars& P, int m
         // row j+1 from row j
         if (j > jb) { dEu = dEd = dHu = dHd = zero; if (lastRowOnly) continue; else continue; }
         const cplx kaj = P.ka[j], kaj1 = P.ka[j + 1];
-        const cplx kr = kaj / kaj1;
-        const cplx kh = kaj * M.zLen[j];
-        const cplx expt = cexp_(mk(-kh.y, kh.x));
-        const cplx expr = 1.0 / expt;
+        const cplx kr = P.kr[j], expt = P.expt[j], expr = P.expr[j];      // computed once per profile in k_sens_scalars
         cplx dexpt = zero, dexpr = zero, dkr = zero;
         if (kp == j) {
             dexpt = mk(0.0, M.zLen[j]) * expt * P.dka[j];
@@ -632,7 +668,7 @@ __device__ inline cplx sens_column(const MeshDev& M, const ProfScalars& P, int m
 // ---------------------------------------------------------------------------------------------
 // K10: gradient contraction, one CTA per system -> Gpart[sys][nCell] (real part of the cell gradient)
 //   TE: compJacTMatVec.jl:235-244 ; TM: :306-318 ; Q term :198-214, :269-285 ; final real() :325-327
-constexpr int kConThreads = 256;
+constexpr int kConThreads = 320;      // >= 3*nz columns of the per-column recursions at nz = 100: one round
 __global__ void __launch_bounds__(kConThreads)
 k_contract(MeshDev M, SysMap sm, const double* __restrict__ freqs, const double* __restrict__ sigma,
            const cplx* __restrict__ F, const cplx* __restrict__ Lam, const cplx* __restrict__ srows,
