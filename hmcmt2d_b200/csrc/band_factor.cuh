@@ -218,7 +218,9 @@ struct EntryProvider {
 __device__ __forceinline__ void gj_invert8(cplx& a0, cplx& a1, bool& bad, const int i, const int t) {
     const int j0 = 2 * t;
     cplx q = mk(1.0, 0.0);
-#pragma unroll
+    // kept rolled: the 8x unrolled body (~800 instructions, executed once per macro-step by one warp) only added instruction
+    // fetch pressure; measured macro-step time is the same either way (the warp shares its scheduler with three tile warps)
+#pragma unroll 1
     for (int k = 0; k < 8; ++k) {
         const int srcRow = 4 * k + t, srcCol = 4 * i + (k >> 1), srcPiv = 4 * k + (k >> 1);
         const cplx mine = (k & 1) ? a1 : a0;

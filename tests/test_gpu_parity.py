@@ -180,3 +180,34 @@ def test_batched_chains_equal_single_chains():
     for c in range(3):
         pred, phi, g = pl1.forward_gradient(ms[c])
         assert np.array_equal(pred[0], pred3[c]) and phi[0] == phi3[c] and np.array_equal(g[0], g3[c])      # bit-identical
+
+
+def test_cfg5_finite_difference_check():
+    """BASELINE.json configs[4]: examples/coprod2 geometry, forward / gradient finite-difference check on the GPU path.
+    Central differences h = 1e-5 in ln(sigma) of the data misfit on probe cells away from the bottom 5 cell rows (the
+    reference's boundary-derivative approximations live there) against the adjoint gradient."""
+    from hmcmt2d_b200 import api
+    mesh, data, inv, prior = load_example("coprod2")
+    pm, pd, pi, pp = to_product(mesh, data, inv, prior)
+    rng = np.random.default_rng(5)
+    m = np.log(0.01) + 0.7 * rng.standard_normal(len(inv.strModel))
+    pl = api.Plan(pm, pd, pi, pp)
+    _, phi0, g = pl.forward_gradient(m)
+    g = g[0]
+    ny, nz = mesh.gridSize
+    nair = len(mesh.airLayer)
+    nrows = nz - nair                                    # earth cell rows (active cells are the earth cells, row-major)
+    assert len(m) == ny * nrows
+    rows = rng.integers(0, nrows - 5, size=10)
+    cols = rng.integers(2, ny - 2, size=10)
+    h = 1e-5
+    worst = 0.0
+    for r, c in zip(rows, cols):
+        a = int(r) * ny + int(c)
+        mp, mm = m.copy(), m.copy()
+        mp[a] += h
+        mm[a] -= h
+        fd = (pl.forward_gradient(mp)[1][0] - pl.forward_gradient(mm)[1][0]) / (2 * h)
+        worst = max(worst, abs(fd - g[a]) / np.abs(g).max())
+    assert worst < 1e-4, worst
+    pl.close()
