@@ -419,7 +419,7 @@ int compute_step(hmcmt_plan* pl, bool wantAdjoint, const cplx* vin) {
     LAUNCH_CHECK(pl);
     HMCMT_CUDA_TRY(cudaStreamWaitEvent(st, pl->evJoin, 0));
     size_t cSmem = (size_t)(5 * M.nz + (M.ny - 1) + M.ny) * sizeof(cplx);
-    k_contract<<<nSys, kConThreads, cSmem, st>>>(M, pl->sm, pl->freqs.p, pl->sigma.p, pl->F.p, pl->Lam.p, pl->srows.p, pl->qrow.p,
+    k_contract<<<dim3(nSys, kConChunks), kConThreads, cSmem, st>>>(M, pl->sm, pl->freqs.p, pl->sigma.p, pl->F.p, pl->Lam.p, pl->srows.p, pl->qrow.p,
                                                  pl->bcs.p, pl->scratch.p, pl->Gpart.p);
     LAUNCH_CHECK(pl);
     k_reduce_grad<<<dim3((pl->nAC + 255) / 256, nCh), 256, 0, st>>>(pl->nAC, M.nCell, pl->nSysPerChain, pl->act2cell.p, pl->Gpart.p,

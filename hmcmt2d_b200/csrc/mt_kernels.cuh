@@ -123,7 +123,7 @@ __device__ __forceinline__ cplx wavenumber(double omega, double s) {
 constexpr int kBcThreads = 128;
 __host__ __device__ inline int boundary_profiles_per_block(int nz) {
     int pb = (int)((44 * 1024) / (6 * sizeof(cplx) * (size_t)nz));
-    return pb < 1 ? 1 : (pb > 8 ? 8 : pb);
+    return pb < 1 ? 1 : (pb > 8 ? 8 : pb);      // the serial phase keeps PB lanes of one warp busy: as many as shared memory allows
 }
 __global__ void __launch_bounds__(kBcThreads)
 k_boundary(MeshDev M, SysMap sm, const double* __restrict__ freqs, const double* __restrict__ sigma, cplx* __restrict__ bc, int PB) {
@@ -178,6 +178,7 @@ k_boundary(MeshDev M, SysMap sm, const double* __restrict__ freqs, const double*
     for (int mi = 0; mi < nM; ++mi) { top[mi] = field(modes[mi], k); last[mi] = top[mi]; }
     const int colOff = (p == 0) ? ny + 1 : (p == 1) ? ny + 1 + nz : -1;
     bool dead = false;
+    double e1 = cabs_(eu + ed);                    // |E| of the previous row: the guard compares consecutive rows
     for (int i = 0; i < nz; ++i) {
         bool live = false;
         if (!dead) {
@@ -186,19 +187,22 @@ k_boundary(MeshDev M, SysMap sm, const double* __restrict__ freqs, const double*
             cplx a = 0.5 * (one + kr), bq = 0.5 * (one - kr);
             cplx nu = (a * ep) * eu + (bq * em) * ed;
             cplx nd = (bq * ep) * eu + (a * em) * ed;
-            double e2 = cabs_(nu + nd), e1 = cabs_(eu + ed);
+            double e2 = cabs_(nu + nd);
             if (e2 - e1 > 0.0 || isnan(e2)) {
                 dead = true;                       // mt1DField.jl:77-81: zero all deeper entries
             } else {
-                eu = nu; ed = nd;
+                eu = nu; ed = nd; e1 = e2;
                 live = true;
             }
         }
-        const cplx ki = K[(i + 1 < nz) ? i + 1 : nz - 1];
-        for (int mi = 0; mi < nM; ++mi) {
-            const cplx val = live ? field(modes[mi], ki) : mk(0.0, 0.0);
-            last[mi] = val;
-            if (colOff >= 0) out[mi][colOff + i] = val / top[mi];
+        // the two edge columns need every row, a bottom profile only its last one
+        if (colOff >= 0 || i == nz - 1) {
+            const cplx ki = K[(i + 1 < nz) ? i + 1 : nz - 1];
+            for (int mi = 0; mi < nM; ++mi) {
+                const cplx val = live ? field(modes[mi], ki) : mk(0.0, 0.0);
+                last[mi] = val;
+                if (colOff >= 0) out[mi][colOff + i] = val / top[mi];
+            }
         }
     }
     if (p >= 2)
@@ -474,6 +478,13 @@ struct ProfScalars {         // per (system, profile), arrays of length nz+1 (la
     cplx* kr;                // [nz] ka[j]/ka[j+1]            } layer transfer factors of the top-down propagation, shared by
     cplx* expt;              // [nz] exp(i ka[j] h_j)          } every column of the sensitivity recursion (sens_column)
     cplx* expr;              // [nz] 1/expt
+    cplx* m11;               // [nz] (1+kr) expt   } the 2x2 layer transfer matrix
+    cplx* m12;               // [nz] (1-kr) expr   }
+    cplx* m21;               // [nz] (1-kr) expt   }
+    cplx* m22;               // [nz] (1+kr) expr   }
+    cplx* kao;               // [nz] ka[j+1] / (omega mu)
+    cplx* dS;                // [4*nz] d(layer matrix j)/d sigma_j     (d11,d12,d21,d22)
+    cplx* dN;                // [4*nz] d(layer matrix j)/d sigma_{j+1}
 };
 __device__ __forceinline__ double sens_sigma(const MeshDev& M, const double* __restrict__ sig, int prof, int k, const double* meanSig) {
     if (prof == 0) return sig[k * M.ny];
@@ -497,14 +508,16 @@ __global__ void k_row_mean(int ny, int nz, const double* __restrict__ sigma, dou
     if (threadIdx.x == 0) meanSig[(size_t)ch * nz + k] = sh[0] / ny;
 }
 
-// scratch layout per (sys,prof): 5*(nz+1) cplx + 1 cplx + pad + 3*nz cplx ; see prof_ptrs
-__host__ __device__ inline size_t prof_stride(int nz) { return 5 * (size_t)(nz + 1) + 2 + 3 * (size_t)nz; }
+// scratch layout per (sys,prof): 5*(nz+1) cplx + 1 cplx + pad + 16*nz cplx ; see prof_ptrs
+__host__ __device__ inline size_t prof_stride(int nz) { return 5 * (size_t)(nz + 1) + 2 + 16 * (size_t)nz; }
 __device__ __forceinline__ ProfScalars prof_ptrs(cplx* base, int nz) {
     ProfScalars P;
     P.ka = base; P.dka = base + (nz + 1); P.eu = base + 2 * (nz + 1); P.ed = base + 3 * (nz + 1);
     P.dz1 = base + 4 * (nz + 1); P.z1 = base + 5 * (nz + 1);
     P.jbreak = reinterpret_cast<int*>(base + 5 * (nz + 1) + 1);
     P.kr = base + 5 * (nz + 1) + 2; P.expt = P.kr + nz; P.expr = P.expt + nz;
+    P.m11 = P.expr + nz; P.m12 = P.m11 + nz; P.m21 = P.m12 + nz; P.m22 = P.m21 + nz; P.kao = P.m22 + nz;
+    P.dS = P.kao + nz; P.dN = P.dS + 4 * nz;
     return P;
 }
 // serial part: one thread per (sys, prof).  grid: ceil(nSys*3/64), block 64
@@ -573,8 +586,23 @@ __global__ void k_sens_scalars(MeshDev M, SysMap sm, int nSys, const double* __r
         cplx kh = P.ka[j] * M.zLen[j];
         cplx expt = cexp_(mk(-kh.y, kh.x));
         cplx expr = 1.0 / expt;
-        P.kr[j] = kr; P.expt[j] = expt; P.expr[j] = expr;      // reused (bit-identical) by every sens_column
         cplx one = mk(1.0, 0.0);
+        // per-layer factors reused (bit-identical) by every column of the sensitivity recursion (sens_column)
+        P.kr[j] = kr; P.expt[j] = expt; P.expr[j] = expr;
+        P.m11[j] = (one + kr) * expt; P.m12[j] = (one - kr) * expr; P.m21[j] = (one - kr) * expt; P.m22[j] = (one + kr) * expr;
+        P.kao[j] = P.ka[j + 1] / omu;
+        {   // derivatives of the layer matrix w.r.t. its own layer (kp == j) and the next one (kp == j+1), MT1DSensitivity.jl:100-118
+            const cplx kaj = P.ka[j], kaj1 = P.ka[j + 1];
+            const cplx dexpt = mk(0.0, M.zLen[j]) * expt * P.dka[j];
+            const cplx dexpr = mk(0.0, -M.zLen[j]) * expr * P.dka[j];
+            cplx dkr = P.dka[j] / kaj1;
+            P.dS[4 * j + 0] = (one + kr) * dexpt + expt * dkr; P.dS[4 * j + 1] = (one - kr) * dexpr - expr * dkr;
+            P.dS[4 * j + 2] = (one - kr) * dexpt - expt * dkr; P.dS[4 * j + 3] = (one + kr) * dexpr + expr * dkr;
+            const cplx zero = mk(0.0, 0.0);
+            dkr = zero - kaj / (kaj1 * kaj1) * P.dka[j + 1];
+            P.dN[4 * j + 0] = (one + kr) * zero + expt * dkr; P.dN[4 * j + 1] = (one - kr) * zero - expr * dkr;
+            P.dN[4 * j + 2] = (one - kr) * zero - expt * dkr; P.dN[4 * j + 3] = (one + kr) * zero + expr * dkr;
+        }
         cplx nu = (0.5 * (one + kr) * expt) * eu + (0.5 * (one - kr) * expr) * ed;
         cplx nd = (0.5 * (one - kr) * expt) * eu + (0.5 * (one + kr) * expr) * ed;
         double e2 = cabs_(nu + nd), e1 = cabs_(eu + ed);
@@ -629,32 +657,36 @@ __device__ inline cplx sens_column(const MeshDev& M, const ProfScalars& P, int m
     for (int j = 0; j < nz; ++j) {
         // row j+1 from row j
         if (j > jb) { dEu = dEd = dHu = dHd = zero; if (lastRowOnly) continue; else continue; }
-        const cplx kaj = P.ka[j], kaj1 = P.ka[j + 1];
-        const cplx kr = P.kr[j], expt = P.expt[j], expr = P.expr[j];      // computed once per profile in k_sens_scalars
-        cplx dexpt = zero, dexpr = zero, dkr = zero;
-        if (kp == j) {
-            dexpt = mk(0.0, M.zLen[j]) * expt * P.dka[j];
-            dexpr = mk(0.0, -M.zLen[j]) * expr * P.dka[j];
-            dkr = P.dka[j] / kaj1;
-        }
-        if (kp == j + 1) dkr = dkr - kaj / (kaj1 * kaj1) * P.dka[j + 1];
-        const cplx m11 = (one + kr) * expt, m12 = (one - kr) * expr, m21 = (one - kr) * expt, m22 = (one + kr) * expr;
-        const cplx d11 = (one + kr) * dexpt + expt * dkr, d12 = (one - kr) * dexpr - expr * dkr;
-        const cplx d21 = (one - kr) * dexpt - expt * dkr, d22 = (one + kr) * dexpr + expr * dkr;
         const cplx eu = P.eu[j], ed = P.ed[j];
-        cplx nEu = 0.5 * (d11 * eu + m11 * dEu + d12 * ed + m12 * dEd);
-        cplx nEd = 0.5 * (d21 * eu + m21 * dEu + d22 * ed + m22 * dEd);
+        // (d11 d12; d21 d22) = d/dsigma_kp of the layer matrix: non-zero only for kp == j or kp == j+1
+        cplx nEu, nEd;
+        if (kp == j || kp == j + 1) {
+            const cplx* D = (kp == j) ? P.dS + 4 * j : P.dN + 4 * j;      // precomputed once per layer in k_sens_scalars
+            nEu = 0.5 * (D[0] * eu + P.m11[j] * dEu + D[1] * ed + P.m12[j] * dEd);
+            nEd = 0.5 * (D[2] * eu + P.m21[j] * dEu + D[3] * ed + P.m22[j] * dEd);
+        } else {                                      // the derivative terms are exact zeros: same sums without them
+            nEu = 0.5 * (P.m11[j] * dEu + P.m12[j] * dEd);
+            nEd = 0.5 * (P.m21[j] * dEu + P.m22[j] * dEd);
+        }
         // NB at j == jb the reference computes row j+1 from the *pre-guard* amplitudes and then zeroes
         // columns >= j+1 of that row (MT1DSensitivity.jl:131-151); P.eu/ed[j+1] are already zero there, but
         // dHu/dHd use epu/epd = the freshly propagated (non-zeroed) amplitudes, so recompute them.
-        cplx epu = P.eu[j + 1], epd = P.ed[j + 1];
-        if (j == jb) {
-            epu = (0.5 * (one + kr) * expt) * eu + (0.5 * (one - kr) * expr) * ed;
-            epd = (0.5 * (one - kr) * expt) * eu + (0.5 * (one + kr) * expr) * ed;
+        const cplx kao = P.kao[j];
+        cplx nHu, nHd;
+        if (kp == j + 1) {
+            cplx epu = P.eu[j + 1], epd = P.ed[j + 1];
+            if (j == jb) {
+                const cplx kr = P.kr[j], expt = P.expt[j], expr = P.expr[j];
+                epu = (0.5 * (one + kr) * expt) * eu + (0.5 * (one - kr) * expr) * ed;
+                epd = (0.5 * (one - kr) * expt) * eu + (0.5 * (one + kr) * expr) * ed;
+            }
+            const cplx dk1 = P.dka[j + 1];
+            nHu = -(epu / omu) * dk1 - kao * nEu;
+            nHd = (epd / omu) * dk1 + kao * nEd;
+        } else {
+            nHu = -(kao * nEu);
+            nHd = kao * nEd;
         }
-        const cplx dk1 = (kp == j + 1) ? P.dka[j + 1] : zero;
-        cplx nHu = -(epu / omu) * dk1 - kaj1 / omu * nEu;
-        cplx nHd = (epd / omu) * dk1 + kaj1 / omu * nEd;
         if (j == jb && kp >= j + 1) { nEu = nEd = nHu = nHd = zero; }
         dEu = nEu; dEd = nEd; dHu = nHu; dHd = nHd;
         cplx dF = (mode == 0) ? dEu + dEd : dHu + dHd;
@@ -666,9 +698,11 @@ __device__ inline cplx sens_column(const MeshDev& M, const ProfScalars& P, int m
 }
 
 // ---------------------------------------------------------------------------------------------
-// K10: gradient contraction, one CTA per system -> Gpart[sys][nCell] (real part of the cell gradient)
+// K10: gradient contraction, kConChunks CTAs per system (each repeats the short boundary-column phase and contracts its share
+// of the cells) -> Gpart[sys][nCell] (real part of the cell gradient)
 //   TE: compJacTMatVec.jl:235-244 ; TM: :306-318 ; Q term :198-214, :269-285 ; final real() :325-327
 constexpr int kConThreads = 320;      // >= 3*nz columns of the per-column recursions at nz = 100: one round
+constexpr int kConChunks = 4;
 __global__ void __launch_bounds__(kConThreads)
 k_contract(MeshDev M, SysMap sm, const double* __restrict__ freqs, const double* __restrict__ sigma,
            const cplx* __restrict__ F, const cplx* __restrict__ Lam, const cplx* __restrict__ srows,
@@ -746,7 +780,8 @@ k_contract(MeshDev M, SysMap sm, const double* __restrict__ freqs, const double*
         if (jn == ny) return bs[ny + 1 + nz + (kn - 1)];
         return bs[ny + 1 + 2 * nz + (jn - 1)];
     };
-    for (int c = tid; c < M.nCell; c += kConThreads) {
+    const int cPer = (M.nCell + kConChunks - 1) / kConChunks, cBeg = (int)blockIdx.y * cPer, cEnd = min(M.nCell, cBeg + cPer);
+    for (int c = cBeg + tid; c < cEnd; c += kConThreads) {
         const int kc = c / ny, jc = c - kc * ny;
         const double dy = M.yLen[jc], dz = M.zLen[kc], area = dy * dz;
         cplx g = mk(0.0, 0.0);
