@@ -6,10 +6,11 @@
 // the sliding window lives: T x T tiles no longer fit one SM's register file, so the window is a circular R x R
 // array in global memory (L2-resident: 1.6 MB per system at b = 299) and the elimination advances kBigNBK = 4
 // macro-steps (32 columns) per pair of stream-ordered launches:
-//   bigband_panel_kernel   one CTA per system: loads the 32 panel columns into shared memory, eliminates the four
-//                          8x8 pivot blocks one after the other (same in-register Gauss-Jordan as the register
-//                          kernel), forms M' = -raw A11^{-1}, forward-eliminates the fused right-hand side and writes
-//                          the four factor panels;
+//   bigband_panel_kernel   kBigSplit CTAs per system: each loads the 32 pivot rows of the panel plus its share of the other
+//                          window rows into shared memory, eliminates the four 8x8 pivot blocks one after the other
+//                          (same in-register Gauss-Jordan as the register kernel; redundantly in every CTA, so the CTAs
+//                          never talk), forms M' = -raw A11^{-1} for its rows, forward-eliminates the fused right-hand
+//                          side and writes its rows of the four factor panels;
 //   bigband_update_kernel  many CTAs per system: rank-32 update of the trailing window with FP64 tensor-core MMAs
 //                          (DMMA.8x8x4), one warp per 8x8 tile, operands straight from L2/L1; four extra CTAs
 //                          refill the recycled window rows from the stencil (assembly stays fused, the matrix is
@@ -24,14 +25,19 @@ namespace hmcmt {
 constexpr int kBigNBK = 4;          // 8-column blocks per panel launch
 constexpr int kBigPanStride = 9;    // complex entries per shared-memory panel row (8 + 1 pad: conflict-free 16-byte accesses)
 constexpr int kBigMaxT = 44;        // window of 44 tiles: b <= 8 * (44 - kBigNBK) = 320
+constexpr int kBigSplit = 8;        // CTAs per system in the panel kernel
 
 __host__ __device__ constexpr int big_T_for(int b) { return ((b + 7) / 8 + kBigNBK + 3) / 4 * 4; }
-// per-system workspace (complex entries): window R*R | M' [NBK][R][8] | raw [NBK][R][8] | rhs window [R]
+// per-system workspace (complex entries): window R*R | M' [NBK][R][8] | raw [NBK][R][8] | rhs window [2][R] (by panel parity)
 __host__ __device__ constexpr size_t big_work_entries(int T) {
-    return (size_t)(TS * T) * (TS * T) + 2 * (size_t)kBigNBK * (TS * T) * 8 + (size_t)(TS * T);
+    return (size_t)(TS * T) * (TS * T) + 2 * (size_t)kBigNBK * (TS * T) * 8 + 2 * (size_t)(TS * T);
+}
+// local rows of one panel CTA: 32 pivot rows + its share of the others, rounded up so that 2 threads per row fill whole warps
+__host__ __device__ constexpr int big_panel_local_rows(int T) {
+    return (kBigNBK * TS + (TS * T - kBigNBK * TS + kBigSplit - 1) / kBigSplit + 15) / 16 * 16;
 }
 __host__ __device__ constexpr size_t big_panel_smem_bytes(int T) {
-    return ((size_t)kBigNBK * (TS * T) * kBigPanStride + (size_t)(TS * T) + 64 + 8) * sizeof(cplx) + 16;
+    return ((size_t)kBigNBK * big_panel_local_rows(T) * kBigPanStride + (size_t)big_panel_local_rows(T) + 64 + 8) * sizeof(cplx);
 }
 
 struct BigView {
@@ -78,51 +84,67 @@ bigband_init_kernel(const BandSys* __restrict__ systems, BandDom dom, int T) {
             v.ywin[r] = (sys.rhs && r < L.nLoc) ? prov.rhs_at(sys.rhs, r) : mk(0.0, 0.0);
 }
 
-// grid nsys, 2R threads (thread = window row r, column half h), dynamic smem = big_panel_smem_bytes(T)
-__global__ void __launch_bounds__(2 * TS * kBigMaxT, 1)
+// grid (kBigSplit, nsys).  The 32 pivot rows of the panel (its 32x32 diagonal block) are factored redundantly by every CTA
+// of a system — that is the serial part, four 8x8 inversions — and the remaining window rows are divided among the CTAs:
+// given the diagonal block's factors the row blocks are independent, so there is no communication between the CTAs.
+// Local rows: 0..31 = pivot rows (block c -> rows 8c..8c+7), then this CTA's share of the other window rows.
+// Threads: 2 per local row (column half h).  CTA 0 alone writes what belongs to the pivot rows.
+// The rhs window is double-buffered by panel parity (every CTA reads all pivot rows of it while CTA 0 rewrites them).
+// dynamic smem = big_panel_smem_bytes(T)
+__global__ void __launch_bounds__(2 * big_panel_local_rows(kBigMaxT))
 bigband_panel_kernel(const BandSys* __restrict__ systems, BandDom dom, int T, int k) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int R = TS * T;
-    cplx* const pan = reinterpret_cast<cplx*>(smem_raw);                  // [NBK][R][kBigPanStride]
-    cplx* const ysh = pan + (size_t)kBigNBK * R * kBigPanStride;          // [R]
-    cplx* const ainv = ysh + R;                                           // [64] row-major A11^{-1}
+    constexpr int ND = kBigNBK * TS;                                      // pivot rows
+    const int chunk = (R - ND + kBigSplit - 1) / kBigSplit;              // other rows per CTA
+    const int NL = big_panel_local_rows(T);                               // local rows (>= ND + chunk; the surplus is idle)
+    cplx* const pan = reinterpret_cast<cplx*>(smem_raw);                  // [NBK][NL][kBigPanStride]
+    cplx* const ysh = pan + (size_t)kBigNBK * NL * kBigPanStride;         // [NL]
+    cplx* const ainv = ysh + NL;                                          // [64] row-major A11^{-1}
     cplx* const zsh = ainv + 64;                                          // [8]
-    int* const failp = reinterpret_cast<int*>(zsh + 8);
 
-    const BandSys sys = systems[blockIdx.x];
+    const BandSys sys = systems[blockIdx.y];
     const LocalDom L = LocalDom::make(dom, 0);
     EntryProvider prov{sys.dr, sys.dm, sys.e1, sys.e2, sys.band, sys.omega, dom.b, L};
     BigView v(sys.big, R);
+    const cplx* const yin = v.ywin + (size_t)(k & 1) * R;
+    cplx* const yout = v.ywin + (size_t)((k + 1) & 1) * R;
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-    const int r = tid >> 1, h = tid & 1;
-    const int s0 = k * kBigNBK;
+    const int lr = tid >> 1, h = tid & 1;                                 // local row, column half
+    const int s0 = k * kBigNBK, q0 = s0 % T;                              // the pivot slots are q0 .. q0+3 (T % 4 == 0: no wrap)
     const int nsub = min(kBigNBK, L.sTot - s0);
-    const int beta = big_block_of_slot(r >> 3, s0, T);
-    auto P = [&](int c, int row, int col) -> cplx& { return pan[((size_t)c * R + row) * kBigPanStride + col]; };
+    const bool first = blockIdx.x == 0;
+    // window row of this local row (-1: none): pivot rows first, then the chunk of the remaining rows in window order
+    int r = -1;
+    if (lr < ND) r = q0 * TS + lr;
+    else {
+        const int o = (int)blockIdx.x * chunk + (lr - ND);               // index among the R - ND non-pivot rows
+        if (lr - ND < chunk && o < R - ND) r = o < q0 * TS ? o : o + ND;
+    }
+    const bool owner = r >= 0 && (lr >= ND || first);                     // writes this row's results
+    const int beta = r >= 0 ? big_block_of_slot(r >> 3, s0, T) : -1;
+    auto P = [&](int c, int row, int col) -> cplx& { return pan[((size_t)c * NL + row) * kBigPanStride + col]; };
 
     for (int c = 0; c < kBigNBK; ++c) {
-        const int pc = (s0 + c) % T;
-        const bool live = c < nsub && beta >= s0 + c;
+        const bool live = r >= 0 && c < nsub && beta >= s0 + c;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) P(c, r, 4 * h + j) = live ? v.win[(size_t)r * R + pc * TS + 4 * h + j] : mk(0.0, 0.0);
+        for (int j = 0; j < 4; ++j) P(c, lr, 4 * h + j) = live ? v.win[(size_t)r * R + (q0 + c) * TS + 4 * h + j] : mk(0.0, 0.0);
     }
-    if (h == 0) ysh[r] = v.ywin[r];
-    if (tid == 0) *failp = 0;
+    if (h == 0) ysh[lr] = r >= 0 ? yin[r] : mk(0.0, 0.0);
     __syncthreads();
 
     for (int c = 0; c < nsub; ++c) {
-        const int pc = (s0 + c) % T;
         if (warp == 0) {
             const int i = lane >> 2, t = lane & 3;
-            cplx a0 = P(c, pc * TS + i, 2 * t), a1 = P(c, pc * TS + i, 2 * t + 1);
+            cplx a0 = P(c, c * TS + i, 2 * t), a1 = P(c, c * TS + i, 2 * t + 1);
             bool bad = false;
             gj_invert8(a0, a1, bad, i, t);
             bad = __any_sync(0xffffffffu, bad);
-            if (bad && lane == 0) { *failp = 1; if (sys.status) *sys.status = kErrSingular; }
+            if (bad && lane == 0 && first && sys.status) *sys.status = kErrSingular;
             ainv[i * 8 + 2 * t] = a0;
             ainv[i * 8 + 2 * t + 1] = a1;
-            cplx acc = a0 * ysh[pc * TS + 2 * t] + a1 * ysh[pc * TS + 2 * t + 1];
+            cplx acc = a0 * ysh[c * TS + 2 * t] + a1 * ysh[c * TS + 2 * t + 1];
 #pragma unroll
             for (int off = 1; off <= 2; off <<= 1) {
                 acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
@@ -130,28 +152,32 @@ bigband_panel_kernel(const BandSys* __restrict__ systems, BandDom dom, int T, in
             }
             if (!sys.rhs) acc = mk(0.0, 0.0);
             if (t == 0) zsh[i] = acc;
-            cplx* dz = sys.ainvz[0] + (size_t)(s0 + c) * AZ;
-            dz[i * 8 + 2 * t] = a0;
-            dz[i * 8 + 2 * t + 1] = a1;
-            if (t == 0) dz[64 + i] = acc;
+            if (first) {
+                cplx* dz = sys.ainvz[0] + (size_t)(s0 + c) * AZ;
+                dz[i * 8 + 2 * t] = a0;
+                dz[i * 8 + 2 * t + 1] = a1;
+                if (t == 0) dz[64 + i] = acc;
+            }
         }
         __syncthreads();
         // M'[r][4h..4h+3] = -sum_k raw[r][k] A11^{-1}[k][4h+j]   (all rows: the partner exchange below must be warp-converged).
-        // Register budget (704 threads -> 88 registers): raw is streamed from shared memory, never held as an array.
+        // raw is streamed from shared memory, never held as an array (register budget).
         const bool below = beta > s0 + c;
         cplx m[4] = {mk(0.0, 0.0), mk(0.0, 0.0), mk(0.0, 0.0), mk(0.0, 0.0)};
         cplx yacc = mk(0.0, 0.0);
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
-            const cplx rv = P(c, r, kk);
+            const cplx rv = P(c, lr, kk);
 #pragma unroll
             for (int j = 0; j < 4; ++j) cfma(m[j], -rv, ainv[kk * 8 + 4 * h + j]);
             cfma(yacc, -rv, zsh[kk]);
         }
-        if (below && h == 0 && sys.rhs) ysh[r] = ysh[r] + yacc;
+        if (below && h == 0 && sys.rhs) ysh[lr] = ysh[lr] + yacc;
         // operands of the trailing update (plain [c][r][8] layout, L2-resident)
+        if (owner) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v.mscr[((size_t)c * R + r) * 8 + 4 * h + j] = below ? m[j] : mk(0.0, 0.0);
+            for (int j = 0; j < 4; ++j) v.mscr[((size_t)c * R + r) * 8 + 4 * h + j] = below ? m[j] : mk(0.0, 0.0);
+        }
         {
             cplx mf[8];
 #pragma unroll
@@ -163,24 +189,23 @@ bigband_panel_kernel(const BandSys* __restrict__ systems, BandDom dom, int T, in
 #pragma unroll
             for (int c2 = 1; c2 < kBigNBK; ++c2) {
                 if (c2 <= c || c2 >= nsub || !below || beta < s0 + c2) continue;
-                const int p2 = (s0 + c2) % T;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    cplx acc = P(c2, r, 4 * h + j);
+                    cplx acc = P(c2, lr, 4 * h + j);
 #pragma unroll
-                    for (int kk = 0; kk < 8; ++kk) cfma(acc, mf[kk], P(c, p2 * TS + 4 * h + j, kk));
-                    P(c2, r, 4 * h + j) = acc;
+                    for (int kk = 0; kk < 8; ++kk) cfma(acc, mf[kk], P(c, c2 * TS + 4 * h + j, kk));
+                    P(c2, lr, 4 * h + j) = acc;
                 }
             }
         }
         cplx rawh[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) rawh[j] = P(c, r, 4 * h + j);
+        for (int j = 0; j < 4; ++j) rawh[j] = P(c, lr, 4 * h + j);
+        if (owner) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v.rscr[((size_t)c * R + r) * 8 + 4 * h + j] = below ? rawh[j] : mk(0.0, 0.0);
-        // factor panel of macro-step s0+c in the solve kernels' image layout [re/im][kk][R][4]; rows of blocks already
-        // eliminated in this launch are outside the band of this panel: zero
-        {
+            for (int j = 0; j < 4; ++j) v.rscr[((size_t)c * R + r) * 8 + 4 * h + j] = below ? rawh[j] : mk(0.0, 0.0);
+            // factor panel of macro-step s0+c in the solve kernels' image layout [re/im][kk][R][4]; rows of blocks already
+            // eliminated in this launch are outside the band of this panel: zero
             double* img = sys.panels[0] + (size_t)(s0 + c) * panel_doubles(T);
             const bool keep = beta >= s0 + c;
             double2 re01 = make_double2(0.0, 0.0), re23 = re01, im01 = re01, im23 = re01;
@@ -195,14 +220,14 @@ bigband_panel_kernel(const BandSys* __restrict__ systems, BandDom dom, int T, in
         }
         __syncthreads();
     }
-    // rhs window: the slots of the eliminated blocks now hold blocks +T
-    if (h == 0) {
-        cplx yv = ysh[r];
+    // rhs window of the next panel: the slots of the eliminated blocks now hold blocks +T
+    if (h == 0 && owner) {
+        cplx yv = ysh[lr];
         if (beta < s0 + nsub) {
             const int gr = (beta + T) * TS + (r & 7);
             yv = (sys.rhs && gr < L.nLoc) ? prov.rhs_at(sys.rhs, gr) : mk(0.0, 0.0);
         }
-        v.ywin[r] = yv;
+        yout[r] = yv;
     }
 }
 
