@@ -152,7 +152,7 @@ struct FactorSmem {
     int fail;
 };
 
-enum { BAR_RAW = 1, BAR_INV = 2, BAR_M = 3, BAR_GJ = 4 };
+enum { BAR_RAW = 1, BAR_INV = 2, BAR_M = 3, BAR_GJ = 4 /* and 5: alternates with the step parity */ };
 // what one launch does: the whole system / own lines of both halves / separator (+ its back-substitution) / back-substitution of the halves
 enum FactorMode { FM_FULL = 0, FM_OWN = 1, FM_SEP = 2, FM_BACK = 3 };
 __host__ __device__ constexpr size_t split_scratch_entries(int R) { return 2 * (size_t)R * R + 3 * (size_t)R; }
@@ -516,7 +516,10 @@ band_factor_kernel(const BandSys* __restrict__ systems, BandDom dom, int mode) {
                 // The tile warps that share a scheduler (and its FP64 / DMMA pipe) with the factor warp hold their bulk of
                 // DMMAs back until it has inverted the next pivot block: that inversion is the serial chain of the loop and
                 // ran 1.5x slower when it had to compete for the pipe.
-                if ((warp & 3) == (NW & 3)) bar_sync(BAR_GJ, kGateThreads);
+                // Two barrier ids alternating with the step parity: the factor warp only arrives, so with a single id it
+                // could arrive for step s+1 before a slow tile warp has waited for step s (it is held back by BAR_RAW one
+                // step later, which makes the alternating pair safe).
+                if ((warp & 3) == (NW & 3)) bar_sync(BAR_GJ + (s & 1), kGateThreads);
                 // pass 2: the rest of the trailing window
 #pragma unroll
                 for (int i = 0; i < TPW; ++i) {
@@ -622,7 +625,7 @@ band_factor_kernel(const BandSys* __restrict__ systems, BandDom dom, int mode) {
                     invert();
                     publish(buf ^ 1);
                 }
-                bar_arrive(BAR_GJ, kGateThreads);              // releases the tile warps on this warp's scheduler into pass 2
+                bar_arrive(BAR_GJ + (s & 1), kGateThreads);    // releases the tile warps on this warp's scheduler into pass 2
                 // ring slot of step s+kPre: its previous content (step s+kPre-kRing) was consumed before BAR_M(s+kPre-kRing)
                 sm.ringRow[(s + kPre) % kRing][lane >> 3][lane & 7] = rowv;
                 if (lane < 8) sm.ringRhs[(s + kPre) % kRing][lane] = rhsv;

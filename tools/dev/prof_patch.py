@@ -2,7 +2,7 @@
 import sys
 src, dst = sys.argv[1], sys.argv[2]
 s = open(src).read()
-s = s.replace("enum { BAR_RAW = 1, BAR_INV = 2, BAR_M = 3, BAR_GJ = 4 };", "enum { BAR_RAW = 1, BAR_INV = 2, BAR_M = 3, BAR_GJ = 4 };\n__device__ unsigned long long g_prof[32];\n#define PT(k) do { if (blockIdx.x == 0 && lane == 0) { unsigned long long _n = clock64(); prof[k] += _n - tlast; tlast = _n; } } while (0)")
+s = s.replace("enum { BAR_RAW = 1, BAR_INV = 2, BAR_M = 3, BAR_GJ = 4 /* and 5: alternates with the step parity */ };", "enum { BAR_RAW = 1, BAR_INV = 2, BAR_M = 3, BAR_GJ = 4 /* and 5: alternates with the step parity */ };\n__device__ unsigned long long g_prof[32];\n#define PT(k) do { if (blockIdx.x == 0 && lane == 0) { unsigned long long _n = clock64(); prof[k] += _n - tlast; tlast = _n; } } while (0)")
 def rep(a, b):
     global s
     assert a in s, a[:60]
