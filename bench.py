@@ -129,6 +129,10 @@ def cpu_steps_per_sec(nworkers: int, nfreq_sample: int, repeats: int = 1, cfg=No
     """Times `nfreq_sample` of the 30 frequencies farmed over `nworkers` processes and extrapolates to the full
     step (frequencies are independent and cost the same: identical sparsity pattern)."""
     import multiprocessing as mp
+    # one process per core, ONE thread per process: the workers inherit these (spawn) before they import numpy / scipy —
+    # without them every worker starts a full BLAS / OpenMP team and the oversubscribed host takes minutes per sample
+    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+        os.environ[var] = "1"
     cfg = cfg or WORKLOAD
     freqs = list(np.linspace(0, cfg["nfreq"] - 1, nfreq_sample).astype(int))
     ctx = mp.get_context("spawn")
