@@ -42,7 +42,10 @@ METRIC = "leapfrog_steps_per_sec"
 UNIT = "steps/s"
 WORKLOAD = dict(workload="cfg2: synthetic 200x100-cell mesh, 30 frequencies, TE+TM, 1 HMC chain per GPU",
                 ny=200, nz=100, nfreq=30, nrx=40, modes="TE+TM", chains_per_gpu=1)
-NCU_FACTOR_DRAM_BYTES = 2.264725e9 + 2.312753e9     # per launch, profiles/r01_factor_ncu.txt
+# dram__bytes_read + dram__bytes_write of the factorisation group per step: FM_OWN capture (24.3 MB + 2.251 GB,
+# profiles/r01_final_factor_own_ncu.txt) + its back-substitution sweep, which streams the factor once exactly like the
+# captured solve sweep (2.279 GB + 23.6 MB, profiles/r01_final_solve_own_ncu.txt); FM_SEP (13 of 2476 macro-steps) neglected
+NCU_FACTOR_DRAM_BYTES = (24.28e6 + 2.250943e9) + (2.278771e9 + 23.64e6)
 FP64_DMMA_PEAK_TFLOPS = 37.1     # measured on this pool's B200 with DMMA.8x8x4 (profiles/r01_fp64_peak_ubench.txt)
 
 
@@ -266,12 +269,13 @@ def run_gpu(args, rank, world, local_rank):
     bytes_launch = 2.0 * 16.0 * N * (b + 1) * nsys
     fac_ms = factor_ms / max(1, factor_n)
     achieved = flops_launch / (fac_ms * 1e-3) / 1e12
-    roofline = dict(bound="tensor", kernel="band_factor_kernel<14> (FP64 DMMA.8x8x4 block LDL^T + fused fwd/back substitution)",
+    roofline = dict(bound="tensor", kernel="factorisation of the 60 systems = band_factor_kernel<14> FM_OWN + FM_SEP (FP64 DMMA.8x8x4 block LDL^T, "
+                    "fused assembly + forward elimination) + band_solve_kernel<14> SM_BACKZ_OWN (its back-substitution), timed as one unit",
                     achieved=achieved, peak=FP64_DMMA_PEAK_TFLOPS, unit="TFLOP/s", frac=achieved / FP64_DMMA_PEAK_TFLOPS,
                     peak_source="measured FP64 DMMA m8n8k4 rate on this pool's B200 (profiles/r01_fp64_peak_ubench.txt); "
                                 "MEASURED_PEAKS.json holds only bf16/HBM peaks: " + peak_src,
-                    traffic=NCU_FACTOR_DRAM_BYTES, traffic_source="dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture "
-                                   "of this kernel at this workload (profiles/r01_factor_ncu.txt)",
+                    traffic=NCU_FACTOR_DRAM_BYTES, traffic_source="dram__bytes_read.sum + dram__bytes_write.sum of ncu --set full captures at this workload: FM_OWN launch "
+                                   "(profiles/r01_final_factor_own_ncu.txt) + one factor-streaming sweep (profiles/r01_final_solve_own_ncu.txt)",
                     algorithmic_flops_per_launch=flops_launch, algorithmic_bytes_per_launch=bytes_launch,
                     hbm_achieved_gbs=bytes_launch / (fac_ms * 1e-3) / 1e9, hbm_peak_gbs=peaks.get("hbm_gbs"),
                     avg_launch_ms=fac_ms, launches_timed=factor_n, share_of_step=fac_ms / (ms / K))
