@@ -32,6 +32,9 @@
 // serves the forward solve (back-substitution fused below) and the adjoint solve (band_solve.cuh).
 #pragma once
 #include <type_traits>
+#ifndef HMCMT_GATE_ALL
+#define HMCMT_GATE_ALL 0      // 1: every tile warp waits for the inversion before pass 2 (measured slower: 141.6 vs 144.9 steps/s at cfg2)
+#endif
 
 #include "common.cuh"
 
@@ -262,7 +265,8 @@ __global__ void __launch_bounds__(FactorCfg<T>::NTHREADS, 1)
 band_factor_kernel(const BandSys* __restrict__ systems, BandDom dom, int mode) {
     using Cfg = FactorCfg<T>;
     constexpr int NW = Cfg::NW, TPW = Cfg::TPW, R = Cfg::R, NTHR = Cfg::NTHREADS;
-    constexpr int kGateThreads = 32 * (NW / 4 + 1);      // warps w <= NW with w % 4 == NW % 4 (the factor warp's scheduler)
+    constexpr bool kGateAll = HMCMT_GATE_ALL;
+    constexpr int kGateThreads = kGateAll ? NTHR : 32 * (NW / 4 + 1);      // warps w <= NW with w % 4 == NW % 4 (the factor warp's scheduler)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FactorSmem<T>& sm = *reinterpret_cast<FactorSmem<T>*>(smem_raw);
 
@@ -519,7 +523,7 @@ band_factor_kernel(const BandSys* __restrict__ systems, BandDom dom, int mode) {
                 // Two barrier ids alternating with the step parity: the factor warp only arrives, so with a single id it
                 // could arrive for step s+1 before a slow tile warp has waited for step s (it is held back by BAR_RAW one
                 // step later, which makes the alternating pair safe).
-                if ((warp & 3) == (NW & 3)) bar_sync(BAR_GJ + (s & 1), kGateThreads);
+                if (kGateAll || (warp & 3) == (NW & 3)) bar_sync(BAR_GJ + (s & 1), kGateThreads);
                 // pass 2: the rest of the trailing window
 #pragma unroll
                 for (int i = 0; i < TPW; ++i) {
