@@ -161,11 +161,15 @@ band_solve_kernel(const SolveJob* __restrict__ jobs, BandDom dom, int mode) {
                 __syncwarp();
             }
             bar_sync(SB_F0 + ((n - 1) & 1), NTHR);
-        } else if (warp == NTHR / 32 - 1) {
+        } else {
+            // far warps (1..6) and the service warp (7) share one loop, so that every named barrier has a single waiting and
+            // a single arriving instruction.
             // service warp: everything that touches global memory, kept off both the near chain and the far arithmetic.
             // lanes 0..7 store z_s, lane 8 refills the TMA stage of step s-1, lanes 16..23 feed the rhs ring with cp.async
             // issued kRhsAhead steps before the rows are needed, so the warp never waits on a load
-            const int rl = lane - 16;
+            const bool service = warp == NTHR / 32 - 1;
+            const int ft = tid - 32, rl = lane - 16;
+            constexpr int NFC = NTHR - 64;         // far compute threads: one per window row
             auto rhs_fetch = [&](int step) {     // rhs rows of the block entering the window at `step` -> ring, asynchronously
                 if (rl >= 0 && rl < 8) {
                     int kind, lrel;
@@ -176,39 +180,36 @@ band_solve_kernel(const SolveJob* __restrict__ jobs, BandDom dom, int mode) {
                 }
                 cp_async_commit();
             };
-            for (int q = 0; q < kRhsAhead; ++q) rhs_fetch(sLo + q);
-            cp_async_wait<kRhsAhead - 1>();
-            for (int k = 0; k < n; ++k) {
-                const int s = sLo + k, it = itBase + k;
-                bar_sync(SB_X0 + (k & 1), NTHR);                         // z_s ready
-                if (lane < 8) zbuf[(size_t)s * 8 + lane] = sm.zv[k & 1][lane];
-                // the stage of step s-1 is free: near is past it and far(s-1) arrived on SB_F before this warp's previous arrive
-                if (lane == 8 && k >= 1 && k - 1 + NST < n) issue(s - 1 + NST, it - 1 + NST, +1);
-                rhs_fetch(s + kRhsAhead);
-                cp_async_wait<kRhsAhead - 1>();                           // the rows of step s+1 have landed
-                bar_arrive(SB_F0 + (k & 1), NTHR);
+            if (service) {
+                for (int q = 0; q < kRhsAhead; ++q) rhs_fetch(sLo + q);
+                cp_async_wait<kRhsAhead - 1>();
             }
-        } else {
-            const int ft = tid - 32;
-            constexpr int NFC = NTHR - 64;         // far compute threads: one per window row
             for (int k = 0; k < n; ++k) {
                 const int s = sLo + k, p = s % T, p1 = (s + 1) % T, it = itBase + k, st = it % NST;
-                mbar_wait(&sm.mbar[st], (uint32_t)((it / NST) & 1));
+                if (!service) mbar_wait(&sm.mbar[st], (uint32_t)((it / NST) & 1));
                 bar_sync(SB_X0 + (k & 1), NTHR);                         // z_s ready
+                if (service) {
+                    if (lane < 8) zbuf[(size_t)s * 8 + lane] = sm.zv[k & 1][lane];
+                    // the stage of step s-1 is free: near is past it and far(s-1) arrived on SB_F in the previous iteration
+                    if (lane == 8 && k >= 1 && k - 1 + NST < n) issue(s - 1 + NST, it - 1 + NST, +1);
+                    rhs_fetch(s + kRhsAhead);
+                    cp_async_wait<kRhsAhead - 1>();                       // the rows of step s+1 have landed
+                } else {
 #pragma unroll
-                for (int r_b = 0; r_b < R; r_b += NFC) {
-                    const int r = r_b + ft;
-                    if (r >= R) continue;
-                    const int slot = r >> 3;
-                    if (slot == p) { sm.y[r] = sm.ringRhs[s % kSolveRing][r & 7]; continue; }      // recycle: slot p now holds local block s+T
-                    if (slot == p1) continue;                                                     // the near warp's block
-                    cplx a0 = sm.y[r], a1 = mk(0.0, 0.0);
+                    for (int r_b = 0; r_b < R; r_b += NFC) {
+                        const int r = r_b + ft;
+                        const int slot = r >> 3;
+                        if (r < R && slot == p) sm.y[r] = sm.ringRhs[s % kSolveRing][r & 7];      // recycle: slot p now holds local block s+T
+                        if (r < R && slot != p && slot != p1) {                                   // (p1 is the near warp's block)
+                            cplx a0 = sm.y[r], a1 = mk(0.0, 0.0);
 #pragma unroll
-                    for (int c = 0; c < 8; c += 2) {
-                        cfma(a0, -mk(sm.stage[st][0][c >> 2][r][c & 3], sm.stage[st][1][c >> 2][r][c & 3]), sm.zv[k & 1][c]);
-                        cfma(a1, -mk(sm.stage[st][0][c >> 2][r][(c & 3) + 1], sm.stage[st][1][c >> 2][r][(c & 3) + 1]), sm.zv[k & 1][c + 1]);
+                            for (int c = 0; c < 8; c += 2) {
+                                cfma(a0, -mk(sm.stage[st][0][c >> 2][r][c & 3], sm.stage[st][1][c >> 2][r][c & 3]), sm.zv[k & 1][c]);
+                                cfma(a1, -mk(sm.stage[st][0][c >> 2][r][(c & 3) + 1], sm.stage[st][1][c >> 2][r][(c & 3) + 1]), sm.zv[k & 1][c + 1]);
+                            }
+                            sm.y[r] = a0 + a1;
+                        }
                     }
-                    sm.y[r] = a0 + a1;
                 }
                 bar_arrive(SB_F0 + (k & 1), NTHR);
             }
@@ -224,8 +225,6 @@ band_solve_kernel(const SolveJob* __restrict__ jobs, BandDom dom, int mode) {
             for (int k = 0; k < NST && k < n; ++k) issue(sHi - 1 - k, itBase + k, -1);
         cta_sync();
         if (warp == 0) {
-            bar_arrive(SB_X0, NTHR);        // the first two far jobs need no new x
-            bar_arrive(SB_X1, NTHR);
             const int c = lane & 7, q = lane >> 3;
             for (int k = 0; k < n; ++k) {
                 const int s = sHi - 1 - k, p = s % T, p1 = (s + 1) % T, it = itBase + k, st = it % NST;
@@ -249,42 +248,46 @@ band_solve_kernel(const SolveJob* __restrict__ jobs, BandDom dom, int mode) {
                 reduce_quad(xv);
                 const cplx xo = sm.az[st][64 + ii] - xv;
                 if (tt == 0) sm.y[p * TS + ii] = xo;
-                bar_arrive(SB_X0 + (k & 1), NTHR);                       // x_s published: far(s-2) may start, and stores x_s
-            }
-        } else if (warp == NTHR / 32 - 1) {
-            // service warp: lanes 0..7 store x of step k-2, lane 8 refills its TMA stage (z_s travels with the panel)
-            for (int k = 0; k < n + 2; ++k) {
-                bar_sync(SB_X0 + (k & 1), NTHR);                          // x of step k-2 published (the last two iterations only drain)
-                const int s = sHi - 1 - k, it = itBase + k;
-                if (k >= 2 && lane < 8) local_store(L, job.x, (s + 2) * TS + lane, sm.y[((s + 2) % T) * TS + lane]);
-                if (k >= 2 && lane == 8 && k - 2 + NST < n) issue(s + 2 - NST, it - 2 + NST, -1);
-                if (k >= n) continue;
-                bar_arrive(SB_F0 + (k & 1), NTHR);
+                __syncwarp();                                             // x_s is read by other lanes of this warp in the next iteration
+                if (k + 2 < n) bar_arrive(SB_X0 + (k & 1), NTHR);        // x_s published: far(s-2) may start (every arrive has its wait)
             }
         } else {
+            // far warps (1..6): partial dot products; service warp (7): lanes 0..7 store x of step k-2, lane 8 refills its TMA
+            // stage (z_s travels with the panel).  One loop for both, see the forward sweep.
+            const bool service = warp == NTHR / 32 - 1;
             const int ft = tid - 32, c = ft & 7, rg = ft >> 3;
             constexpr int NRG = (NTHR - 64) / 8;          // row groups of the far compute warps
-            for (int k = 0; k < n + 2; ++k) {
-                bar_sync(SB_X0 + (k & 1), NTHR);                          // x of step k-2 published (the last two iterations only drain)
-                if (k >= n) continue;
+            for (int k = 0; k < n; ++k) {
+                if (k >= 2) bar_sync(SB_X0 + (k & 1), NTHR);              // x of step k-2 published (the first two jobs need no new x)
                 const int s = sHi - 1 - k, p = s % T, p1 = (s + 1) % T, it = itBase + k, st = it % NST;
-                mbar_wait(&sm.mbar[st], (uint32_t)((it / NST) & 1));
-                cplx a0 = mk(0.0, 0.0), a1 = mk(0.0, 0.0);
+                if (service) {
+                    if (k >= 2 && lane < 8) local_store(L, job.x, (s + 2) * TS + lane, sm.y[((s + 2) % T) * TS + lane]);
+                    if (k >= 2 && lane == 8 && k - 2 + NST < n) issue(s + 2 - NST, it - 2 + NST, -1);
+                } else {
+                    mbar_wait(&sm.mbar[st], (uint32_t)((it / NST) & 1));
+                    cplx a0 = mk(0.0, 0.0), a1 = mk(0.0, 0.0);
 #pragma unroll
-                for (int r_b = 0; r_b < R; r_b += 2 * NRG) {
-                    const int r0 = r_b + rg, r1 = r0 + NRG;
-                    if (r0 < R && (r0 >> 3) != p && (r0 >> 3) != p1)
-                        cfma(a0, mk(sm.stage[st][0][c >> 2][r0][c & 3], sm.stage[st][1][c >> 2][r0][c & 3]), sm.y[r0]);
-                    if (r1 < R && (r1 >> 3) != p && (r1 >> 3) != p1)
-                        cfma(a1, mk(sm.stage[st][0][c >> 2][r1][c & 3], sm.stage[st][1][c >> 2][r1][c & 3]), sm.y[r1]);
+                    for (int r_b = 0; r_b < R; r_b += 2 * NRG) {
+                        const int r0 = r_b + rg, r1 = r0 + NRG;
+                        if (r0 < R && (r0 >> 3) != p && (r0 >> 3) != p1)
+                            cfma(a0, mk(sm.stage[st][0][c >> 2][r0][c & 3], sm.stage[st][1][c >> 2][r0][c & 3]), sm.y[r0]);
+                        if (r1 < R && (r1 >> 3) != p && (r1 >> 3) != p1)
+                            cfma(a1, mk(sm.stage[st][0][c >> 2][r1][c & 3], sm.stage[st][1][c >> 2][r1][c & 3]), sm.y[r1]);
+                    }
+                    cplx acc = a0 + a1;
+                    reduce_rows_in_warp(acc);
+                    if (lane < 8) sm.part[k & 1][warp - 1][lane] = acc;
                 }
-                cplx acc = a0 + a1;
-                reduce_rows_in_warp(acc);
-                if (lane < 8) sm.part[k & 1][warp - 1][lane] = acc;
                 bar_arrive(SB_F0 + (k & 1), NTHR);
             }
         }
         cta_sync();
+        // the solutions of the last two steps (the service warp stores x of step k-2 while step k runs)
+        if (warp == NTHR / 32 - 1 && lane < 8)
+            for (int kk = (n >= 2 ? n - 2 : 0); kk < n; ++kk) {
+                const int sx = sHi - 1 - kk;
+                local_store(L, job.x, sx * TS + lane, sm.y[(sx % T) * TS + lane]);
+            }
         itBase += n;
     };
 
