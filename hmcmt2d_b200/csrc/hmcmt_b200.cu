@@ -44,7 +44,7 @@ struct hmcmt_plan {
     int ny = 0, nz = 0, nFreq = 0, nRx = 0, nData = 0, nAC = 0, nChains = 1, nModes = 0, nComp = 0;
     int modeList[2] = {0, 1};
     int nSysPerChain = 0, nSys = 0, nFull = 0;      // nFull = nFreq*nRx*nModes per chain
-    int T = 0, S = 0, b = 0, device = 0;
+    int T = 0, S = 0, b = 0, device = 0, conStaged = 0, numSMs = 148;
     BandDom dom{};
     int steps0 = 0, steps1 = 0;                     // macro-steps of half 0 (own lines + separator) / half 1 (0 when not split)
     double beta = 1.0, lo = 0.0, hi = 0.0;
@@ -65,7 +65,7 @@ struct hmcmt_plan {
     DevBuf<double> yLen, zLen, zNode, freqs, fdy1, fdy2, wL, wR, bg, wmVal, wd, m, p, mref, sigma, meanSig, planes;
     DevBuf<double> xbuf, Gpart, phiPart, phi, gsig, gdata, gtotal, energies, panels, curM, curP, chainScal, zmom;
     DevBuf<int> fid, iL, iR, cell2act, act2cell, wmPtr, wmIdx, status, driftFlag, packed2full, Lsteps;
-    DevBuf<cplx> obs, bc, bcs, rhs, x, F, lam, Lam, srows, qrow, scratch, predFull, ainvz, zadj, vin, predPacked, wexp, bigWork;
+    DevBuf<cplx> obs, bc, bcs, rhs, x, F, lam, Lam, srows, qrow, scratch, predFull, ainvz, zadj, vin, predPacked, wexp, bigWork, conCols;
     DevBuf<BandSys> sysDesc;
     DevBuf<SolveJob> jobs, fwdJobs;                 // fwdJobs: backward sweeps of the fused forward systems (large-bandwidth path)
     // pinned staging for the host-buffer entry points
@@ -367,6 +367,8 @@ int compute_step(hmcmt_plan* pl, bool wantAdjoint, const cplx* vin) {
     k_stencil_planes<<<dim3((M.N + 255) / 256, nCh * pl->nModes), 256, 0, st>>>(M, pl->sm, pl->sigma.p, pl->planes.p);
     LAUNCH_CHECK(pl);
     {
+        // as many profiles per block as shared memory allows: the serial phase keeps PB lanes of one warp busy and is bound by
+        // FP64 issue slots, so fewer profiles per block (even when that avoids a second wave of blocks) measured slower
         const int PB = boundary_profiles_per_block(M.nz);
         k_boundary<<<dim3((M.ny + 1 + PB - 1) / PB, nCh * pl->sm.nFreq), kBcThreads, (size_t)PB * M.nz * 6 * sizeof(cplx), st>>>(
             M, pl->sm, pl->freqs.p, pl->sigma.p, pl->bc.p, PB);
@@ -418,9 +420,11 @@ int compute_step(hmcmt_plan* pl, bool wantAdjoint, const cplx* vin) {
     k_node_field<<<dim3((M.nNode + 255) / 256, nSys), 256, 0, st>>>(M, pl->lam.p, nullptr, pl->Lam.p);
     LAUNCH_CHECK(pl);
     HMCMT_CUDA_TRY(cudaStreamWaitEvent(st, pl->evJoin, 0));
-    size_t cSmem = (size_t)(5 * M.nz + (M.ny - 1) + M.ny) * sizeof(cplx);
-    k_contract<<<dim3(nSys, kConChunks), kConThreads, cSmem, st>>>(M, pl->sm, pl->freqs.p, pl->sigma.p, pl->F.p, pl->Lam.p, pl->srows.p, pl->qrow.p,
-                                                 pl->bcs.p, pl->scratch.p, pl->Gpart.p);
+    k_contract_cols<<<nSys, kConThreads, contract_cols_smem(M.ny, M.nz, pl->conStaged), st>>>(M, pl->sm, pl->freqs.p, pl->sigma.p, pl->Lam.p,
+                                                                                               pl->srows.p, pl->scratch.p, pl->conCols.p, pl->conStaged);
+    LAUNCH_CHECK(pl);
+    k_contract_cells<<<dim3((M.nCell + 255) / 256, nSys), 256, 0, st>>>(M, pl->sm, pl->freqs.p, pl->sigma.p, pl->F.p, pl->Lam.p, pl->qrow.p,
+                                                                        pl->bcs.p, pl->conCols.p, pl->Gpart.p);
     LAUNCH_CHECK(pl);
     k_reduce_grad<<<dim3((pl->nAC + 255) / 256, nCh), 256, 0, st>>>(pl->nAC, M.nCell, pl->nSysPerChain, pl->act2cell.p, pl->Gpart.p,
                                                                    pl->m.p, pl->mref.p, pl->wmPtr.p, pl->wmIdx.p, pl->wmVal.p, pl->beta,
@@ -462,6 +466,10 @@ int hmcmt_plan_create(const hmcmt_problem* pr, hmcmt_plan** out) {
     hmcmt_plan* pl = new (std::nothrow) hmcmt_plan();
     if (!pl) return kErrAlloc;
     pl->device = pr->device;
+    {
+        int nsm = 0;
+        if (cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, pr->device) == cudaSuccess && nsm > 0) pl->numSMs = nsm;
+    }
     pl->ny = pr->ny; pl->nz = pr->nz; pl->nFreq = pr->nFreq; pl->nRx = pr->nRx; pl->nData = pr->nData; pl->nAC = pr->nAC;
     pl->nChains = pr->nChains; pl->nComp = pr->nComp; pl->nModes = pr->nComp;
     for (int c = 0; c < pr->nComp; ++c) pl->modeList[c] = pr->compMode[c];
@@ -580,6 +588,7 @@ int hmcmt_plan_create(const hmcmt_problem* pr, hmcmt_plan** out) {
     ok(pl->wexp.alloc(pl->dom.split ? nSys * wexpN : 0));
     const size_t bigN = pl->T > 14 ? big_work_entries(pl->T) : 0;
     ok(pl->bigWork.alloc(nSys * bigN));
+    ok(pl->conCols.alloc(nSys * contract_cols_out(ny, nz)));
     ok(pl->fwdJobs.alloc(nSys));
     ok(pl->status.alloc(nSys)); ok(pl->driftFlag.alloc(1)); ok(pl->Lsteps.alloc(nCh));
     ok(pl->sysDesc.alloc(nSys)); ok(pl->jobs.alloc(nSys));
@@ -632,9 +641,10 @@ int hmcmt_plan_create(const hmcmt_problem* pr, hmcmt_plan** out) {
     {
         // wide meshes: the receiver / contraction kernels stage whole node rows in shared memory
         const size_t rxSmem = (size_t)(6 * (M.ny + 1) + 3 * M.ny) * sizeof(cplx);
-        const size_t cSmem = (size_t)(5 * M.nz + (M.ny - 1) + M.ny) * sizeof(cplx);
+        pl->conStaged = contract_cols_smem(M.ny, M.nz, 1) <= 200 * 1024 ? 1 : 0;
+        const size_t cSmem = contract_cols_smem(M.ny, M.nz, pl->conStaged);
         if ((rxSmem > 48 * 1024 && cudaFuncSetAttribute(k_rx_adjoint, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rxSmem) != cudaSuccess) ||
-            (cSmem > 48 * 1024 && cudaFuncSetAttribute(k_contract, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cSmem) != cudaSuccess)) {
+            (cSmem > 48 * 1024 && cudaFuncSetAttribute(k_contract_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cSmem) != cudaSuccess)) {
             hmcmt_destroy(pl);
             return kErrArg;
         }
@@ -670,7 +680,7 @@ void hmcmt_destroy(hmcmt_plan* pl) {
     pl->driftFlag.release(); pl->packed2full.release(); pl->Lsteps.release(); pl->obs.release(); pl->bc.release(); pl->bcs.release();
     pl->rhs.release(); pl->x.release(); pl->F.release(); pl->lam.release(); pl->Lam.release(); pl->srows.release(); pl->qrow.release();
     pl->scratch.release(); pl->predFull.release(); pl->ainvz.release(); pl->zadj.release(); pl->vin.release();
-    pl->predPacked.release(); pl->xbuf.release(); pl->wexp.release(); pl->bigWork.release(); pl->fwdJobs.release(); pl->sysDesc.release(); pl->jobs.release();
+    pl->predPacked.release(); pl->conCols.release(); pl->xbuf.release(); pl->wexp.release(); pl->bigWork.release(); pl->fwdJobs.release(); pl->sysDesc.release(); pl->jobs.release();
     if (pl->pin) cudaFreeHost(pl->pin);
     delete pl;
 }

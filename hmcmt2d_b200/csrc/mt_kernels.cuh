@@ -698,40 +698,48 @@ __device__ inline cplx sens_column(const MeshDev& M, const ProfScalars& P, int m
 }
 
 // ---------------------------------------------------------------------------------------------
-// K10: gradient contraction, kConChunks CTAs per system (each repeats the short boundary-column phase and contracts its share
-// of the cells) -> Gpart[sys][nCell] (real part of the cell gradient)
+// K10: gradient contraction -> Gpart[sys][nCell] (real part of the cell gradient), two kernels:
+//   k_contract_cols   one CTA per system: t = -Aio^T lambda + s[io], then the boundary-derivative columns dBC^T t by per-column
+//                     recursions over the three 1-D profiles (their per-layer factors are staged in shared memory first: the
+//                     recursion is a chain of dependent steps and must not wait on global loads);
+//   k_contract_cells  fully parallel over cells.
 //   TE: compJacTMatVec.jl:235-244 ; TM: :306-318 ; Q term :198-214, :269-285 ; final real() :325-327
 constexpr int kConThreads = 320;      // >= 3*nz columns of the per-column recursions at nz = 100: one round
-constexpr int kConChunks = 4;
+__host__ __device__ inline size_t contract_cols_out(int ny, int nz) { return 3 * (size_t)nz + ny; }      // oL | oR | oM | colw
+// shared memory of k_contract_cols: the t vectors, plus the staged profile scalars when they fit (staged = 1)
+__host__ __device__ inline size_t contract_cols_smem(int ny, int nz, int staged) {
+    return ((size_t)(2 * nz + (ny - 1)) + (staged ? 3 * prof_stride(nz) : 0)) * sizeof(cplx);
+}
 __global__ void __launch_bounds__(kConThreads)
-k_contract(MeshDev M, SysMap sm, const double* __restrict__ freqs, const double* __restrict__ sigma,
-           const cplx* __restrict__ F, const cplx* __restrict__ Lam, const cplx* __restrict__ srows,
-           const cplx* __restrict__ qrow, const cplx* __restrict__ bcs, cplx* __restrict__ scratch,
-           double* __restrict__ Gpart) {
+k_contract_cols(MeshDev M, SysMap sm, const double* __restrict__ freqs, const double* __restrict__ sigma,
+                const cplx* __restrict__ Lam, const cplx* __restrict__ srows, cplx* __restrict__ scratch,
+                cplx* __restrict__ cols, int staged) {
     extern __shared__ __align__(16) unsigned char smraw[];
     const int ny = M.ny, nz = M.nz;
     cplx* tL = reinterpret_cast<cplx*>(smraw);   // nz   (node rows 1..nz)
     cplx* tR = tL + nz;                            // nz
     cplx* tB = tR + nz;                            // ny-1 (nodes jn = 1..ny-1)
-    cplx* oL = tB + (ny - 1);                      // nz : (dBC^T t) on the left cell column
-    cplx* oR = oL + nz;
-    cplx* oM = oR + nz;                            // nz : dE_mean[end, k']
-    cplx* colw = oM + nz;                          // ny
+    cplx* prof = staged ? tB + (ny - 1)            // 3 * prof_stride(nz): the three profiles' scalars, staged
+                        : scratch + (size_t)blockIdx.x * 3 * prof_stride(nz);       // (too deep a mesh: read them in place)
     const int sys = blockIdx.x;
     int ch, mi, mode, f;
     sys_decode(sm, sys, ch, mi, mode, f);
     const int tid = threadIdx.x;
     const double omega = 2.0 * kPi * freqs[f], omu = omega * kMu0;
     const double* sig = sigma + (size_t)ch * M.nCell;
-    const cplx* Fs = F + (size_t)sys * M.nNode;
     const cplx* Ls = Lam + (size_t)sys * M.nNode;
     const cplx* so = srows + (size_t)sys * 2 * (ny + 1);
-    const cplx* bs = bcs + (size_t)sys * M.nb;
+    cplx* out = cols + (size_t)sys * contract_cols_out(ny, nz);
+    cplx *oL = out, *oR = out + nz, *oM = out + 2 * nz, *colw = out + 3 * nz;
     auto node = [&](int jn, int kn) { return (size_t)kn * (ny + 1) + jn; };
     auto sAt = [&](int jn, int kn) {       // s on boundary nodes: only node rows zid, zid+1 are non-zero
         int row = kn - M.zid;
         return (row == 0 || row == 1) ? so[row * (ny + 1) + jn] : mk(0.0, 0.0);
     };
+    if (staged) {
+        const cplx* src = scratch + (size_t)sys * 3 * prof_stride(nz);
+        for (size_t i = tid; i < 3 * prof_stride(nz); i += kConThreads) prof[i] = src[i];
+    }
     // t = -Aio^T lambda + s[io]  (Aio[n,b] = -W(edge n-b)):  t_b = W * lambda_n + s_b
     for (int kn = tid + 1; kn <= nz; kn += kConThreads) {
         cplx l = mk(0.0, 0.0), r = mk(0.0, 0.0);
@@ -751,10 +759,10 @@ k_contract(MeshDev M, SysMap sm, const double* __restrict__ freqs, const double*
     __syncthreads();
     // dBC^T t: per-column recursions (MT1DSensitivity.jl), three profiles
     for (int w = tid; w < 3 * nz; w += kConThreads) {
-        int prof = w / nz, kp = w - prof * nz;
-        ProfScalars P = prof_ptrs(scratch + ((size_t)sys * 3 + prof) * prof_stride(nz), nz);
-        if (prof == 0) oL[kp] = sens_column(M, P, mode, omu, kp, tL, false);
-        else if (prof == 1) oR[kp] = sens_column(M, P, mode, omu, kp, tR, false);
+        int pr = w / nz, kp = w - pr * nz;
+        ProfScalars P = prof_ptrs(prof + (size_t)pr * prof_stride(nz), nz);
+        if (pr == 0) oL[kp] = sens_column(M, P, mode, omu, kp, tL, false);
+        else if (pr == 1) oR[kp] = sens_column(M, P, mode, omu, kp, tR, false);
         else oM[kp] = sens_column(M, P, mode, omu, kp, nullptr, true);
     }
     for (int jc = tid; jc < ny; jc += kConThreads) {
@@ -769,9 +777,28 @@ k_contract(MeshDev M, SysMap sm, const double* __restrict__ freqs, const double*
         }
         colw[jc] = a;
     }
-    __syncthreads();
-    double* G = Gpart + (size_t)sys * M.nCell;
+}
+
+// grid (ceil(nCell/256), nSys), block 256
+__global__ void __launch_bounds__(256)
+k_contract_cells(MeshDev M, SysMap sm, const double* __restrict__ freqs, const double* __restrict__ sigma,
+                 const cplx* __restrict__ F, const cplx* __restrict__ Lam, const cplx* __restrict__ qrow,
+                 const cplx* __restrict__ bcs, const cplx* __restrict__ cols, double* __restrict__ Gpart) {
+    const int ny = M.ny, nz = M.nz;
+    const int sys = blockIdx.y;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= M.nCell) return;
+    int ch, mi, mode, f;
+    sys_decode(sm, sys, ch, mi, mode, f);
+    const double omega = 2.0 * kPi * freqs[f];
+    const double* sig = sigma + (size_t)ch * M.nCell;
+    const cplx* Fs = F + (size_t)sys * M.nNode;
+    const cplx* Ls = Lam + (size_t)sys * M.nNode;
+    const cplx* bs = bcs + (size_t)sys * M.nb;
+    const cplx* in = cols + (size_t)sys * contract_cols_out(ny, nz);
+    const cplx *oL = in, *oR = in + nz, *oM = in + 2 * nz, *colw = in + 3 * nz;
     const cplx* qo = qrow + (size_t)sys * ny;
+    auto node = [&](int jn, int kn) { return (size_t)kn * (ny + 1) + jn; };
     // field with the derivative routine's boundary values (TM term, compJacTMatVec.jl:309,315)
     auto Hf = [&](int jn, int kn) -> cplx {
         if (jn >= 1 && jn <= ny - 1 && kn >= 1 && kn <= nz - 1) return Fs[node(jn, kn)];
@@ -780,47 +807,44 @@ k_contract(MeshDev M, SysMap sm, const double* __restrict__ freqs, const double*
         if (jn == ny) return bs[ny + 1 + nz + (kn - 1)];
         return bs[ny + 1 + 2 * nz + (jn - 1)];
     };
-    const int cPer = (M.nCell + kConChunks - 1) / kConChunks, cBeg = (int)blockIdx.y * cPer, cEnd = min(M.nCell, cBeg + cPer);
-    for (int c = cBeg + tid; c < cEnd; c += kConThreads) {
-        const int kc = c / ny, jc = c - kc * ny;
-        const double dy = M.yLen[jc], dz = M.zLen[kc], area = dy * dz;
-        cplx g = mk(0.0, 0.0);
-        if (mode == 0) {
-            cplx sum = mk(0.0, 0.0);
+    const int kc = c / ny, jc = c - kc * ny;
+    const double dy = M.yLen[jc], dz = M.zLen[kc], area = dy * dz;
+    cplx g = mk(0.0, 0.0);
+    if (mode == 0) {
+        cplx sum = mk(0.0, 0.0);
 #pragma unroll
-            for (int dk = 0; dk < 2; ++dk)
+        for (int dk = 0; dk < 2; ++dk)
 #pragma unroll
-                for (int dj = 0; dj < 2; ++dj) {
-                    int jn = jc + dj, kn = kc + dk;
-                    if (jn >= 1 && jn <= ny - 1 && kn >= 1 && kn <= nz - 1) sum += 0.25 * (Fs[node(jn, kn)] * Ls[node(jn, kn)]);
-                }
-            g = mk(0.0, -omega) * (area * sum);
-        } else {
-            // four edges of the cell: gradient of H (with bcs boundary) times -(gradient of lambda), weight 1/2
-            cplx sum = mk(0.0, 0.0);
-#pragma unroll
-            for (int dk = 0; dk < 2; ++dk) {     // y-edges on node rows kc, kc+1
-                int kn = kc + dk;
-                cplx gh = (Hf(jc + 1, kn) - Hf(jc, kn)) / dy;
-                cplx gl = (Ls[node(jc + 1, kn)] - Ls[node(jc, kn)]) / dy;
-                sum += 0.5 * (gh * (-gl));
+            for (int dj = 0; dj < 2; ++dj) {
+                int jn = jc + dj, kn = kc + dk;
+                if (jn >= 1 && jn <= ny - 1 && kn >= 1 && kn <= nz - 1) sum += 0.25 * (Fs[node(jn, kn)] * Ls[node(jn, kn)]);
             }
+        g = mk(0.0, -omega) * (area * sum);
+    } else {
+        // four edges of the cell: gradient of H (with bcs boundary) times -(gradient of lambda), weight 1/2
+        cplx sum = mk(0.0, 0.0);
 #pragma unroll
-            for (int dj = 0; dj < 2; ++dj) {     // z-edges on node columns jc, jc+1
-                int jn = jc + dj;
-                cplx gh = (Hf(jn, kc + 1) - Hf(jn, kc)) / dz;
-                cplx gl = (Ls[node(jn, kc + 1)] - Ls[node(jn, kc)]) / dz;
-                sum += 0.5 * (gh * (-gl));
-            }
-            const double s = sig[c];
-            g = (area * (-1.0 / (s * s))) * sum;
+        for (int dk = 0; dk < 2; ++dk) {     // y-edges on node rows kc, kc+1
+            int kn = kc + dk;
+            cplx gh = (Hf(jc + 1, kn) - Hf(jc, kn)) / dy;
+            cplx gl = (Ls[node(jc + 1, kn)] - Ls[node(jc, kn)]) / dy;
+            sum += 0.5 * (gh * (-gl));
         }
-        if (jc == 0) g += oL[kc];
-        if (jc == ny - 1) g += oR[kc];
-        g += oM[kc] * colw[jc];
-        if (kc == M.zid) g += qo[jc];
-        G[c] = g.x;
+#pragma unroll
+        for (int dj = 0; dj < 2; ++dj) {     // z-edges on node columns jc, jc+1
+            int jn = jc + dj;
+            cplx gh = (Hf(jn, kc + 1) - Hf(jn, kc)) / dz;
+            cplx gl = (Ls[node(jn, kc + 1)] - Ls[node(jn, kc)]) / dz;
+            sum += 0.5 * (gh * (-gl));
+        }
+        const double s = sig[c];
+        g = (area * (-1.0 / (s * s))) * sum;
     }
+    if (jc == 0) g += oL[kc];
+    if (jc == ny - 1) g += oR[kc];
+    g += oM[kc] * colw[jc];
+    if (kc == M.zid) g += qo[jc];
+    Gpart[(size_t)sys * M.nCell + c] = g.x;
 }
 
 // ---------------------------------------------------------------------------------------------
