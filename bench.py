@@ -58,45 +58,65 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  nvidia-smi needs a moment
+    to start, so it is launched ahead of the warm-up (`start`), `mark` records when the timed region begins, and `stop` keeps
+    the samples whose own timestamps fall inside the region (or, if the region was shorter than one sampling period, the
+    samples taken under the identical load right before it — `window` says which)."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
         self.proc = None
+        self.t_mark = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.proc.stdout.readline()          # blocks until nvidia-smi is up and has printed its first sample
         except Exception:
             self.proc = None
+
+    def mark(self):
+        self.t_mark = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        t_end = time.time()
+        time.sleep(0.06)
         self.proc.terminate()
         try:
             out, _ = self.proc.communicate(timeout=5)
         except Exception:
             self.proc.kill()
             out = ""
-        sm, mx, reasons = [], [], set()
+        import datetime
+        rows = []
         for ln in out.splitlines():
             f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
+            if len(f) < 10:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[2]), float(f[3]), f[6:10]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+        t0 = self.t_mark if self.t_mark is not None else 0.0
+        inside = [r for r in rows if t0 <= r[0] <= t_end + 0.06]
+        window = "timed region"
+        if not inside:
+            inside = rows[-3:]                   # same load (warm-up steps of the same workload) right before the region
+            window = "timed region shorter than the sampling period: last samples under the same load before it"
+        sm, mx, reasons = [], [], set()
+        for _, a, b, flags in inside:
+            sm.append(a); mx.append(b)
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), flags):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def build_problem(cfg=None):
@@ -207,14 +227,15 @@ def run_gpu(args, rank, world, local_rank):
     K, W = args.steps, max(3, args.warmup)
 
     # ---------------- device-resident arm (`value`) ----------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     pl.set_state(m0, p0, m0)
     pl.leapfrog_steps_device(dt, W)
     pl.sync()
     pl.kernel_time(reset=True)
     launches0 = pl.info(10)
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.mark()
     pl.timer_start()
     pl.leapfrog_steps_device(dt, K)
     ms = pl.timer_stop()
@@ -341,14 +362,15 @@ def run_gpu_cfg4(args, rank, world, local_rank):
     dt = prior.dt
     K, W = args.steps, max(3, args.warmup)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     sp.set_state(m0, p0, m0)
     sp.leapfrog_steps_device(dt, W)
     sp.sync()
     pl.kernel_time(reset=True)
     launches0 = pl.info(10)
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.mark()
     pl.timer_start()
     sp.leapfrog_steps_device(dt, K)
     ms = pl.timer_stop()
