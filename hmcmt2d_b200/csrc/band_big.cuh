@@ -9,8 +9,9 @@
 //   bigband_panel_kernel   kBigSplit CTAs per system: each loads the 32 pivot rows of the panel plus its share of the other
 //                          window rows into shared memory, eliminates the four 8x8 pivot blocks one after the other
 //                          (same in-register Gauss-Jordan as the register kernel; redundantly in every CTA, so the CTAs
-//                          never talk), forms M' = -raw A11^{-1} for its rows, forward-eliminates the fused right-hand
-//                          side and writes its rows of the four factor panels;
+//                          never talk), forms M' = -raw A11^{-1} and the in-panel updates for its row blocks with
+//                          DMMA.8x8x4 (one warp per 8-row block), forward-eliminates the fused right-hand side and
+//                          writes its rows of the four factor panels;
 //   bigband_update_kernel  many CTAs per system: rank-32 update of the trailing window with FP64 tensor-core MMAs
 //                          (DMMA.8x8x4), one warp per 8x8 tile, operands straight from L2/L1; four extra CTAs
 //                          refill the recycled window rows from the stencil (assembly stays fused, the matrix is
@@ -32,12 +33,13 @@ __host__ __device__ constexpr int big_T_for(int b) { return ((b + 7) / 8 + kBigN
 __host__ __device__ constexpr size_t big_work_entries(int T) {
     return (size_t)(TS * T) * (TS * T) + 2 * (size_t)kBigNBK * (TS * T) * 8 + 2 * (size_t)(TS * T);
 }
-// local rows of one panel CTA: 32 pivot rows + its share of the others, rounded up so that 2 threads per row fill whole warps
+// local rows of one panel CTA: the 4 pivot blocks + its share of the other window blocks (one warp per 8-row block)
 __host__ __device__ constexpr int big_panel_local_rows(int T) {
-    return (kBigNBK * TS + (TS * T - kBigNBK * TS + kBigSplit - 1) / kBigSplit + 15) / 16 * 16;
+    return TS * (kBigNBK + (T - kBigNBK + kBigSplit - 1) / kBigSplit);
 }
 __host__ __device__ constexpr size_t big_panel_smem_bytes(int T) {
-    return ((size_t)kBigNBK * big_panel_local_rows(T) * kBigPanStride + (size_t)big_panel_local_rows(T) + 64 + 8) * sizeof(cplx);
+    return ((size_t)kBigNBK * big_panel_local_rows(T) * kBigPanStride + (size_t)big_panel_local_rows(T) + 64 + 8 +
+            (size_t)big_panel_local_rows(T) * kBigPanStride) * sizeof(cplx);
 }
 
 struct BigView {
@@ -85,23 +87,25 @@ bigband_init_kernel(const BandSys* __restrict__ systems, BandDom dom, int T) {
 }
 
 // grid (kBigSplit, nsys).  The 32 pivot rows of the panel (its 32x32 diagonal block) are factored redundantly by every CTA
-// of a system — that is the serial part, four 8x8 inversions — and the remaining window rows are divided among the CTAs:
+// of a system — that is the serial part, four 8x8 inversions — and the remaining window row blocks are divided among the CTAs:
 // given the diagonal block's factors the row blocks are independent, so there is no communication between the CTAs.
-// Local rows: 0..31 = pivot rows (block c -> rows 8c..8c+7), then this CTA's share of the other window rows.
-// Threads: 2 per local row (column half h).  CTA 0 alone writes what belongs to the pivot rows.
+// Local row blocks: 0..3 = pivot blocks, then this CTA's share of the other window blocks.  One warp per local 8-row block:
+// M' = raw (-A11^{-1}) and the in-panel updates are 8x8x8 complex products on the FP64 tensor cores (DMMA.8x8x4, the
+// register kernel's formulation).  CTA 0 alone writes what belongs to the pivot rows.
 // The rhs window is double-buffered by panel parity (every CTA reads all pivot rows of it while CTA 0 rewrites them).
-// dynamic smem = big_panel_smem_bytes(T)
-__global__ void __launch_bounds__(2 * big_panel_local_rows(kBigMaxT))
+// block = 32 * big_panel_local_rows(T) / 8 threads, dynamic smem = big_panel_smem_bytes(T)
+__global__ void __launch_bounds__(4 * big_panel_local_rows(kBigMaxT))
 bigband_panel_kernel(const BandSys* __restrict__ systems, BandDom dom, int T, int k) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int R = TS * T;
     constexpr int ND = kBigNBK * TS;                                      // pivot rows
-    const int chunk = (R - ND + kBigSplit - 1) / kBigSplit;              // other rows per CTA
-    const int NL = big_panel_local_rows(T);                               // local rows (>= ND + chunk; the surplus is idle)
+    const int chunkBlocks = (T - kBigNBK + kBigSplit - 1) / kBigSplit;   // other row blocks per CTA
+    const int NL = big_panel_local_rows(T);                               // local rows = ND + 8 * chunkBlocks
     cplx* const pan = reinterpret_cast<cplx*>(smem_raw);                  // [NBK][NL][kBigPanStride]
     cplx* const ysh = pan + (size_t)kBigNBK * NL * kBigPanStride;         // [NL]
     cplx* const ainv = ysh + NL;                                          // [64] row-major A11^{-1}
     cplx* const zsh = ainv + 64;                                          // [8]
+    cplx* const mwAll = zsh + 8;                                          // [NL/8][8][kBigPanStride]: M' of each warp's row block
 
     const BandSys sys = systems[blockIdx.y];
     const LocalDom L = LocalDom::make(dom, 0);
@@ -109,34 +113,42 @@ bigband_panel_kernel(const BandSys* __restrict__ systems, BandDom dom, int T, in
     BigView v(sys.big, R);
     const cplx* const yin = v.ywin + (size_t)(k & 1) * R;
     cplx* const yout = v.ywin + (size_t)((k + 1) & 1) * R;
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-    const int lr = tid >> 1, h = tid & 1;                                 // local row, column half
     const int s0 = k * kBigNBK, q0 = s0 % T;                              // the pivot slots are q0 .. q0+3 (T % 4 == 0: no wrap)
     const int nsub = min(kBigNBK, L.sTot - s0);
     const bool first = blockIdx.x == 0;
-    // window row of this local row (-1: none): pivot rows first, then the chunk of the remaining rows in window order
-    int r = -1;
-    if (lr < ND) r = q0 * TS + lr;
-    else {
-        const int o = (int)blockIdx.x * chunk + (lr - ND);               // index among the R - ND non-pivot rows
-        if (lr - ND < chunk && o < R - ND) r = o < q0 * TS ? o : o + ND;
-    }
-    const bool owner = r >= 0 && (lr >= ND || first);                     // writes this row's results
-    const int beta = r >= 0 ? big_block_of_slot(r >> 3, s0, T) : -1;
+    // window slot of a local row block (-1: none): pivot blocks first, then this CTA's share of the others in window order
+    auto slot_of = [&](int lb) {
+        if (lb < kBigNBK) return q0 + lb;
+        const int ob = (int)blockIdx.x * chunkBlocks + (lb - kBigNBK);   // index among the T - NBK non-pivot blocks
+        if (lb - kBigNBK >= chunkBlocks || ob >= T - kBigNBK) return -1;
+        return ob < q0 ? ob : ob + kBigNBK;
+    };
     auto P = [&](int c, int row, int col) -> cplx& { return pan[((size_t)c * NL + row) * kBigPanStride + col]; };
 
-    for (int c = 0; c < kBigNBK; ++c) {
-        const bool live = r >= 0 && c < nsub && beta >= s0 + c;
+    for (int idx = tid; idx < 2 * NL; idx += blockDim.x) {
+        const int lr = idx >> 1, h = idx & 1, slot = slot_of(lr >> 3);
+        const int r = slot < 0 ? -1 : slot * TS + (lr & 7);
+        const int beta = slot < 0 ? -1 : big_block_of_slot(slot, s0, T);
+        for (int c = 0; c < kBigNBK; ++c) {
+            const bool live = r >= 0 && c < nsub && beta >= s0 + c;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) P(c, lr, 4 * h + j) = live ? v.win[(size_t)r * R + (q0 + c) * TS + 4 * h + j] : mk(0.0, 0.0);
+            for (int j = 0; j < 4; ++j) P(c, lr, 4 * h + j) = live ? v.win[(size_t)r * R + (q0 + c) * TS + 4 * h + j] : mk(0.0, 0.0);
+        }
+        if (h == 0) ysh[lr] = r >= 0 ? yin[r] : mk(0.0, 0.0);
     }
-    if (h == 0) ysh[lr] = r >= 0 ? yin[r] : mk(0.0, 0.0);
     __syncthreads();
 
+    // this warp's row block (warp-uniform)
+    const int lr0 = warp * TS, slot = slot_of(warp);
+    const int beta = slot < 0 ? -1 : big_block_of_slot(slot, s0, T);
+    const bool owner = slot >= 0 && (warp >= kBigNBK || first);           // writes this row block's results
+    const int rg = slot * TS + g;                                         // window row of lane group g
+    cplx* const mw = mwAll + (size_t)warp * TS * kBigPanStride;
     for (int c = 0; c < nsub; ++c) {
         if (warp == 0) {
-            const int i = lane >> 2, t = lane & 3;
+            const int i = g;
             cplx a0 = P(c, c * TS + i, 2 * t), a1 = P(c, c * TS + i, 2 * t + 1);
             bool bad = false;
             gj_invert8(a0, a1, bad, i, t);
@@ -160,74 +172,82 @@ bigband_panel_kernel(const BandSys* __restrict__ systems, BandDom dom, int T, in
             }
         }
         __syncthreads();
-        // M'[r][4h..4h+3] = -sum_k raw[r][k] A11^{-1}[k][4h+j]   (all rows: the partner exchange below must be warp-converged).
-        // raw is streamed from shared memory, never held as an array (register budget).
-        const bool below = beta > s0 + c;
-        cplx m[4] = {mk(0.0, 0.0), mk(0.0, 0.0), mk(0.0, 0.0), mk(0.0, 0.0)};
-        cplx yacc = mk(0.0, 0.0);
+        const bool below = beta > s0 + c, keep = beta >= s0 + c;
+        // M'[X] = raw_c[X] (-A11^{-1}): lane (g,t) ends up with entries (g, 2t) and (g, 2t+1)
+        cplx m0 = mk(0.0, 0.0), m1 = mk(0.0, 0.0);
+        if (below) {
+            double mre[2] = {0.0, 0.0}, mim[2] = {0.0, 0.0}, t1[2] = {0.0, 0.0}, t2[2] = {0.0, 0.0};
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-            const cplx rv = P(c, lr, kk);
+            for (int kk = 0; kk < 2; ++kk) {
+                const cplx a = P(c, lr0 + g, 4 * kk + t);
+                const cplx bq = ainv[(4 * kk + t) * 8 + g];
+                dmma884(mre, a.x, -bq.x);
+                dmma884(mim, a.x, -bq.y);
+                dmma884(t1, -a.y, -bq.y);
+                dmma884(t2, a.y, -bq.x);
+            }
+            m0 = mk(mre[0] + t1[0], mim[0] + t2[0]);
+            m1 = mk(mre[1] + t1[1], mim[1] + t2[1]);
+            // fused forward elimination of the rhs: y_X -= raw_c[X] z
+            if (t == 0 && sys.rhs) {
+                cplx acc = ysh[lr0 + g];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) cfma(m[j], -rv, ainv[kk * 8 + 4 * h + j]);
-            cfma(yacc, -rv, zsh[kk]);
+                for (int kk = 0; kk < 8; ++kk) cfma(acc, -P(c, lr0 + g, kk), zsh[kk]);
+                ysh[lr0 + g] = acc;
+            }
         }
-        if (below && h == 0 && sys.rhs) ysh[lr] = ysh[lr] + yacc;
+        mw[g * kBigPanStride + 2 * t] = m0;
+        mw[g * kBigPanStride + 2 * t + 1] = m1;
         // operands of the trailing update (plain [c][r][8] layout, L2-resident)
         if (owner) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) v.mscr[((size_t)c * R + r) * 8 + 4 * h + j] = below ? m[j] : mk(0.0, 0.0);
+            v.mscr[((size_t)c * R + rg) * 8 + 2 * t] = m0;
+            v.mscr[((size_t)c * R + rg) * 8 + 2 * t + 1] = m1;
         }
-        {
-            cplx mf[8];
+        __syncwarp();
+        if (below) {
+            double are[2], aim[2];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {      // static indices only: the array must stay in registers
-                const cplx o = mk(__shfl_xor_sync(0xffffffffu, m[j].x, 1), __shfl_xor_sync(0xffffffffu, m[j].y, 1));
-                mf[j] = h ? o : m[j];
-                mf[4 + j] = h ? m[j] : o;
+            for (int kk = 0; kk < 2; ++kk) {
+                const cplx a = mw[g * kBigPanStride + 4 * kk + t];
+                are[kk] = a.x; aim[kk] = a.y;
             }
+            for (int c2 = c + 1; c2 < nsub; ++c2) {
+                if (beta < s0 + c2) continue;                            // (warp-uniform)
+                const cplx c0 = P(c2, lr0 + g, 2 * t), c1 = P(c2, lr0 + g, 2 * t + 1);
+                double cre[2] = {c0.x, c1.x}, cim[2] = {c0.y, c1.y}, t1[2] = {0.0, 0.0}, t2[2] = {0.0, 0.0};
 #pragma unroll
-            for (int c2 = 1; c2 < kBigNBK; ++c2) {
-                if (c2 <= c || c2 >= nsub || !below || beta < s0 + c2) continue;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    cplx acc = P(c2, lr, 4 * h + j);
-#pragma unroll
-                    for (int kk = 0; kk < 8; ++kk) cfma(acc, mf[kk], P(c, c2 * TS + 4 * h + j, kk));
-                    P(c2, lr, 4 * h + j) = acc;
+                for (int kk = 0; kk < 2; ++kk) {
+                    const cplx bq = P(c, c2 * TS + g, 4 * kk + t);     // raw_c restricted to the rows of pivot block c2
+                    dmma884(cre, are[kk], bq.x);
+                    dmma884(cim, are[kk], bq.y);
+                    dmma884(t1, -aim[kk], bq.y);
+                    dmma884(t2, aim[kk], bq.x);
                 }
+                P(c2, lr0 + g, 2 * t) = mk(cre[0] + t1[0], cim[0] + t2[0]);
+                P(c2, lr0 + g, 2 * t + 1) = mk(cre[1] + t1[1], cim[1] + t2[1]);
             }
         }
-        cplx rawh[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) rawh[j] = P(c, lr, 4 * h + j);
         if (owner) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) v.rscr[((size_t)c * R + r) * 8 + 4 * h + j] = below ? rawh[j] : mk(0.0, 0.0);
+            const cplx e0 = P(c, lr0 + g, 2 * t), e1 = P(c, lr0 + g, 2 * t + 1);
+            v.rscr[((size_t)c * R + rg) * 8 + 2 * t] = below ? e0 : mk(0.0, 0.0);
+            v.rscr[((size_t)c * R + rg) * 8 + 2 * t + 1] = below ? e1 : mk(0.0, 0.0);
             // factor panel of macro-step s0+c in the solve kernels' image layout [re/im][kk][R][4]; rows of blocks already
             // eliminated in this launch are outside the band of this panel: zero
             double* img = sys.panels[0] + (size_t)(s0 + c) * panel_doubles(T);
-            const bool keep = beta >= s0 + c;
-            double2 re01 = make_double2(0.0, 0.0), re23 = re01, im01 = re01, im23 = re01;
-            if (keep) {
-                re01 = make_double2(rawh[0].x, rawh[1].x); re23 = make_double2(rawh[2].x, rawh[3].x);
-                im01 = make_double2(rawh[0].y, rawh[1].y); im23 = make_double2(rawh[2].y, rawh[3].y);
-            }
-            double2* pre = reinterpret_cast<double2*>(img + ((size_t)(0 * 2 + h) * R + r) * 4);
-            double2* pim = reinterpret_cast<double2*>(img + ((size_t)(1 * 2 + h) * R + r) * 4);
-            pre[0] = re01; pre[1] = re23;
-            pim[0] = im01; pim[1] = im23;
+            const int kkI = t >> 1, tt = 2 * (t & 1);
+            *reinterpret_cast<double2*>(img + ((size_t)(0 * 2 + kkI) * R + rg) * 4 + tt) = keep ? make_double2(e0.x, e1.x) : make_double2(0.0, 0.0);
+            *reinterpret_cast<double2*>(img + ((size_t)(1 * 2 + kkI) * R + rg) * 4 + tt) = keep ? make_double2(e0.y, e1.y) : make_double2(0.0, 0.0);
         }
         __syncthreads();
     }
     // rhs window of the next panel: the slots of the eliminated blocks now hold blocks +T
-    if (h == 0 && owner) {
-        cplx yv = ysh[lr];
+    if (owner && t == 0) {
+        cplx yv = ysh[lr0 + g];
         if (beta < s0 + nsub) {
-            const int gr = (beta + T) * TS + (r & 7);
+            const int gr = (beta + T) * TS + g;
             yv = (sys.rhs && gr < L.nLoc) ? prov.rhs_at(sys.rhs, gr) : mk(0.0, 0.0);
         }
-        yout[r] = yv;
+        yout[rg] = yv;
     }
 }
 

@@ -170,7 +170,7 @@ int launch_factor_big(cudaStream_t st, int T, const BandSys* sys, int nsys, cons
     const size_t smem = big_panel_smem_bytes(T);
     bigband_init_kernel<<<dim3(T, nsys), 256, 0, st>>>(sys, dom, T);
     for (int k = 0; k < nPanels; ++k) {
-        bigband_panel_kernel<<<dim3(kBigSplit, nsys), 2 * big_panel_local_rows(T), smem, st>>>(sys, dom, T, k);
+        bigband_panel_kernel<<<dim3(kBigSplit, nsys), 4 * big_panel_local_rows(T), smem, st>>>(sys, dom, T, k);
         if (k + 1 < nPanels) bigband_update_kernel<<<dim3(nBlocks + kBigNBK, nsys), 256, 0, st>>>(sys, dom, T, k, nYq, nBlocks);
     }
     HMCMT_CUDA_TRY(cudaGetLastError());
