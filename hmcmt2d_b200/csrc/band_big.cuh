@@ -151,7 +151,7 @@ bigband_panel_kernel(const BandSys* __restrict__ systems, BandDom dom, int T, in
             const int i = g;
             cplx a0 = P(c, c * TS + i, 2 * t), a1 = P(c, c * TS + i, 2 * t + 1);
             bool bad = false;
-            gj_invert8(a0, a1, bad, i, t);
+            gj_invert8<true>(a0, a1, bad, i, t);
             bad = __any_sync(0xffffffffu, bad);
             if (bad && lane == 0 && first && sys.status) *sys.status = kErrSingular;
             ainv[i * 8 + 2 * t] = a0;

@@ -31,7 +31,7 @@ __global__ void k_lat(double* out, long long* cyc, int iters) {
     cplx a0 = mk((i == 2 * t) ? 4.0 : 0.1 * (i + 2 * t), 0.3), a1 = mk((i == 2 * t + 1) ? 4.0 : 0.1 * (i + 2 * t + 1), 0.2);
     bool bad = false;
     t0 = clock64();
-    for (int r = 0; r < 16; ++r) { gj_invert8(a0, a1, bad, i, t); a0.x += 1.0; }
+    for (int r = 0; r < 16; ++r) { gj_invert8<true>(a0, a1, bad, i, t); a0.x += 1.0; }
     t1 = clock64();
     cyc[4] = (t1 - t0) / 16;
     out[threadIdx.x] = c[0] + c[1] + a0.x + a1.y + (bad ? 1 : 0);
