@@ -1,10 +1,11 @@
-// Forward + backward substitution with the block-LDL^T factor written by band_factor_kernel.
+// Forward + backward substitution with the block-LDL^T factor written by band_factor_kernel / band_big.cuh.
 // Replaces `applyMUMPS(Ainv, rhs)` / `Ainv \ rhs` for the adjoint solve (compJacTMatVec.jl:220-224,
-// 291-295) and `solve_mumps_cmplx_` (MUMPSfuncs.jl:123-132).  HBM-bound: streams the 16*8T*8-byte
-// panel images with TMA bulk loads (solve_stages(T) panels in flight on mbarriers) — 2 reads of the
-// factor per right-hand side.  Split systems use the same launch sequence as the factorisation
-// (FM_OWN: forward sweep of both halves, FM_SEP: separator forward + backward, FM_BACK: backward
-// sweep of both halves), hand-over through global scratch in stream order.
+// 291-295), the back-substitution half of the forward solve (mt2DTE.jl:53, mt2DTM.jl:52) and `solve_mumps_cmplx_`
+// (MUMPSfuncs.jl:123-132).  HBM-bound: streams the 16*8T*8-byte panel images with TMA bulk loads (solve_stages(T) panels in
+// flight on mbarriers), one read of the factor per sweep.  Each sweep is a software pipeline of three warp roles (near /
+// far / service, see below) so that the dependency between consecutive 8-column steps runs inside one warp.
+// Split systems use the same launch sequence as the factorisation (FM_OWN: forward sweep of both halves, FM_SEP: separator
+// forward + backward, FM_BACK: backward sweep of both halves), hand-over through global scratch in stream order.
 #pragma once
 #include "band_factor.cuh"
 
