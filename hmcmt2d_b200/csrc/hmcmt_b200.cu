@@ -85,15 +85,27 @@ namespace {
         }                                                         \
     } while (0)
 
+// cudaFuncSetAttribute is per device: a process may hold plans on several GPUs (api.parallelHMCSampler without torchrun),
+// so the "already configured" flags are kept per device.
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool need() {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+        if (done[dev]) return false;
+        done[dev] = true;
+        return true;
+    }
+};
+
 // A split system takes three launches in stream order: own lines of both halves, separator, back-substitution of both halves.
 template <int T>
 int launch_factor_T(cudaStream_t st, const BandSys* sys, int nsys, const BandDom& dom, const SolveJob* fwdJobs) {
-    static bool configured = false;
+    static PerDeviceOnce once;
     size_t smem = sizeof(FactorSmem<T>), smemSolve = sizeof(SolveSmem<T>);
-    if (!configured) {
+    if (once.need()) {
         HMCMT_CUDA_TRY(cudaFuncSetAttribute(band_factor_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         HMCMT_CUDA_TRY(cudaFuncSetAttribute(band_solve_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemSolve));
-        configured = true;
     }
     constexpr int NT = FactorCfg<T>::NTHREADS;
     if (!dom.split) {
@@ -110,11 +122,10 @@ int launch_factor_T(cudaStream_t st, const BandSys* sys, int nsys, const BandDom
 }
 template <int T>
 int launch_solve_T(cudaStream_t st, const SolveJob* jobs, int njobs, const BandDom& dom) {
-    static bool configured = false;
+    static PerDeviceOnce once;
     size_t smem = sizeof(SolveSmem<T>);
-    if (!configured) {
+    if (once.need()) {
         HMCMT_CUDA_TRY(cudaFuncSetAttribute(band_solve_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
     }
     if (!dom.split) {
         band_solve_kernel<T><<<njobs, kSolveThreads, smem, st>>>(jobs, dom, FM_FULL);
@@ -132,11 +143,10 @@ int launch_solve_T(cudaStream_t st, const SolveJob* jobs, int njobs, const BandD
 namespace {
 template <int T>
 int launch_solve_mode_T(cudaStream_t st, const SolveJob* jobs, int njobs, const BandDom& dom, int mode) {
-    static bool configured = false;
+    static PerDeviceOnce once;
     size_t smem = sizeof(SolveSmem<T>);
-    if (!configured) {
+    if (once.need()) {
         HMCMT_CUDA_TRY(cudaFuncSetAttribute(band_solve_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
     }
     band_solve_kernel<T><<<njobs, kSolveThreads, smem, st>>>(jobs, dom, mode);
     HMCMT_CUDA_TRY(cudaGetLastError());
@@ -159,11 +169,10 @@ int launch_solve_big(cudaStream_t st, int T, const SolveJob* jobs, int njobs, co
 // Large-bandwidth factorisation: init, then one panel launch + one trailing-update launch per 32 columns, then the
 // backward sweep of the fused forward system (fwdJobs, optional).
 int launch_factor_big(cudaStream_t st, int T, const BandSys* sys, int nsys, const BandDom& dom, const SolveJob* fwdJobs, int* nLaunches) {
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    if (once.need()) {
         HMCMT_CUDA_TRY(cudaFuncSetAttribute(bigband_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)big_panel_smem_bytes(kBigMaxT)));
-        configured = true;
     }
     const int R = TS * T, sTot = (dom.N + TS - 1) / TS, nPanels = (sTot + kBigNBK - 1) / kBigNBK;
     const int npos = T - kBigNBK, nYq = (npos + 3) / 4, nBlocks = ((npos + 1) / 2) * nYq;

@@ -34,8 +34,9 @@ extern "C" {
 /* factorMUMPS(A::SparseMatrixCSC{ComplexF64},sym,ooc)  MUMPSfuncs.jl:24-39 (ccall :32-35).
  * sym: 0 unsymmetric, 1 "SPD", 2 general symmetric (:25-26).  Only symmetric matrices are
  * supported (the hot path passes sym=1 for a complex-symmetric matrix, mt2DTE.jl:51); the
- * matrix is factorised as pivot-free block LDL^T without conjugation.  Returns an opaque handle;
- * *status < 0 on error. */
+ * matrix is factorised as pivot-free block LDL^T without conjugation (banded: half-bandwidth <= 104
+ * in registers, 105..320 through a global-memory window; wider matrices return -3).  Returns an
+ * opaque handle; *status < 0 on error. */
 int64_t factor_mumps_cmplx_(const int64_t* n, const int64_t* sym, const int64_t* ooc, const double* nzval,
                             const int64_t* rowval, const int64_t* colptr, int64_t* status);
 /* factorMUMPS(A::SparseMatrixCSC{Float64},...)  MUMPSfuncs.jl:41-56 (ccall :49-52) */

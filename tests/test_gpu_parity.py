@@ -211,3 +211,20 @@ def test_cfg5_finite_difference_check():
         worst = max(worst, abs(fd - g[a]) / np.abs(g).max())
     assert worst < 1e-4, worst
     pl.close()
+
+
+def test_tiny_problem_against_committed_fixture():
+    """The same seeded problem against the committed oracle vector (tests/golden/tiny_oracle.npz)."""
+    import os
+    from hmcmt2d_b200 import api
+    from tests.helpers import GOLDEN
+    ref = np.load(os.path.join(GOLDEN, "tiny_oracle.npz"))
+    mesh, data, inv, prior = tiny_problem(seed=3)
+    pm, pd, pi, pp = to_product(mesh, data, inv, prior)
+    pi.strModel = ref["m"].copy()
+    pred, phi, g = api.compDataGradient(pm, pd, pi, pp)
+    assert (np.abs(pred - ref["pred"]) / np.abs(ref["pred"])).max() < TOL
+    assert abs(phi - ref["phi"]) / abs(ref["phi"]) < TOL
+    assert np.abs(g - ref["g"]).max() / np.abs(ref["g"]).max() < TOL
+    m2, p2 = api.proposeLeapfrog(api.HMCParameter(len(ref["m"]), ref["m"].copy(), ref["p0"].copy()), pm, pd, pi, pp, intstep=2)
+    assert np.abs(m2 - ref["m2"]).max() < TOL and np.abs(p2 - ref["p2"]).max() < TOL * max(1.0, np.abs(ref["p2"]).max())

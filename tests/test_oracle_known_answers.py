@@ -123,3 +123,19 @@ def test_rx_adjoint_closed_form_matches_sparse_L_Q():
         assert np.abs(s0 - s_ref[zid * (ny + 1):(zid + 1) * (ny + 1)]).max() / np.abs(s_ref).max() < 1e-12
         assert np.abs(s1 - s_ref[(zid + 1) * (ny + 1):(zid + 2) * (ny + 1)]).max() / np.abs(s_ref).max() < 1e-12
         assert np.abs(q - q_ref[zid * ny:(zid + 1) * ny]).max() / max(np.abs(q_ref).max(), 1e-300) < 1e-12
+
+
+def test_oracle_reproduces_committed_fixture():
+    """tests/golden/tiny_oracle.npz (tests/golden/make_oracle_fixture.py): the oracle must not drift."""
+    import importlib.util
+    import os
+    from tests.helpers import GOLDEN
+    spec = importlib.util.spec_from_file_location("make_oracle_fixture", os.path.join(GOLDEN, "make_oracle_fixture.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    now = mod.compute()
+    ref = np.load(os.path.join(GOLDEN, "tiny_oracle.npz"))
+    for key in ("pred", "g", "m2", "p2"):
+        scale = np.abs(ref[key]).max()
+        assert np.abs(now[key] - ref[key]).max() <= 1e-12 * scale, key
+    assert abs(now["phi"] - ref["phi"]) <= 1e-12 * abs(ref["phi"])
