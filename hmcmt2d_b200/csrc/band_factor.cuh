@@ -24,12 +24,14 @@
 // lines before it, CTA 1 the lines after it in reverse order, both towards the separator (launch
 // FM_OWN, 2 CTAs per system).  Each exports its window — its share of the separator's Schur
 // complement — to global scratch; a second launch (FM_SEP, 1 CTA per system) sums the two images,
-// eliminates the separator and back-substitutes it; a third launch (FM_BACK, 2 CTAs per system)
-// back-substitutes the two halves.  Stream order is the only synchronisation between the CTAs of a
-// system.  This halves the sequential pivot chain and doubles the SMs a single chain can use.
+// eliminates the separator and back-substitutes it; a third launch (2 CTAs per system) back-substitutes
+// the two halves — the pipelined sweep of band_solve.cuh in SM_BACKZ_OWN mode when the caller provides
+// solve jobs, else this kernel in FM_BACK mode.  Stream order is the only synchronisation between the
+// CTAs of a system.  This halves the sequential pivot chain and doubles the SMs a single chain can use.
 //
 // The stored factor is { raw_s (8T x 8), [A11_s^{-1} (8x8) | z_s (8)] } per macro-step and rank; it
-// serves the forward solve (back-substitution fused below) and the adjoint solve (band_solve.cuh).
+// serves the forward solve (back-substitution fused below for unsplit systems and the separator) and
+// the adjoint solve (band_solve.cuh).
 #pragma once
 #include <type_traits>
 #ifndef HMCMT_GATE_ALL
