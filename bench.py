@@ -178,8 +178,8 @@ def run_reference(args, rank):
     cores = os.cpu_count() or 1
     nsample = min(WORKLOAD["nfreq"], cores)
     vals = []
-    for _ in range(max(1, args.warmup) - 1 + 0):
-        pass
+    # every "step" of this arm is one bounded sample (nsample frequencies farmed over all host cores, extrapolated to the
+    # full step); at most three samples, whatever --steps says, so that the arm ends within a minute or two
     for _ in range(max(1, min(args.steps, 3))):
         v, wall = cpu_steps_per_sec(cores, nsample)
         vals.append(v)
