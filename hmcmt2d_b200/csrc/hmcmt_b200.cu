@@ -650,6 +650,17 @@ int hmcmt_plan_create(const hmcmt_problem* pr, hmcmt_plan** out) {
     {
         // wide meshes: the receiver / contraction kernels stage whole node rows in shared memory
         const size_t rxSmem = (size_t)(6 * (M.ny + 1) + 3 * M.ny) * sizeof(cplx);
+        // very deep meshes: one profile of the boundary kernel no longer fits the default 48 KB of dynamic shared memory
+        const size_t bcSmem = (size_t)boundary_profiles_per_block(M.nz) * M.nz * 6 * sizeof(cplx);
+        if (bcSmem > 227 * 1024) {
+            fprintf(stderr, "[hmcmt_b200] nz = %d: the boundary kernel needs %zu bytes of shared memory per profile\n", M.nz, bcSmem);
+            hmcmt_destroy(pl);
+            return kErrArg;
+        }
+        if (bcSmem > 48 * 1024 && cudaFuncSetAttribute(k_boundary, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bcSmem) != cudaSuccess) {
+            hmcmt_destroy(pl);
+            return kErrCuda;
+        }
         pl->conStaged = contract_cols_smem(M.ny, M.nz, 1) <= 200 * 1024 ? 1 : 0;
         const size_t cSmem = contract_cols_smem(M.ny, M.nz, pl->conStaged);
         if ((rxSmem > 48 * 1024 && cudaFuncSetAttribute(k_rx_adjoint, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rxSmem) != cudaSuccess) ||
