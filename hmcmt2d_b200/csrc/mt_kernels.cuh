@@ -153,60 +153,77 @@ k_boundary(MeshDev M, SysMap sm, const double* __restrict__ freqs, const double*
     }
     __syncthreads();
     const int p = p0 + threadIdx.x;
-    if ((int)threadIdx.x >= PB || p > ny) return;               // ny+1 profiles (2 + ny-1) and ny+1 top-row entries
-    const cplx *K = A(threadIdx.x, 0), *TH = A(threadIdx.x, 1), *EP = A(threadIdx.x, 2), *EM = A(threadIdx.x, 3),
-               *ZP = A(threadIdx.x, 4), *KR = A(threadIdx.x, 5);
+    const bool active = (int)threadIdx.x < PB && p <= ny;        // ny+1 profiles (2 + ny-1) and ny+1 top-row entries
+    const int nM = sm.nModes;
     cplx* out[2];
     int modes[2];
-    const int nM = sm.nModes;
     for (int mi = 0; mi < nM; ++mi) {
         out[mi] = bc + (size_t)((ch * sm.nModes + mi) * sm.nFreq + f) * M.nb;
         modes[mi] = mi == 0 ? sm.mode0 : sm.mode1;
-        out[mi][p] = mk(1.0, 0.0);              // top row
     }
-    // bottom-up impedance recursion
-    cplx zt = ZP[nz - 1];
-    for (int j = nz - 1; j >= 0; --j) {
-        const cplx zp = ZP[j], th = TH[j];
-        zt = zp * (zt + zp * th) / (zp + zt * th);
-    }
-    const cplx k = K[0];
-    cplx r0 = omu / (zt * k);
-    cplx eu = 0.5 * (mk(1.0, 0.0) - r0), ed = 0.5 * (mk(1.0, 0.0) + r0);
-    auto field = [&](int mode, cplx kk) { return (mode == 0) ? eu + ed : (ed * kk - eu * kk) / omu; };   // E or H
-    cplx top[2], last[2];
-    for (int mi = 0; mi < nM; ++mi) { top[mi] = field(modes[mi], k); last[mi] = top[mi]; }
-    const int colOff = (p == 0) ? ny + 1 : (p == 1) ? ny + 1 + nz : -1;
-    bool dead = false;
-    double e1 = cabs_(eu + ed);                    // |E| of the previous row: the guard compares consecutive rows
-    for (int i = 0; i < nz; ++i) {
-        bool live = false;
-        if (!dead) {
-            const cplx kr = KR[i], ep = EP[i], em = EM[i];
-            cplx one = mk(1.0, 0.0);
-            cplx a = 0.5 * (one + kr), bq = 0.5 * (one - kr);
-            cplx nu = (a * ep) * eu + (bq * em) * ed;
-            cplx nd = (bq * ep) * eu + (a * em) * ed;
-            double e2 = cabs_(nu + nd);
-            if (e2 - e1 > 0.0 || isnan(e2)) {
-                dead = true;                       // mt1DField.jl:77-81: zero all deeper entries
-            } else {
-                eu = nu; ed = nd; e1 = e2;
-                live = true;
-            }
+    auto field_of = [&](int mode, cplx eu, cplx ed, cplx kk) { return (mode == 0) ? eu + ed : (ed * kk - eu * kk) / omu; };   // E or H
+    if (active) {
+        const cplx *K = A(threadIdx.x, 0), *TH = A(threadIdx.x, 1), *EP = A(threadIdx.x, 2), *EM = A(threadIdx.x, 3),
+                   *ZP = A(threadIdx.x, 4), *KR = A(threadIdx.x, 5);
+        for (int mi = 0; mi < nM; ++mi) out[mi][p] = mk(1.0, 0.0);      // top row
+        // bottom-up impedance recursion
+        cplx zt = ZP[nz - 1];
+        for (int j = nz - 1; j >= 0; --j) {
+            const cplx zp = ZP[j], th = TH[j];
+            zt = zp * (zt + zp * th) / (zp + zt * th);
         }
-        // the two edge columns need every row, a bottom profile only its last one
-        if (colOff >= 0 || i == nz - 1) {
-            const cplx ki = K[(i + 1 < nz) ? i + 1 : nz - 1];
+        const cplx k = K[0];
+        cplx r0 = omu / (zt * k);
+        cplx eu = 0.5 * (mk(1.0, 0.0) - r0), ed = 0.5 * (mk(1.0, 0.0) + r0);
+        const cplx eu0 = eu, ed0 = ed;
+        // the two edge columns (p = 0, 1) need every row: their amplitudes are parked in shared memory (the tanh / impedance
+        // arrays are dead by now) and turned into normalised fields by the whole block below; a bottom profile only needs its
+        // last row
+        const bool edge = p < 2;
+        cplx* EU = A(threadIdx.x, 1);
+        cplx* ED = A(threadIdx.x, 4);
+        bool dead = false, live = false;
+        double e1 = cabs_(eu + ed);                    // |E| of the previous row: the guard compares consecutive rows
+        for (int i = 0; i < nz; ++i) {
+            live = false;
+            if (!dead) {
+                const cplx kr = KR[i], ep = EP[i], em = EM[i];
+                cplx one = mk(1.0, 0.0);
+                cplx a = 0.5 * (one + kr), bq = 0.5 * (one - kr);
+                cplx nu = (a * ep) * eu + (bq * em) * ed;
+                cplx nd = (bq * ep) * eu + (a * em) * ed;
+                double e2 = cabs_(nu + nd);
+                if (e2 - e1 > 0.0 || isnan(e2)) {
+                    dead = true;                       // mt1DField.jl:77-81: zero all deeper entries
+                } else {
+                    eu = nu; ed = nd; e1 = e2;
+                    live = true;
+                }
+            }
+            if (edge) { EU[i] = live ? eu : mk(0.0, 0.0); ED[i] = live ? ed : mk(0.0, 0.0); }
+        }
+        if (edge) {
+            A(threadIdx.x, 5)[0] = eu0;                // (the ratio array is dead as well)
+            A(threadIdx.x, 5)[1] = ed0;
+        } else {
+            const cplx ki = K[nz - 1];
             for (int mi = 0; mi < nM; ++mi) {
-                const cplx val = live ? field(modes[mi], ki) : mk(0.0, 0.0);
-                last[mi] = val;
-                if (colOff >= 0) out[mi][colOff + i] = val / top[mi];
+                const cplx last = live ? field_of(modes[mi], eu, ed, ki) : mk(0.0, 0.0);
+                out[mi][ny + 1 + 2 * nz + (p - 2)] = last / field_of(modes[mi], eu0, ed0, k);
             }
         }
     }
-    if (p >= 2)
-        for (int mi = 0; mi < nM; ++mi) out[mi][ny + 1 + 2 * nz + (p - 2)] = last[mi] / top[mi];
+    if (p0 >= 2) return;                               // only the first block(s) of a (chain, frequency) hold the edge columns p = 0, 1
+    __syncthreads();
+    for (int item = threadIdx.x; item < 2 * nM * nz; item += kBcThreads) {
+        const int pl = item / (nM * nz), rem = item - pl * nM * nz, mi = rem / nz, i = rem - mi * nz;
+        const int pg = p0 + pl;                        // global profile of local profile pl
+        if (pl >= PB || pg >= 2) continue;
+        const cplx* K = A(pl, 0);
+        const cplx top = field_of(modes[mi], A(pl, 5)[0], A(pl, 5)[1], K[0]);
+        const cplx val = field_of(modes[mi], A(pl, 1)[i], A(pl, 4)[i], K[(i + 1 < nz) ? i + 1 : nz - 1]);
+        out[mi][ny + 1 + pg * nz + i] = val / top;
+    }
 }
 
 // rhs = -Aio*bc in internal ordering (mt2DTE.jl:44).  grid: (ceil(N/256), nSys)
