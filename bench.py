@@ -74,7 +74,9 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.proc.stdout.readline()          # blocks until nvidia-smi is up and has printed its first sample
+            import select
+            if select.select([self.proc.stdout], [], [], 5.0)[0]:      # wait (bounded) until nvidia-smi is up:
+                self.proc.stdout.readline()                             # its first sample
         except Exception:
             self.proc = None
 
