@@ -61,7 +61,6 @@ struct BandSys {
     double* panels[2];   // per half (rank): [steps][16*R] doubles: re/im x kk x R x 4 (exactly the smem operand layout)
     cplx* ainvz[2];      // per half (rank): [steps][72]: A11^{-1} row-major, then z = A11^{-1} * (forward-eliminated rhs block)
     cplx* wexp;          // split only: hand-over scratch [2][R*R] window images, [2][R] rhs windows, [R] separator solution
-    cplx* big;           // large-bandwidth path only (band_big.cuh): per-system workspace of big_work_entries(T) entries
     int* status;         // 0 ok, -10 zero/NaN pivot block
 };
 
@@ -221,7 +220,7 @@ struct EntryProvider {
 // with an exact power-of-two rescale, so no reciprocal sits on the 8-pivot dependency chain; every row carries
 // its accumulated scale q_i and the true inverse is  a_ij / q_i, formed with one reciprocal per row at the end.
 // UNROLL: the fully unrolled form has the shorter dependency chain (2 000 vs ~3 000 cycles alone) and suits kernels whose other
-// warps wait for it (band_big.cuh); inside band_factor_kernel, where ~800 more instructions per macro-step compete for the
+// warps wait for it (mf_kernels.cuh); inside band_factor_kernel, where ~800 more instructions per macro-step compete for the
 // instruction cache with the tile warps' code, the rolled loop measured 5 % faster end to end.
 template <bool UNROLL>
 __device__ __forceinline__ void gj_invert8(cplx& a0, cplx& a1, bool& bad, const int i, const int t) {

@@ -1,4 +1,4 @@
-// Forward + backward substitution with the block-LDL^T factor written by band_factor_kernel / band_big.cuh.
+// Forward + backward substitution with the block-LDL^T factor written by band_factor_kernel.
 // Replaces `applyMUMPS(Ainv, rhs)` / `Ainv \ rhs` for the adjoint solve (compJacTMatVec.jl:220-224,
 // 291-295), the back-substitution half of the forward solve (mt2DTE.jl:53, mt2DTM.jl:52) and `solve_mumps_cmplx_`
 // (MUMPSfuncs.jl:123-132).  HBM-bound: streams the 16*8T*8-byte panel images with TMA bulk loads (solve_stages(T) panels in
@@ -26,7 +26,7 @@ constexpr int kSolveThreads = 256;
 constexpr int kSolveRing = 8, kRhsAhead = 5;   // rhs ring of the forward sweep: depth and prefetch distance (steps)
 enum { SB_X0 = 1, SB_X1 = 2, SB_F0 = 3, SB_F1 = 4 };      // named barriers of the sweep pipeline
 // extra launch mode of the solve kernel: backward sweep only, z read from the factor's [A11^{-1} | z] stream (the fused
-// forward system of the large-bandwidth factorisation, band_big.cuh)
+// forward system of a split factorisation)
 constexpr int SM_BACKZ = 4;
 // the same for the two halves of a split system (2 CTAs per system, window initialised with the separator solution)
 constexpr int SM_BACKZ_OWN = 5;

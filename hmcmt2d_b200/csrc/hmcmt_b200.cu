@@ -10,7 +10,7 @@
 #include "../../include/hmcmt_b200.h"
 #include "band_factor.cuh"
 #include "band_solve.cuh"
-#include "band_big.cuh"
+#include "mf_solver.cuh"
 #include "mt_kernels.cuh"
 
 using namespace hmcmt;
@@ -57,7 +57,7 @@ struct hmcmt_plan {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> factorEvents;
     size_t factorEventsUsed = 0;
     int64_t launches = 0, factorLaunches = 0;
-    bool haveForward = false, sigmaDirect = false;
+    bool haveForward = false, sigmaDirect = false, useMf = false, timeFactor = false;
     // host copies
     std::vector<double> h_yLen, h_zLen, h_freqs;
     std::vector<int> h_packed2full;      // [nData] full index (without chain) of each packed datum
@@ -65,15 +65,20 @@ struct hmcmt_plan {
     DevBuf<double> yLen, zLen, zNode, freqs, fdy1, fdy2, wL, wR, bg, wmVal, wd, m, p, mref, sigma, meanSig, planes;
     DevBuf<double> xbuf, Gpart, phiPart, phi, gsig, gdata, gtotal, energies, panels, curM, curP, chainScal, zmom;
     DevBuf<int> fid, iL, iR, cell2act, act2cell, wmPtr, wmIdx, status, driftFlag, packed2full, Lsteps;
-    DevBuf<cplx> obs, bc, bcs, rhs, x, F, lam, Lam, srows, qrow, scratch, predFull, ainvz, zadj, vin, predPacked, wexp, bigWork, conCols;
+    DevBuf<cplx> obs, bc, bcs, rhs, x, F, lam, Lam, srows, qrow, scratch, predFull, ainvz, zadj, vin, predPacked, wexp, conCols;
     DevBuf<BandSys> sysDesc;
-    DevBuf<SolveJob> jobs, fwdJobs;                 // fwdJobs: backward sweeps of the fused forward systems (large-bandwidth path)
+    DevBuf<SolveJob> jobs, fwdJobs;                 // fwdJobs: back-substitution sweeps of the fused forward systems (split systems)
+    // wide meshes (half-bandwidth > 104): nested-dissection multifrontal solver (mf_solver.cuh) instead of the band kernels
+    mf::Solver* mfs = nullptr;
+    DevBuf<mf::MtValSys> mfSys;
     // pinned staging for the host-buffer entry points
     double* pin = nullptr;
     size_t pinBytes = 0;
 };
 
 namespace {
+
+constexpr size_t kMaxFactorEvents = 4096;      // CUDA-event pairs kept for hmcmt_kernel_time (opt-in, bounded)
 
 #define LAUNCH_CHECK(pl)                                          \
     do {                                                          \
@@ -140,71 +145,17 @@ int launch_solve_T(cudaStream_t st, const SolveJob* jobs, int njobs, const BandD
 
 }  // namespace
 
-namespace {
-template <int T>
-int launch_solve_mode_T(cudaStream_t st, const SolveJob* jobs, int njobs, const BandDom& dom, int mode) {
-    static PerDeviceOnce once;
-    size_t smem = sizeof(SolveSmem<T>);
-    if (once.need()) {
-        HMCMT_CUDA_TRY(cudaFuncSetAttribute(band_solve_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    }
-    band_solve_kernel<T><<<njobs, kSolveThreads, smem, st>>>(jobs, dom, mode);
-    HMCMT_CUDA_TRY(cudaGetLastError());
-    return kOk;
-}
-// large-bandwidth windows (band_big.cuh): one unsplit sweep per system
-int launch_solve_big(cudaStream_t st, int T, const SolveJob* jobs, int njobs, const BandDom& dom, int mode) {
-    switch (T) {
-        case 16: return launch_solve_mode_T<16>(st, jobs, njobs, dom, mode);
-        case 20: return launch_solve_mode_T<20>(st, jobs, njobs, dom, mode);
-        case 24: return launch_solve_mode_T<24>(st, jobs, njobs, dom, mode);
-        case 28: return launch_solve_mode_T<28>(st, jobs, njobs, dom, mode);
-        case 32: return launch_solve_mode_T<32>(st, jobs, njobs, dom, mode);
-        case 36: return launch_solve_mode_T<36>(st, jobs, njobs, dom, mode);
-        case 40: return launch_solve_mode_T<40>(st, jobs, njobs, dom, mode);
-        case 44: return launch_solve_mode_T<44>(st, jobs, njobs, dom, mode);
-        default: return kErrArg;
-    }
-}
-// Large-bandwidth factorisation: init, then one panel launch + one trailing-update launch per 32 columns, then the
-// backward sweep of the fused forward system (fwdJobs, optional).
-int launch_factor_big(cudaStream_t st, int T, const BandSys* sys, int nsys, const BandDom& dom, const SolveJob* fwdJobs, int* nLaunches) {
-    static PerDeviceOnce once;
-    if (once.need()) {
-        HMCMT_CUDA_TRY(cudaFuncSetAttribute(bigband_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)big_panel_smem_bytes(kBigMaxT)));
-    }
-    const int R = TS * T, sTot = (dom.N + TS - 1) / TS, nPanels = (sTot + kBigNBK - 1) / kBigNBK;
-    const int npos = T - kBigNBK, nYq = (npos + 3) / 4, nBlocks = ((npos + 1) / 2) * nYq;
-    const size_t smem = big_panel_smem_bytes(T);
-    bigband_init_kernel<<<dim3(T, nsys), 256, 0, st>>>(sys, dom, T);
-    for (int k = 0; k < nPanels; ++k) {
-        bigband_panel_kernel<<<dim3(kBigSplit, nsys), 4 * big_panel_local_rows(T), smem, st>>>(sys, dom, T, k);
-        if (k + 1 < nPanels) bigband_update_kernel<<<dim3(nBlocks + kBigNBK, nsys), 256, 0, st>>>(sys, dom, T, k, nYq, nBlocks);
-    }
-    HMCMT_CUDA_TRY(cudaGetLastError());
-    int n = 2 * nPanels;
-    if (fwdJobs) {
-        int rc = launch_solve_big(st, T, fwdJobs, nsys, dom, SM_BACKZ);
-        if (rc) return rc;
-        ++n;
-    }
-    if (nLaunches) *nLaunches = n;
-    return kOk;
-}
-}  // namespace
-
 namespace hmcmt {
 // shared with mumps_shim.cu
 int round_T(int b) {
-    if (b > 8 * 14 - 8) return big_T_for(b);      // window in global memory (band_big.cuh)
+    if (b > 8 * 14 - 8) return 0;                 // too wide for the register window: multifrontal solver (mf_solver.cuh)
     int T = band_T_for(b);
     if (T < 2) T = 2;
     if (T & 1) ++T;
     return T;
 }
-// fwdJobs: backward-sweep jobs of the fused forward systems, needed by the large-bandwidth path only (the register-window
-// kernel back-substitutes inside the factor launch).  nLaunches (optional) receives the number of kernels launched.
+// fwdJobs: back-substitution jobs of the fused forward systems (split systems: the pipelined sweep of band_solve.cuh).
+// nLaunches (optional) receives the number of kernels launched.
 int launch_factor(cudaStream_t st, int T, const BandSys* sys, int nsys, const BandDom& dom, const SolveJob* fwdJobs, int* nLaunches) {
     if (nLaunches) *nLaunches = dom.split ? 3 : 1;
     switch (T) {
@@ -215,9 +166,7 @@ int launch_factor(cudaStream_t st, int T, const BandSys* sys, int nsys, const Ba
         case 10: return launch_factor_T<10>(st, sys, nsys, dom, fwdJobs);
         case 12: return launch_factor_T<12>(st, sys, nsys, dom, fwdJobs);
         case 14: return launch_factor_T<14>(st, sys, nsys, dom, fwdJobs);
-        default:
-            if (T > 14 && T <= kBigMaxT && T % 4 == 0 && !dom.split) return launch_factor_big(st, T, sys, nsys, dom, fwdJobs, nLaunches);
-            return kErrArg;
+        default: return kErrArg;
     }
 }
 int launch_solve(cudaStream_t st, int T, const SolveJob* jobs, int njobs, const BandDom& dom) {
@@ -229,13 +178,20 @@ int launch_solve(cudaStream_t st, int T, const SolveJob* jobs, int njobs, const 
         case 10: return launch_solve_T<10>(st, jobs, njobs, dom);
         case 12: return launch_solve_T<12>(st, jobs, njobs, dom);
         case 14: return launch_solve_T<14>(st, jobs, njobs, dom);
-        default:
-            if (T > 14 && !dom.split) return launch_solve_big(st, T, jobs, njobs, dom, FM_FULL);
-            return kErrArg;
+        default: return kErrArg;
     }
 }
-int max_band_T() { return kBigMaxT; }
-size_t big_work_bytes(int T) { return T > 14 ? big_work_entries(T) * sizeof(cplx) : 0; }
+// multifrontal tuning knobs (leaf boxes of the nested dissection; largest front handled by the single-CTA kernel)
+int mf_leaf_size() {
+    const char* e = std::getenv("HMCMT_MF_LEAF");
+    const int v = e ? std::atoi(e) : 16;
+    return v < 1 ? 1 : v;
+}
+int mf_small_front() {
+    const char* e = std::getenv("HMCMT_MF_FSMALL");
+    int v = e ? std::atoi(e) : 144;
+    return v < 0 ? 0 : (v > 144 ? 144 : v);
+}
 }  // namespace hmcmt
 
 namespace {
@@ -396,22 +352,35 @@ int compute_step(hmcmt_plan* pl, bool wantAdjoint, const cplx* vin) {
         LAUNCH_CHECK(pl);
         HMCMT_CUDA_TRY(cudaEventRecord(pl->evJoin, pl->side));
     }
-    // factorisation + fused forward solve
+    // factorisation + forward solve (timed with CUDA events only when the caller asked for it: hmcmt_kernel_time(reset=1))
     {
-        if (pl->factorEventsUsed == pl->factorEvents.size()) {
-            cudaEvent_t a, b;
-            HMCMT_CUDA_TRY(cudaEventCreate(&a));
-            HMCMT_CUDA_TRY(cudaEventCreate(&b));
-            pl->factorEvents.emplace_back(a, b);
+        std::pair<cudaEvent_t, cudaEvent_t>* ev = nullptr;
+        if (pl->timeFactor && pl->factorEventsUsed < kMaxFactorEvents) {
+            if (pl->factorEventsUsed == pl->factorEvents.size()) {
+                cudaEvent_t a, b;
+                HMCMT_CUDA_TRY(cudaEventCreate(&a));
+                HMCMT_CUDA_TRY(cudaEventCreate(&b));
+                pl->factorEvents.emplace_back(a, b);
+            }
+            ev = &pl->factorEvents[pl->factorEventsUsed++];
+            HMCMT_CUDA_TRY(cudaEventRecord(ev->first, st));
         }
-        auto& ev = pl->factorEvents[pl->factorEventsUsed++];
-        HMCMT_CUDA_TRY(cudaEventRecord(ev.first, st));
-        int nl = 0;
-        int rc = launch_factor(st, pl->T, pl->sysDesc.p, nSys, pl->dom, pl->fwdJobs.p, &nl);
+        int rc;
+        if (pl->useMf) {
+            rc = pl->mfs->set_mt_values(st, M.N, pl->mfSys.p);
+            if (rc) return rc;
+            ++pl->launches;
+            rc = pl->mfs->factor(st, pl->status.p, &pl->launches);
+            if (rc) return rc;
+            rc = pl->mfs->solve(st, 1, pl->rhs.p, M.N, pl->x.p, M.N, &pl->launches);
+        } else {
+            int nl = 0;
+            rc = launch_factor(st, pl->T, pl->sysDesc.p, nSys, pl->dom, pl->fwdJobs.p, &nl);
+            pl->launches += nl;
+        }
         if (rc) return rc;
-        pl->launches += nl;
         ++pl->factorLaunches;
-        HMCMT_CUDA_TRY(cudaEventRecord(ev.second, st));
+        if (ev) HMCMT_CUDA_TRY(cudaEventRecord(ev->second, st));
     }
     k_node_field<<<dim3((M.nNode + 255) / 256, nSys), 256, 0, st>>>(M, pl->x.p, pl->bc.p, pl->F.p);
     LAUNCH_CHECK(pl);
@@ -423,9 +392,13 @@ int compute_step(hmcmt_plan* pl, bool wantAdjoint, const cplx* vin) {
     LAUNCH_CHECK(pl);
     pl->haveForward = true;
     if (!wantAdjoint) return kOk;
-    int rc = launch_solve(st, pl->T, pl->jobs.p, nSys, pl->dom);      // lam <- A^{-1} s[ii]  (in place)
+    int rc;                                                            // lam <- A^{-1} s[ii]  (in place)
+    if (pl->useMf) rc = pl->mfs->solve(st, 1, pl->lam.p, M.N, pl->lam.p, M.N, &pl->launches);
+    else {
+        rc = launch_solve(st, pl->T, pl->jobs.p, nSys, pl->dom);
+        pl->launches += pl->dom.split ? 3 : 1;
+    }
     if (rc) return rc;
-    pl->launches += pl->dom.split ? 3 : 1;
     k_node_field<<<dim3((M.nNode + 255) / 256, nSys), 256, 0, st>>>(M, pl->lam.p, nullptr, pl->Lam.p);
     LAUNCH_CHECK(pl);
     HMCMT_CUDA_TRY(cudaStreamWaitEvent(st, pl->evJoin, 0));
@@ -493,22 +466,23 @@ int hmcmt_plan_create(const hmcmt_problem* pr, hmcmt_plan** out) {
     M.nCell = ny * nz; M.nNode = (ny + 1) * (nz + 1); M.nb = 2 * (ny + nz);
     pl->b = M.nf;
     pl->T = round_T(pl->b);
+    if (M.nf < 2) { delete pl; return kErrArg; }
+    {
+        const char* env = std::getenv("HMCMT_SOLVER");          // "mf": multifrontal solver also for narrow meshes
+        pl->useMf = pl->T == 0 || (env && !std::strcmp(env, "mf"));
+        if (pl->useMf) pl->T = 0;
+    }
     {
         // two CTAs per system when there are enough lines: halves the sequential pivot chain
         const char* env = std::getenv("HMCMT_SPLIT");
         int want = env ? std::atoi(env) : 1;
-        pl->dom = BandDom{M.N, M.nf, pl->b, M.nl, (want && M.nl >= 9 && pl->T <= 14) ? 1 : 0, M.nl / 2};
-        LocalDom L0 = LocalDom::make(pl->dom, 0);
-        pl->steps0 = L0.sTot;
-        pl->steps1 = pl->dom.split ? LocalDom::make(pl->dom, 1).sOwn : 0;
-        pl->S = pl->steps0 + pl->steps1;
-    }
-    if (M.nf < 2) { delete pl; return kErrArg; }
-    if (pl->T > max_band_T()) {
-        fprintf(stderr, "[hmcmt_b200] half-bandwidth %d needs a tile window T=%d > %d: not supported\n",
-                pl->b, pl->T, max_band_T());
-        delete pl;
-        return kErrArg;
+        pl->dom = BandDom{M.N, M.nf, pl->b, M.nl, (!pl->useMf && want && M.nl >= 9) ? 1 : 0, M.nl / 2};
+        if (!pl->useMf) {
+            LocalDom L0 = LocalDom::make(pl->dom, 0);
+            pl->steps0 = L0.sTot;
+            pl->steps1 = pl->dom.split ? LocalDom::make(pl->dom, 1).sOwn : 0;
+            pl->S = pl->steps0 + pl->steps1;
+        }
     }
     pl->nSysPerChain = pl->nModes * pl->nFreq;
     pl->nSys = pl->nSysPerChain * pl->nChains;
@@ -595,8 +569,6 @@ int hmcmt_plan_create(const hmcmt_problem* pr, hmcmt_plan** out) {
     ok(pl->ainvz.alloc(nSys * (size_t)pl->S * AZ)); ok(pl->zadj.alloc(nSys * (size_t)pl->S * 8));
     const size_t wexpN = split_scratch_entries(TS * pl->T);
     ok(pl->wexp.alloc(pl->dom.split ? nSys * wexpN : 0));
-    const size_t bigN = pl->T > 14 ? big_work_entries(pl->T) : 0;
-    ok(pl->bigWork.alloc(nSys * bigN));
     ok(pl->conCols.alloc(nSys * contract_cols_out(ny, nz)));
     ok(pl->fwdJobs.alloc(nSys));
     ok(pl->status.alloc(nSys)); ok(pl->driftFlag.alloc(1)); ok(pl->Lsteps.alloc(nCh));
@@ -627,7 +599,6 @@ int hmcmt_plan_create(const hmcmt_problem* pr, hmcmt_plan** out) {
         d.ainvz[0] = pl->ainvz.p + s * (size_t)pl->S * AZ;
         d.ainvz[1] = d.ainvz[0] + (size_t)pl->steps0 * AZ;
         d.wexp = pl->dom.split ? pl->wexp.p + s * wexpN : nullptr;
-        d.big = bigN ? pl->bigWork.p + s * bigN : nullptr;
         d.x = pl->x.p + s * N;
         d.status = pl->status.p + s;
         SolveJob& j = jb[s];
@@ -669,6 +640,21 @@ int hmcmt_plan_create(const hmcmt_problem* pr, hmcmt_plan** out) {
             return kErrArg;
         }
     }
+    if (pl->useMf) {
+        // nested-dissection multifrontal solver for all systems of the plan (one symbolic analysis, shared by every system)
+        std::vector<std::vector<int>> sn;
+        std::vector<mf::Entry> ent;
+        mf::mf_order_grid(M.nl, M.nf, mf_leaf_size(), sn);
+        mf::mf_grid_entries(M.nl, M.nf, ent);
+        mf::Symbolic S;
+        if (!mf::mf_symbolic(M.N, sn, ent, mf_small_front(), S)) { hmcmt_destroy(pl); return kErrArg; }
+        int mrc = kOk;
+        pl->mfs = mf::Solver::create(std::move(S), pl->nSys, 1, 3 * (int64_t)M.N, &mrc);
+        if (!pl->mfs) { hmcmt_destroy(pl); return mrc; }
+        std::vector<mf::MtValSys> mv(nSys);
+        for (size_t s = 0; s < nSys; ++s) { mv[s].planes = sd[s].dr; mv[s].omega = sd[s].omega; }
+        if (pl->mfSys.upload(mv.data(), nSys) != kOk) { hmcmt_destroy(pl); return kErrAlloc; }
+    }
     if (cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&pl->side, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&pl->evFork, cudaEventDisableTiming) != cudaSuccess ||
@@ -700,7 +686,7 @@ void hmcmt_destroy(hmcmt_plan* pl) {
     pl->driftFlag.release(); pl->packed2full.release(); pl->Lsteps.release(); pl->obs.release(); pl->bc.release(); pl->bcs.release();
     pl->rhs.release(); pl->x.release(); pl->F.release(); pl->lam.release(); pl->Lam.release(); pl->srows.release(); pl->qrow.release();
     pl->scratch.release(); pl->predFull.release(); pl->ainvz.release(); pl->zadj.release(); pl->vin.release();
-    pl->predPacked.release(); pl->conCols.release(); pl->xbuf.release(); pl->wexp.release(); pl->bigWork.release(); pl->fwdJobs.release(); pl->sysDesc.release(); pl->jobs.release();
+    pl->predPacked.release(); pl->conCols.release(); pl->xbuf.release(); pl->wexp.release(); pl->mfSys.release(); delete pl->mfs; pl->mfs = nullptr; pl->fwdJobs.release(); pl->sysDesc.release(); pl->jobs.release();
     if (pl->pin) cudaFreeHost(pl->pin);
     delete pl;
 }
@@ -713,12 +699,15 @@ int64_t hmcmt_plan_info(const hmcmt_plan* pl, int what) {
         case 2: return pl->M.nCell;
         case 3: return pl->M.nb;
         case 4: return pl->b;
-        case 5: return pl->T;
+        case 5: return pl->T;                                      // 0: multifrontal solver
         case 6: return pl->S;
         case 7: return pl->nSysPerChain;
         case 8: return pl->M.zid;
-        case 9: return (int64_t)pl->S * (panel_doubles(pl->T) * 8 + AZ * 16);
+        case 9: return pl->useMf ? pl->mfs->factor_doubles() * 8 : (int64_t)pl->S * (panel_doubles(pl->T) * 8 + AZ * 16);
         case 10: return pl->launches;
+        case 11: return pl->useMf ? 1 : 0;
+        case 12: return pl->useMf ? (int64_t)pl->mfs->factor_flops() : (int64_t)(4.0 * pl->M.N * (double)pl->b * pl->b);
+        case 13: return pl->dom.split;
         default: return -1;
     }
 }
@@ -751,7 +740,7 @@ int hmcmt_kernel_time(hmcmt_plan* pl, int reset, float* factor_ms, int64_t* fact
     }
     if (factor_ms) *factor_ms = tot;
     if (factor_launches) *factor_launches = (int64_t)pl->factorEventsUsed;
-    if (reset) pl->factorEventsUsed = 0;
+    if (reset) { pl->factorEventsUsed = 0; pl->timeFactor = true; }      // timing is opt-in: the first reset switches it on
     return kOk;
 }
 

@@ -1,0 +1,282 @@
+// Host orchestration of the multifrontal solver (see mf_solver.cuh, mf_kernels.cuh).
+#include "mf_solver.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+
+#include "mf_kernels.cuh"
+
+namespace hmcmt {
+namespace mf {
+
+namespace {
+struct PerDeviceOnceMf {
+    bool done[64] = {};
+    bool need() {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+        if (done[dev]) return false;
+        done[dev] = true;
+        return true;
+    }
+};
+constexpr size_t kMaxSmem = 227 * 1024;
+
+template <int NW>
+int launch_small(cudaStream_t st, const Tables& tb, const int* list, int n, int nsys, size_t smem) {
+    static PerDeviceOnceMf once;
+    if (once.need()) HMCMT_CUDA_TRY(cudaFuncSetAttribute(mf_small_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    mf_small_kernel<NW><<<dim3(n, nsys), NW * 32, smem, st>>>(tb, list);
+    return kOk;
+}
+}  // namespace
+
+template <typename Tp>
+int Solver::upload(const std::vector<Tp>& h, Tp** d) {
+    *d = nullptr;
+    const size_t n = std::max<size_t>(h.size(), 1);
+    if (cudaMalloc(d, n * sizeof(Tp)) != cudaSuccess) return kErrAlloc;
+    owned.push_back(*d);
+    bytes += n * sizeof(Tp);
+    if (!h.empty() && cudaMemcpy(*d, h.data(), h.size() * sizeof(Tp), cudaMemcpyHostToDevice) != cudaSuccess) return kErrCuda;
+    return kOk;
+}
+
+Solver* Solver::create(Symbolic&& S, int nsys, int maxRhs, int64_t valCount, int* rc) {
+    Solver* s = new Solver();
+    s->S = std::move(S);
+    int r = s->build(nsys, maxRhs, valCount);
+    if (rc) *rc = r;
+    if (r != kOk) { delete s; return nullptr; }
+    return s;
+}
+
+Solver::~Solver() {
+    for (void* p : owned) cudaFree(p);
+}
+
+int Solver::build(int nsys_, int maxRhs_, int64_t valCount_) {
+    nsys = nsys_; maxRhs = std::max(1, maxRhs_); valCount = valCount_;
+    int rc;
+#define MF_TRY(x) do { rc = (x); if (rc) return rc; } while (0)
+    MF_TRY(upload(S.fronts, &d_fronts));
+    MF_TRY(upload(S.rows, &d_rows));
+    MF_TRY(upload(S.rel, &d_rel));
+    MF_TRY(upload(S.children, &d_children));
+    MF_TRY(upload(S.orig, &d_orig));
+    MF_TRY(upload(S.chunks, &d_chunks));
+    MF_TRY(upload(S.pos2orig, &d_pos2orig));
+    auto dalloc = [&](void** p, size_t nbytes) {
+        *p = nullptr;
+        if (nbytes == 0) nbytes = 16;
+        if (cudaMalloc(p, nbytes) != cudaSuccess) return (int)kErrAlloc;
+        owned.push_back(*p);
+        bytes += nbytes;
+        return (int)kOk;
+    };
+    MF_TRY(dalloc((void**)&d_fac, (size_t)nsys * S.factorDoubles * sizeof(double)));
+    for (int p = 0; p < 2; ++p) MF_TRY(dalloc((void**)&d_arena[p], (size_t)nsys * S.arenaDoubles[p] * sizeof(double)));
+    MF_TRY(dalloc((void**)&d_vals, (size_t)nsys * valCount * sizeof(cplx)));
+    MF_TRY(dalloc((void**)&d_v, (size_t)nsys * maxRhs * S.Np * sizeof(cplx)));
+    MF_TRY(dalloc((void**)&d_upd, (size_t)nsys * maxRhs * S.updEntries * sizeof(cplx)));
+
+    // launch schedule
+    sched.assign(S.maxDepth + 1, DepthSchedule());
+    for (int d = 0; d <= S.maxDepth; ++d) {
+        DepthSchedule& D = sched[d];
+        const std::vector<int>& sm = S.byDepthSmall[d];
+        const std::vector<int>& bg = S.byDepthBig[d];
+        int* p = nullptr;
+        D.nSmall = (int)sm.size();
+        if (D.nSmall) {
+            MF_TRY(upload(sm, &p));
+            D.smallList = p;
+            int mx = 0;
+            for (int k : sm) mx = std::max(mx, S.fronts[k].fp());
+            D.smallSmem = mf_sweep_smem_bytes(mx / 8);
+            D.smallWarps = mx <= 64 ? 4 : (mx <= 104 ? 8 : 16);
+        }
+        D.nBig = (int)bg.size();
+        D.bigBytes = (size_t)S.bigDoublesAtDepth[d] * sizeof(double);
+        std::vector<int> all(bg);
+        all.insert(all.end(), sm.begin(), sm.end());
+        D.nAll = (int)all.size();
+        if (D.nAll) { MF_TRY(upload(all, &p)); D.allList = p; }
+        if (!D.nBig) continue;
+        MF_TRY(upload(bg, &p));
+        D.bigList = p;
+        std::vector<int2> op;
+        int maxChild = 0, maxChunk = 0;
+        for (int k : bg) {
+            const Front& F = S.fronts[k];
+            for (int e = 0; e < F.nOrig; ++e) op.push_back(make_int2(k, F.origPtr + e));
+            maxChild = std::max(maxChild, F.nChild);
+            maxChunk = std::max(maxChunk, F.nChunk);
+        }
+        int2* p2 = nullptr;
+        D.nOrigPairs = (int)op.size();
+        if (D.nOrigPairs) { MF_TRY(upload(op, &p2)); D.origPairs = p2; }
+        for (int c = 0; c < maxChild; ++c) {
+            std::vector<int2> cp;
+            for (int k : bg) {
+                const Front& F = S.fronts[k];
+                if (F.nChild > c) {
+                    const int ch = S.children[F.childPtr + c];
+                    cp.push_back(make_int2(k, ch));
+                    D.maxChildU = std::max(D.maxChildU, S.fronts[ch].u);
+                }
+            }
+            MF_TRY(upload(cp, &p2));
+            D.childPasses.emplace_back(p2, (int)cp.size());
+        }
+        for (int c = 0; c < maxChunk; ++c) {
+            DepthSchedule::ChunkStep cs;
+            std::vector<int> inv;
+            std::vector<GemmJob> jobs;
+            std::vector<GemmTile> pt, st;
+            int maxSc = 0;
+            for (int k : bg) {
+                const Front& F = S.fronts[k];
+                if (F.nChunk <= c) continue;
+                const Chunk& ch = S.chunks[F.chunkPtr + c];
+                const int sc = ch.p1 - ch.p0, fp = F.fp(), mr = fp - ch.p1, par = F.depth & 1;
+                inv.push_back(k);
+                maxSc = std::max(maxSc, sc);
+                if (mr <= 0) continue;
+                GemmJob jp{};      // M = F21 G
+                jp.aOff = F.frontOff; jp.aSp = par; jp.ldA = fp; jp.rA = ch.p1; jp.kA = ch.p0;
+                jp.bOff = ch.gOff; jp.bSp = 2; jp.ldB = sc; jp.rB = 0; jp.kB = 0;
+                jp.cOff = ch.mOff; jp.cSp = 2; jp.ldC = mr; jp.rC = 0; jp.cC = 0;
+                jp.m = mr; jp.n = sc; jp.K = sc; jp.lower = 0; jp.beta = 0; jp.alpha = 1.0;
+                const int jpi = (int)jobs.size();
+                jobs.push_back(jp);
+                for (int bi = 0; bi < (mr + 63) / 64; ++bi)
+                    for (int bj = 0; bj < (sc + 63) / 64; ++bj) pt.push_back(GemmTile{jpi, bi, bj});
+                GemmJob js{};      // F22 -= M F21^T (lower tiles)
+                js.aOff = ch.mOff; js.aSp = 2; js.ldA = mr; js.rA = 0; js.kA = 0;
+                js.bOff = F.frontOff; js.bSp = par; js.ldB = fp; js.rB = ch.p1; js.kB = ch.p0;
+                js.cOff = F.frontOff; js.cSp = par; js.ldC = fp; js.rC = ch.p1; js.cC = ch.p1;
+                js.m = mr; js.n = mr; js.K = sc; js.lower = 1; js.beta = 1; js.alpha = -1.0;
+                const int jsi = (int)jobs.size();
+                jobs.push_back(js);
+                for (int bi = 0; bi < (mr + 63) / 64; ++bi)
+                    for (int bj = 0; bj <= bi; ++bj) st.push_back(GemmTile{jsi, bi, bj});
+            }
+            MF_TRY(upload(inv, &p));
+            cs.invList = p; cs.nInv = (int)inv.size();
+            cs.invSmem = mf_sweep_smem_bytes(maxSc / 8);
+            GemmJob* pj = nullptr;
+            GemmTile* ptile = nullptr;
+            MF_TRY(upload(jobs, &pj));
+            cs.jobs = pj;
+            MF_TRY(upload(pt, &ptile));
+            cs.panelTiles = ptile; cs.nPanelTiles = (int)pt.size();
+            MF_TRY(upload(st, &ptile));
+            cs.schurTiles = ptile; cs.nSchurTiles = (int)st.size();
+            D.chunkSteps.push_back(cs);
+        }
+    }
+    solveSmem = (size_t)(2 * S.maxFp + 16) * sizeof(cplx);
+    if (solveSmem > kMaxSmem || mf_sweep_smem_bytes(std::max(S.maxFpSmall, 8) / 8) > kMaxSmem) return kErrArg;
+#undef MF_TRY
+    return kOk;
+}
+
+int Solver::set_mt_values(cudaStream_t st, int N, const MtValSys* dSys) {
+    if (valCount < 3 * (int64_t)N) return kErrArg;
+    mf_mt_vals_kernel<<<dim3((3 * N + 255) / 256, nsys), 256, 0, st>>>(N, dSys, d_vals, valCount);
+    HMCMT_CUDA_TRY(cudaGetLastError());
+    return kOk;
+}
+
+int Solver::factor(cudaStream_t st, int* dStatus, int64_t* nLaunches) {
+    Tables tb{};
+    tb.fronts = d_fronts; tb.rows = d_rows; tb.rel = d_rel; tb.children = d_children; tb.orig = d_orig; tb.chunks = d_chunks;
+    tb.pos2orig = d_pos2orig; tb.fac = d_fac; tb.arena[0] = d_arena[0]; tb.arena[1] = d_arena[1];
+    tb.facStride = S.factorDoubles; tb.arenaStride[0] = S.arenaDoubles[0]; tb.arenaStride[1] = S.arenaDoubles[1];
+    tb.vals = d_vals; tb.valStride = valCount; tb.status = dStatus;
+    static PerDeviceOnceMf once;
+    if (once.need()) {
+        HMCMT_CUDA_TRY(cudaFuncSetAttribute(mf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+        HMCMT_CUDA_TRY(cudaFuncSetAttribute(mf_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes));
+    }
+    int64_t nl = 0;
+    for (int d = S.maxDepth; d >= 0; --d) {
+        const DepthSchedule& D = sched[d];
+        const int par = d & 1;
+        if (D.nSmall) {
+            int rc = kOk;
+            if (D.smallWarps == 4) rc = launch_small<4>(st, tb, D.smallList, D.nSmall, nsys, D.smallSmem);
+            else if (D.smallWarps == 8) rc = launch_small<8>(st, tb, D.smallList, D.nSmall, nsys, D.smallSmem);
+            else rc = launch_small<16>(st, tb, D.smallList, D.nSmall, nsys, D.smallSmem);
+            if (rc) return rc;
+            ++nl;
+        }
+        if (!D.nBig) continue;
+        HMCMT_CUDA_TRY(cudaMemset2DAsync(d_arena[par], (size_t)S.arenaDoubles[par] * sizeof(double), 0, D.bigBytes, nsys, st));
+        if (D.nOrigPairs) {
+            mf_asm_orig_kernel<<<dim3((D.nOrigPairs + 255) / 256, nsys), 256, 0, st>>>(tb, D.origPairs, D.nOrigPairs);
+            ++nl;
+        }
+        for (const auto& cp : D.childPasses) {
+            if (!cp.second) continue;
+            const int nseg = std::max(1, std::min(32, (D.maxChildU + 3) / 4));
+            mf_asm_child_kernel<<<dim3(cp.second, nsys, nseg), 256, 0, st>>>(tb, cp.first);
+            ++nl;
+        }
+        for (size_t c = 0; c < D.chunkSteps.size(); ++c) {
+            const DepthSchedule::ChunkStep& cs = D.chunkSteps[c];
+            if (!cs.nInv) continue;
+            mf_inv_kernel<<<dim3(cs.nInv, nsys), kInvWarps * 32, cs.invSmem, st>>>(tb, cs.invList, (int)c);
+            ++nl;
+            if (cs.nPanelTiles) {
+                mf_gemm_kernel<<<dim3(cs.nPanelTiles, nsys), kGemmThreads, kGemmSmemBytes, st>>>(
+                    tb, (const GemmJob*)cs.jobs, (const GemmTile*)cs.panelTiles);
+                ++nl;
+            }
+            if (cs.nSchurTiles) {
+                mf_gemm_kernel<<<dim3(cs.nSchurTiles, nsys), kGemmThreads, kGemmSmemBytes, st>>>(
+                    tb, (const GemmJob*)cs.jobs, (const GemmTile*)cs.schurTiles);
+                ++nl;
+            }
+        }
+    }
+    HMCMT_CUDA_TRY(cudaGetLastError());
+    if (nLaunches) *nLaunches += nl;
+    return kOk;
+}
+
+int Solver::solve(cudaStream_t st, int nrhs, const cplx* B, int64_t ldb, cplx* X, int64_t ldx, int64_t* nLaunches) {
+    if (nrhs < 1 || nrhs > maxRhs) return kErrArg;
+    Tables tb{};
+    tb.fronts = d_fronts; tb.rows = d_rows; tb.rel = d_rel; tb.children = d_children; tb.orig = d_orig; tb.chunks = d_chunks;
+    tb.pos2orig = d_pos2orig; tb.fac = d_fac; tb.arena[0] = d_arena[0]; tb.arena[1] = d_arena[1];
+    tb.facStride = S.factorDoubles; tb.arenaStride[0] = S.arenaDoubles[0]; tb.arenaStride[1] = S.arenaDoubles[1];
+    tb.vals = d_vals; tb.valStride = valCount; tb.status = nullptr;
+    SolveArgs sa{B, X, ldb, ldx, d_v, d_upd, (int64_t)S.Np, S.updEntries, nrhs};
+    static PerDeviceOnceMf once;
+    if (once.need()) {
+        HMCMT_CUDA_TRY(cudaFuncSetAttribute(mf_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+        HMCMT_CUDA_TRY(cudaFuncSetAttribute(mf_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    }
+    const int nvec = nsys * nrhs;
+    int64_t nl = 0;
+    for (int d = S.maxDepth; d >= 0; --d) {
+        const DepthSchedule& D = sched[d];
+        if (!D.nAll) continue;
+        mf_fwd_kernel<<<dim3(D.nAll, nvec), kSolveMfThreads, solveSmem, st>>>(tb, sa, D.allList);
+        ++nl;
+    }
+    for (int d = 0; d <= S.maxDepth; ++d) {
+        const DepthSchedule& D = sched[d];
+        if (!D.nAll) continue;
+        mf_bwd_kernel<<<dim3(D.nAll, nvec), kSolveMfThreads, solveSmem, st>>>(tb, sa, D.allList);
+        ++nl;
+    }
+    HMCMT_CUDA_TRY(cudaGetLastError());
+    if (nLaunches) *nLaunches += nl;
+    return kOk;
+}
+
+}  // namespace mf
+}  // namespace hmcmt

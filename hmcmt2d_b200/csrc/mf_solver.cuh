@@ -1,0 +1,89 @@
+// Host side of the multifrontal solver: owns the symbolic tables on the device, the per-batch arenas and the launch
+// schedule (depth by depth, deepest first).  Used by the Level-2 plan (hmcmt_b200.cu) for wide meshes and by the Level-1
+// shim (mumps_shim.cu) for arbitrary symmetric matrices.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "common.cuh"
+#include "mf_symbolic.h"
+
+namespace hmcmt {
+namespace mf {
+
+// one MT stencil system: planes = [dr | dm | e1 | e2] (4 N doubles, internal ordering of mt_kernels.cuh), A = dr + i omega dm on
+// the diagonal, e1 / e2 the in-line / cross-line couplings
+struct MtValSys {
+    const double* planes;
+    double omega;
+};
+
+struct DepthSchedule {
+    int nSmall = 0, smallWarps = 4;
+    size_t smallSmem = 0;
+    const int* smallList = nullptr;
+    int nBig = 0;
+    const int* bigList = nullptr;
+    int nOrigPairs = 0;
+    const int2* origPairs = nullptr;
+    std::vector<std::pair<const int2*, int>> childPasses;      // (pairs, count)
+    int maxChildU = 0;
+    struct ChunkStep {
+        const int* invList = nullptr;
+        int nInv = 0;
+        size_t invSmem = 0;
+        const void* jobs = nullptr;          // GemmJob[2*nInv]: panel jobs then trailing-update jobs
+        const void* panelTiles = nullptr;
+        int nPanelTiles = 0;
+        const void* schurTiles = nullptr;
+        int nSchurTiles = 0;
+    };
+    std::vector<ChunkStep> chunkSteps;
+    size_t bigBytes = 0;                     // leading part of the depth arena holding the large fronts (zeroed before assembly)
+    const int* allList = nullptr;            // solve: every front of the depth
+    int nAll = 0;
+};
+
+class Solver {
+  public:
+    // S is consumed.  nsys systems are factorised together; up to maxRhs right-hand sides per system in one solve call;
+    // valCount complex values per system (the sources referenced by the pattern entries).
+    static Solver* create(Symbolic&& S, int nsys, int maxRhs, int64_t valCount, int* rc);
+    ~Solver();
+    cplx* vals() { return d_vals; }
+    int64_t val_stride() const { return valCount; }
+    const Symbolic& symbolic() const { return S; }
+    // fills vals() of every system from its stencil planes (pattern of mf_grid_entries: [diag N | e1 N | e2 N])
+    int set_mt_values(cudaStream_t st, int N, const MtValSys* dSys);
+    // numeric factorisation of all systems from vals(); status: device array [nsys] (set to -10 on a singular pivot block)
+    int factor(cudaStream_t st, int* dStatus, int64_t* nLaunches = nullptr);
+    // nrhs right-hand sides per system: vector (sys, r) at B + (sys*nrhs + r)*ldb, original numbering; X may alias B
+    int solve(cudaStream_t st, int nrhs, const cplx* B, int64_t ldb, cplx* X, int64_t ldx, int64_t* nLaunches = nullptr);
+    size_t device_bytes() const { return bytes; }
+    double factor_flops() const { return S.flops; }
+    int64_t factor_doubles() const { return S.factorDoubles; }
+
+  private:
+    Solver() = default;
+    int build(int nsys, int maxRhs, int64_t valCount);
+    template <typename Tp>
+    int upload(const std::vector<Tp>& h, Tp** d);
+    Symbolic S;
+    int nsys = 0, maxRhs = 1;
+    int64_t valCount = 0;
+    size_t bytes = 0;
+    std::vector<void*> owned;
+    std::vector<DepthSchedule> sched;
+    // device tables
+    Front* d_fronts = nullptr;
+    int *d_rows = nullptr, *d_rel = nullptr, *d_children = nullptr, *d_pos2orig = nullptr;
+    OrigEntry* d_orig = nullptr;
+    Chunk* d_chunks = nullptr;
+    double* d_fac = nullptr;
+    double* d_arena[2] = {nullptr, nullptr};
+    cplx *d_vals = nullptr, *d_v = nullptr, *d_upd = nullptr;
+    size_t solveSmem = 0;
+};
+
+}  // namespace mf
+}  // namespace hmcmt

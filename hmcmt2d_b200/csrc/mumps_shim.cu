@@ -1,9 +1,15 @@
 // Level-1 ABI: the Fortran-style symbols the reference's Julia wrapper ccalls in
 // MUMPS/src/MUMPSfuncs.jl (factor :32-35/:49-52, solve :105-107/:128-130, sparse rhs :115-118/:139-143,
-// destroy :155-156/:170-171).  The factorisation runs on the B200 band kernel; matrices must be
-// structurally symmetric (sym = 1 or 2; the hot path passes sym = 1 for complex-symmetric Aii).
+// destroy :155-156/:170-171).  Matrices must be structurally symmetric (sym = 1 or 2; the hot path passes sym = 1 for the
+// complex-symmetric Aii).  Like MUMPS, the library chooses its own elimination order: matrices whose half-bandwidth in the
+// CALLER's numbering is <= 104 go to the register-window band kernel (band_factor.cuh); everything else — e.g. the
+// reference's y-fastest Aii (b = ny-1, MT2DFwdSolver.jl:232-234) or the 3-D div-grad matrices of MUMPS/test — is ordered by
+// nested dissection (breadth-first level-set bisection, mf_symbolic.h) and factorised by the multifrontal kernels
+// (mf_kernels.cuh).  The symbolic analysis is cached per sparsity pattern, so the per-frequency factorMUMPS calls of the
+// unmodified reference (mt2DTE.jl:50-53 inside the frequency loop) analyse the pattern once.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
@@ -12,23 +18,27 @@
 #include "../../include/hmcmt_b200.h"
 #include "band_factor.cuh"
 #include "band_solve.cuh"
+#include "mf_solver.cuh"
 
 namespace hmcmt {
 int round_T(int b);
 int launch_factor(cudaStream_t st, int T, const BandSys* sys, int nsys, const BandDom& dom, const SolveJob* fwdJobs, int* nLaunches);
-size_t big_work_bytes(int T);
 int launch_solve(cudaStream_t st, int T, const SolveJob* jobs, int njobs, const BandDom& dom);
-int max_band_T();
+int mf_leaf_size();
+int mf_small_front();
 }  // namespace hmcmt
 using namespace hmcmt;
 
 namespace {
+
+constexpr int kShimMaxRhs = 16;       // right-hand sides per multifrontal solve launch
 
 struct Factor {
     int n = 0, b = 0, T = 0, S = 0;
     bool isReal = false;
     double* panels = nullptr;
     cplx* ainvz = nullptr;
+    mf::Solver* mfs = nullptr;          // multifrontal factor (general ordering); else the band factor above
 };
 std::mutex g_mu;
 std::unordered_map<int64_t, Factor*> g_factors;
@@ -38,7 +48,91 @@ void free_factor(Factor* f) {
     if (!f) return;
     if (f->panels) cudaFree(f->panels);
     if (f->ainvz) cudaFree(f->ainvz);
+    delete f->mfs;
     delete f;
+}
+
+// ---- multifrontal path ----------------------------------------------------------------------------------------------
+// symbolic analysis cached per sparsity pattern (key: n, nnz and an FNV hash of colptr / rowval)
+struct PatternKey {
+    int64_t n, nnz;
+    uint64_t h;
+    bool operator==(const PatternKey& o) const { return n == o.n && nnz == o.nnz && h == o.h; }
+};
+struct PatternHash {
+    size_t operator()(const PatternKey& k) const { return (size_t)(k.h ^ (uint64_t)k.n * 0x9e3779b97f4a7c15ull); }
+};
+std::unordered_map<PatternKey, mf::Symbolic*, PatternHash> g_symbolic;
+
+uint64_t fnv(const int64_t* p, int64_t n, uint64_t h) {
+    for (int64_t i = 0; i < n; ++i) { h ^= (uint64_t)p[i]; h *= 0x100000001b3ull; }
+    return h;
+}
+
+const mf::Symbolic* symbolic_for(int64_t n, const int64_t* rowval, const int64_t* colptr) {
+    const int64_t nnz = colptr[n] - 1;
+    const int64_t knobs[2] = {mf_leaf_size(), mf_small_front()};
+    PatternKey key{n, nnz, fnv(knobs, 2, fnv(rowval, nnz, fnv(colptr, n + 1, 0xcbf29ce484222325ull)))};
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_symbolic.find(key);
+        if (it != g_symbolic.end()) return it->second;
+    }
+    std::vector<mf::Entry> ent;
+    ent.reserve((size_t)nnz / 2 + n);
+    std::vector<int> ptr(n + 1, 0);
+    for (int64_t j = 0; j < n; ++j)
+        for (int64_t k = colptr[j] - 1; k < colptr[j + 1] - 1; ++k) {
+            const int64_t i = rowval[k] - 1;
+            if (i < 0 || i >= n) return nullptr;
+            if (i < j) continue;                          // the lower triangle is what LDL^T reads
+            ent.push_back(mf::Entry{(int)i, (int)j, (int)k});
+            if (i != j) { ++ptr[i + 1]; ++ptr[j + 1]; }
+        }
+    for (int64_t i = 0; i < n; ++i) ptr[i + 1] += ptr[i];
+    std::vector<int> adj(ptr[n]), at(ptr.begin(), ptr.end() - 1);
+    for (const mf::Entry& e : ent)
+        if (e.row != e.col) { adj[at[e.row]++] = e.col; adj[at[e.col]++] = e.row; }
+    std::vector<std::vector<int>> sn;
+    mf::mf_order_graph((int)n, ptr, adj, mf_leaf_size(), sn);
+    mf::Symbolic* S = new mf::Symbolic();
+    if (!mf::mf_symbolic((int)n, sn, ent, mf_small_front(), *S)) { delete S; return nullptr; }
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_symbolic.size() >= 8) {                         // a handful of patterns at most (TE / TM, real / complex tests)
+        for (auto& kv : g_symbolic) delete kv.second;
+        g_symbolic.clear();
+    }
+    g_symbolic[key] = S;
+    return S;
+}
+
+int64_t factor_mf(int64_t n, const double* nzval, const int64_t* rowval, const int64_t* colptr, bool isReal, int64_t* status) {
+    auto fail = [&](int code) { if (status) *status = code; return (int64_t)0; };
+    const mf::Symbolic* S0 = symbolic_for(n, rowval, colptr);
+    if (!S0) return fail(kErrArg);
+    const int64_t nnz = colptr[n] - 1;
+    int rc = kOk;
+    mf::Symbolic copy = *S0;
+    mf::Solver* sv = mf::Solver::create(std::move(copy), 1, kShimMaxRhs, nnz, &rc);
+    if (!sv) return fail(rc);
+    std::vector<cplx> hv((size_t)nnz);
+    for (int64_t k = 0; k < nnz; ++k) hv[k] = isReal ? mk(nzval[k], 0.0) : mk(nzval[2 * k], nzval[2 * k + 1]);
+    int* dstatus = nullptr;
+    if (cudaMalloc(&dstatus, sizeof(int)) != cudaSuccess) { delete sv; return fail(kErrAlloc); }
+    cudaMemset(dstatus, 0, sizeof(int));
+    cudaMemcpy(sv->vals(), hv.data(), hv.size() * sizeof(cplx), cudaMemcpyHostToDevice);
+    rc = sv->factor(nullptr, dstatus);
+    int hst = 0;
+    if (rc == kOk && cudaDeviceSynchronize() != cudaSuccess) rc = kErrCuda;
+    if (rc == kOk) cudaMemcpy(&hst, dstatus, sizeof(int), cudaMemcpyDeviceToHost);
+    cudaFree(dstatus);
+    if (rc != kOk || hst != 0) { delete sv; return fail(rc != kOk ? rc : hst); }
+    Factor* f = new Factor();
+    f->n = (int)n; f->isReal = isReal; f->mfs = sv;
+    std::lock_guard<std::mutex> lk(g_mu);
+    int64_t h = g_next++;
+    g_factors[h] = f;
+    return h;
 }
 
 // common factor path; vals are complex (re,im) or real depending on isReal
@@ -62,10 +156,11 @@ int64_t factor_common(int64_t n, int64_t sym, const double* nzval, const int64_t
         for (int64_t k = colptr[j] - 1; k < colptr[j + 1] - 1; ++k) b = std::max<int64_t>(b, std::llabs(rowval[k] - 1 - j));
     if (b < 1) b = 1;
     int T = round_T((int)b);
-    if (T > max_band_T()) {
-        fprintf(stderr, "[hmcmt_b200] factor_mumps: half-bandwidth %lld exceeds the supported maximum %d\n",
-                (long long)b, 8 * max_band_T() - 32);
-        return fail(kErrArg);
+    {
+        const char* env = std::getenv("HMCMT_SHIM_SOLVER");      // "mf": multifrontal for every matrix; "band": refuse wide matrices
+        const bool forceMf = env && !std::strcmp(env, "mf"), forceBand = env && !std::strcmp(env, "band");
+        if ((T == 0 && !forceBand) || forceMf) return factor_mf(n, nzval, rowval, colptr, isReal, status);
+        if (T == 0) return fail(kErrArg);
     }
     // lower band image: band[g*(b+1)+d] = A[g][g-d]   (the lower triangle is what LDL^T reads)
     std::vector<cplx> band((size_t)n * (b + 1), mk(0.0, 0.0));
@@ -79,21 +174,20 @@ int64_t factor_common(int64_t n, int64_t sym, const double* nzval, const int64_t
     Factor* f = new Factor();
     f->n = (int)n; f->b = (int)b; f->T = T; f->S = (int)((n + TS - 1) / TS); f->isReal = isReal;
     cplx* dband = nullptr;
-    cplx* dbig = nullptr;
     BandSys* dsys = nullptr;
     int* dstatus = nullptr;
-    auto cleanup = [&]() { if (dband) cudaFree(dband); if (dbig) cudaFree(dbig); if (dsys) cudaFree(dsys); if (dstatus) cudaFree(dstatus); };
+    auto cleanup = [&]() { if (dband) cudaFree(dband); if (dsys) cudaFree(dsys); if (dstatus) cudaFree(dstatus); };
     if (cudaMalloc(&dband, band.size() * sizeof(cplx)) != cudaSuccess ||
         cudaMalloc(&f->panels, (size_t)f->S * panel_doubles(T) * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&f->ainvz, (size_t)f->S * AZ * sizeof(cplx)) != cudaSuccess || cudaMalloc(&dsys, sizeof(BandSys)) != cudaSuccess ||
-        cudaMalloc(&dstatus, sizeof(int)) != cudaSuccess || (big_work_bytes(T) && cudaMalloc(&dbig, big_work_bytes(T)) != cudaSuccess)) {
+        cudaMalloc(&dstatus, sizeof(int)) != cudaSuccess) {
         cleanup(); free_factor(f);
         return fail(kErrAlloc);
     }
     cudaMemcpy(dband, band.data(), band.size() * sizeof(cplx), cudaMemcpyHostToDevice);
     cudaMemset(dstatus, 0, sizeof(int));
     BandSys s{};
-    s.band = dband; s.omega = 0.0; s.rhs = nullptr; s.panels[0] = f->panels; s.panels[1] = nullptr; s.ainvz[0] = f->ainvz; s.ainvz[1] = nullptr; s.wexp = nullptr; s.big = dbig; s.x = nullptr; s.status = dstatus;
+    s.band = dband; s.omega = 0.0; s.rhs = nullptr; s.panels[0] = f->panels; s.panels[1] = nullptr; s.ainvz[0] = f->ainvz; s.ainvz[1] = nullptr; s.wexp = nullptr; s.x = nullptr; s.status = dstatus;
     cudaMemcpy(dsys, &s, sizeof(BandSys), cudaMemcpyHostToDevice);
     BandDom dom{(int)n, (int)b, (int)b, 0, 0, 0};
     int rc = launch_factor(nullptr, T, dsys, 1, dom, nullptr, nullptr);
@@ -121,6 +215,26 @@ int64_t solve_common(int64_t h, int64_t nrhs, const double* rhs, double* x, bool
     const size_t n = f->n;
     std::vector<cplx> hb(n * nrhs);
     for (size_t i = 0; i < n * (size_t)nrhs; ++i) hb[i] = isRealIO ? mk(rhs[i], 0.0) : mk(rhs[2 * i], rhs[2 * i + 1]);
+    if (f->mfs) {
+        cplx* db = nullptr;
+        if (cudaMalloc(&db, hb.size() * sizeof(cplx)) != cudaSuccess) return kErrAlloc;
+        cudaMemcpy(db, hb.data(), hb.size() * sizeof(cplx), cudaMemcpyHostToDevice);
+        int rc = kOk;
+        for (int64_t r0 = 0; r0 < nrhs && rc == kOk; r0 += kShimMaxRhs) {
+            const int nr = (int)std::min<int64_t>(kShimMaxRhs, nrhs - r0);
+            rc = f->mfs->solve(nullptr, nr, db + r0 * n, (int64_t)n, db + r0 * n, (int64_t)n);
+        }
+        if (rc == kOk && cudaDeviceSynchronize() != cudaSuccess) rc = kErrCuda;
+        if (rc == kOk) {
+            cudaMemcpy(hb.data(), db, hb.size() * sizeof(cplx), cudaMemcpyDeviceToHost);
+            for (size_t i = 0; i < hb.size(); ++i) {
+                if (isRealIO) x[i] = hb[i].x;
+                else { x[2 * i] = hb[i].x; x[2 * i + 1] = hb[i].y; }
+            }
+        }
+        cudaFree(db);
+        return rc;
+    }
     cplx *dx = nullptr, *dz = nullptr;
     SolveJob* djobs = nullptr;
     auto cleanup = [&]() { if (dx) cudaFree(dx); if (dz) cudaFree(dz); if (djobs) cudaFree(djobs); };
@@ -220,7 +334,7 @@ void solve_mumps_cmplx_sparse_rhs_(const int64_t* handle, const int64_t* nzrhs, 
 // debug: copy the raw factor (panel images, pivot-block inverses) back to the host
 int64_t hmcmt_debug_get_factor(int64_t handle, double* panels, double* ainv, int64_t* dims) {
     Factor* f = lookup(handle);
-    if (!f) return kErrArg;
+    if (!f || f->mfs) return kErrArg;
     if (dims) { dims[0] = f->n; dims[1] = f->b; dims[2] = f->T; dims[3] = f->S; }
     if (panels) cudaMemcpy(panels, f->panels, (size_t)f->S * panel_doubles(f->T) * sizeof(double), cudaMemcpyDeviceToHost);
     if (ainv) cudaMemcpy(ainv, f->ainvz, (size_t)f->S * AZ * sizeof(cplx), cudaMemcpyDeviceToHost);
