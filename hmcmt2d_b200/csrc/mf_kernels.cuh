@@ -43,7 +43,9 @@ struct Tables {
     const cplx* vals;       // [nsys][valStride]
     int64_t valStride;
     int* status;            // [nsys]
+    unsigned long long* prof;   // optional (HMCMT_MF_PROF=1): per-phase cycle totals of mf_small_kernel, thread 0 of every CTA
 };
+#define MF_PROF_MARK(slot) do { if (tb.prof && threadIdx.x == 0) { const long long _t = clock64(); atomicAdd(tb.prof + (slot), (unsigned long long)(_t - _t0)); _t0 = _t; } } while (0)
 
 // ------------------------------------------------------------------------------------------------------------------------
 // block sweep of the first npb pivot blocks of an nb x nb tile matrix held in shared memory (lower-triangle tiles, 128 doubles
@@ -51,24 +53,36 @@ struct Tables {
 template <int NW>
 __device__ __forceinline__ void mf_sweep(double* __restrict__ tiles, double* __restrict__ raw, double* __restrict__ mm,
                                          double* __restrict__ nainv, int* __restrict__ fail, const int nb, const int npb) {
-    constexpr int NT = NW * 32;
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int g = lane >> 2, t = lane & 3;
     const int R = nb * 8;
+    const int nT = nb * (nb + 1) / 2;
     auto tileP = [&](int I, int J) { return tiles + (size_t)(I * (I + 1) / 2 + J) * 128; };
     auto opnd = [&](double* base, int pl, int kk, int row) { return base + ((size_t)(pl * 2 + kk) * R + row) * 4; };
+    // lane roles of the tile <-> operand-panel copies: plane, row, k-half
+    const int cpl = lane >> 4, crow = (lane >> 1) & 7, ckk = lane & 1;
     for (int kb = 0; kb < npb; ++kb) {
-        // (a) column block kb of the symmetric matrix as an operand panel: raw_I = A[I][kb]
-        for (int idx = tid; idx < nb * 64; idx += NT) {
-            const int I = idx >> 6, r = (idx >> 3) & 7, c = idx & 7;
-            const double* src = I >= kb ? tileP(I, kb) + r * 8 + c : tileP(kb, I) + c * 8 + r;
-            opnd(raw, 0, c >> 2, I * 8 + r)[c & 3] = src[0];
-            opnd(raw, 1, c >> 2, I * 8 + r)[c & 3] = src[64];
+        // (a) column block kb of the symmetric matrix as an operand panel: raw_I = A[I][kb]  (one tile per warp and trip)
+        for (int I = warp; I < nb; I += NW) {
+            double2 v01, v23;
+            if (I >= kb) {
+                const double* src = tileP(I, kb) + cpl * 64 + crow * 8 + ckk * 4;
+                v01 = *reinterpret_cast<const double2*>(src);
+                v23 = *reinterpret_cast<const double2*>(src + 2);
+            } else {
+                const double* src = tileP(kb, I) + cpl * 64 + (ckk * 4) * 8 + crow;
+                v01 = make_double2(src[0], src[8]);
+                v23 = make_double2(src[16], src[24]);
+            }
+            double* dst = opnd(raw, cpl, ckk, I * 8 + crow);
+            *reinterpret_cast<double2*>(dst) = v01;
+            *reinterpret_cast<double2*>(dst + 2) = v23;
         }
-        __syncthreads();
-        // (b) P = A[kb][kb]^{-1} in registers; publish -P as the B operand and as the new diagonal tile
+        // (b) P = A[kb][kb]^{-1} in registers (warp 0 reads the diagonal tile itself: no barrier needed before);
+        //     publish -P as the B operand and as the new diagonal tile
         if (warp == 0) {
+            __syncwarp();
             double* D = tileP(kb, kb);
             const double2 vre = *reinterpret_cast<const double2*>(D + g * 8 + 2 * t);
             const double2 vim = *reinterpret_cast<const double2*>(D + 64 + g * 8 + 2 * t);
@@ -79,10 +93,16 @@ __device__ __forceinline__ void mf_sweep(double* __restrict__ tiles, double* __r
             const int j0 = 2 * t;
             *reinterpret_cast<double2*>(nainv + ((0 * 2 + (j0 >> 2)) * 8 + g) * 4 + (j0 & 3)) = make_double2(-a0.x, -a1.x);
             *reinterpret_cast<double2*>(nainv + ((1 * 2 + (j0 >> 2)) * 8 + g) * 4 + (j0 & 3)) = make_double2(-a0.y, -a1.y);
-            *reinterpret_cast<double2*>(D + g * 8 + 2 * t) = make_double2(-a0.x, -a1.x);
-            *reinterpret_cast<double2*>(D + 64 + g * 8 + 2 * t) = make_double2(-a0.y, -a1.y);
         }
         __syncthreads();
+        if (warp == 0) {       // the raw copy of the diagonal tile is complete: the tile itself may now take -P
+            double* D = tileP(kb, kb);
+            const int j0 = 2 * t;
+            const double2 pre = *reinterpret_cast<const double2*>(nainv + ((0 * 2 + (j0 >> 2)) * 8 + g) * 4 + (j0 & 3));
+            const double2 pim = *reinterpret_cast<const double2*>(nainv + ((1 * 2 + (j0 >> 2)) * 8 + g) * 4 + (j0 & 3));
+            *reinterpret_cast<double2*>(D + g * 8 + 2 * t) = pre;
+            *reinterpret_cast<double2*>(D + 64 + g * 8 + 2 * t) = pim;
+        }
         // (c) m_I = raw_I (-P) for every block row I != kb
         for (int I = warp; I < nb; I += NW) {
             if (I == kb) continue;
@@ -102,30 +122,26 @@ __device__ __forceinline__ void mf_sweep(double* __restrict__ tiles, double* __r
             *reinterpret_cast<double2*>(opnd(mm, 1, t >> 1, r) + (t & 1) * 2) = make_double2(mim[0], mim[1]);
         }
         __syncthreads();
-        // (d) A[I][J] += m_I raw_J^T for I,J != kb ;  (e) column kb <- raw P = -m
-        int cnt = 0;
-        for (int I = 0; I < nb; ++I)
-            for (int J = 0; J <= I; ++J, ++cnt) {
-                if (cnt % NW != warp) continue;
-                double* T = tileP(I, J);
-                if (I == kb && J == kb) continue;
-                if (J == kb) {              // I > kb
-                    const double2 a = *reinterpret_cast<const double2*>(opnd(mm, 0, t >> 1, I * 8 + g) + (t & 1) * 2);
-                    const double2 b = *reinterpret_cast<const double2*>(opnd(mm, 1, t >> 1, I * 8 + g) + (t & 1) * 2);
-                    *reinterpret_cast<double2*>(T + g * 8 + 2 * t) = make_double2(-a.x, -a.y);
-                    *reinterpret_cast<double2*>(T + 64 + g * 8 + 2 * t) = make_double2(-b.x, -b.y);
-                    continue;
-                }
-                if (I == kb) {              // J < kb: transposed
+        // (d) A[I][J] += m_I raw_J^T for I,J != kb ;  (e) column kb <- raw P = -m.   Lower tiles dealt round-robin to the warps.
+        int I = 0, J = warp;
+        while (J > I) { J -= I + 1; ++I; }
+        for (int L = warp; L < nT; L += NW) {
+            double* T = tileP(I, J);
+            if (I == kb && J == kb) {
+            } else if (J == kb) {              // I > kb
+                const double2 a = *reinterpret_cast<const double2*>(opnd(mm, 0, t >> 1, I * 8 + g) + (t & 1) * 2);
+                const double2 b = *reinterpret_cast<const double2*>(opnd(mm, 1, t >> 1, I * 8 + g) + (t & 1) * 2);
+                *reinterpret_cast<double2*>(T + g * 8 + 2 * t) = make_double2(-a.x, -a.y);
+                *reinterpret_cast<double2*>(T + 64 + g * 8 + 2 * t) = make_double2(-b.x, -b.y);
+            } else if (I == kb) {              // J < kb: transposed
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        T[g * 8 + 2 * t + e] = -opnd(mm, 0, g >> 2, J * 8 + 2 * t + e)[g & 3];
-                        T[64 + g * 8 + 2 * t + e] = -opnd(mm, 1, g >> 2, J * 8 + 2 * t + e)[g & 3];
-                    }
-                    continue;
+                for (int e = 0; e < 2; ++e) {
+                    T[g * 8 + 2 * t + e] = -opnd(mm, 0, g >> 2, J * 8 + 2 * t + e)[g & 3];
+                    T[64 + g * 8 + 2 * t + e] = -opnd(mm, 1, g >> 2, J * 8 + 2 * t + e)[g & 3];
                 }
-                double2 cr = *reinterpret_cast<const double2*>(T + g * 8 + 2 * t);
-                double2 ci = *reinterpret_cast<const double2*>(T + 64 + g * 8 + 2 * t);
+            } else {
+                const double2 cr = *reinterpret_cast<const double2*>(T + g * 8 + 2 * t);
+                const double2 ci = *reinterpret_cast<const double2*>(T + 64 + g * 8 + 2 * t);
                 double cre[2] = {cr.x, cr.y}, cim[2] = {ci.x, ci.y}, t1[2] = {0.0, 0.0}, t2[2] = {0.0, 0.0};
                 const int ra = I * 8 + g, rb = J * 8 + g;
 #pragma unroll
@@ -140,6 +156,9 @@ __device__ __forceinline__ void mf_sweep(double* __restrict__ tiles, double* __r
                 *reinterpret_cast<double2*>(T + g * 8 + 2 * t) = make_double2(cre[0] + t1[0], cre[1] + t1[1]);
                 *reinterpret_cast<double2*>(T + 64 + g * 8 + 2 * t) = make_double2(cim[0] + t2[0], cim[1] + t2[1]);
             }
+            J += NW;
+            while (J > I) { J -= I + 1; ++I; }
+        }
         __syncthreads();
     }
 }
@@ -156,6 +175,28 @@ __device__ __forceinline__ cplx mf_tile_get(const double* tiles, int a, int b) {
     return mk(T[0], T[64]);
 }
 
+// one 8x8 tile (shared memory, [plane][8][8]) -> k-grouped global matrix with ld rows at (row0, col0); executed by one warp:
+// lane = (chunk, row): chunk = (plane, column group of four), 32 contiguous bytes per lane, 256 per eight lanes.
+// TRANSPOSED: the tile holds the transposed block.  sign: +1 / -1.
+template <bool TRANSPOSED>
+__device__ __forceinline__ void mf_store_tile(const double* __restrict__ T, double* __restrict__ dst, int ld, int row0, int col0,
+                                              double sign, int lane) {
+    const int pl = lane >> 4, cg = (lane >> 3) & 1, row = lane & 7;
+    double2 v01, v23;
+    if (!TRANSPOSED) {
+        const double* src = T + pl * 64 + row * 8 + cg * 4;
+        v01 = *reinterpret_cast<const double2*>(src);
+        v23 = *reinterpret_cast<const double2*>(src + 2);
+    } else {
+        const double* src = T + pl * 64 + (cg * 4) * 8 + row;
+        v01 = make_double2(src[0], src[8]);
+        v23 = make_double2(src[16], src[24]);
+    }
+    double* out = dst + kg_off(ld, row0 + row, col0 + cg * 4, pl);
+    *reinterpret_cast<double2*>(out) = make_double2(sign * v01.x, sign * v01.y);
+    *reinterpret_cast<double2*>(out + 2) = make_double2(sign * v23.x, sign * v23.y);
+}
+
 // ------------------------------------------------------------------------------------------------------------------------
 // small fronts: one CTA per (front, system).  list[blockIdx.x] = front id.
 template <int NW>
@@ -164,7 +205,8 @@ mf_small_kernel(Tables tb, const int* __restrict__ list) {
     constexpr int NT = NW * 32;
     extern __shared__ __align__(16) unsigned char mf_smem[];
     const Front F = tb.fronts[list[blockIdx.x]];
-    const int sys = blockIdx.y, tid = threadIdx.x;
+    const int sys = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int fp = F.sp + F.up, nb = fp >> 3, npb = F.sp >> 3;
     const int nT = nb * (nb + 1) / 2;
     double* tiles = reinterpret_cast<double*>(mf_smem);
@@ -172,13 +214,49 @@ mf_small_kernel(Tables tb, const int* __restrict__ list) {
     double* mm = raw + 16 * (size_t)fp;
     double* nainv = mm + 16 * (size_t)fp;
     int* fail = reinterpret_cast<int*>(nainv + 128);
-    for (int i = tid; i < nT * 128; i += NT) tiles[i] = 0.0;
+    long long _t0 = clock64();
+    for (int i = tid; i < nT * 64; i += NT) reinterpret_cast<double2*>(tiles)[i] = make_double2(0.0, 0.0);
     if (tid == 0) *fail = 0;
     __syncthreads();
+    MF_PROF_MARK(0);
     auto addr = [&](int a, int b) {       // a >= b
         return tiles + (size_t)((a >> 3) * ((a >> 3) + 1) / 2 + (b >> 3)) * 128 + (a & 7) * 8 + (b & 7);
     };
-    // original matrix entries of the pivot columns
+    // extend-add of the children's update matrices.  Up to two children are added in ONE pass with shared-memory atomics onto the
+    // zeroed tiles: 0 + a + b does not depend on the order, so the result stays deterministic; further children take a pass each.
+    const double* carena = tb.arena[(F.depth + 1) & 1] + (size_t)sys * tb.arenaStride[(F.depth + 1) & 1];
+    for (int c0 = 0; c0 < F.nChild; c0 += 2) {
+        const int nc = min(2, F.nChild - c0);
+        for (int c = c0; c < c0 + nc; ++c) {
+            const Front& C = tb.fronts[tb.children[F.childPtr + c]];
+            const int cu = C.u, cup = C.up;
+            const int ld = C.isBig ? C.sp + cup : cup, off = C.isBig ? C.sp : 0;
+            const double* U = carena + C.frontOff;
+            const int* rel = tb.rel + C.rowPtr;
+            const int ng = (cu + 3) >> 2;
+            for (int idx = tid; idx < ng * cup; idx += NT) {
+                const int jg = idx / cup, i = idx - jg * cup;
+                if (i >= cu || i < 4 * jg) continue;
+                const double* pr = U + kg_off(ld, off + i, off + 4 * jg, 0);
+                const double* pi = U + kg_off(ld, off + i, off + 4 * jg, 1);
+                const double2 r01 = *reinterpret_cast<const double2*>(pr), r23 = *reinterpret_cast<const double2*>(pr + 2);
+                const double2 i01 = *reinterpret_cast<const double2*>(pi), i23 = *reinterpret_cast<const double2*>(pi + 2);
+                const double re[4] = {r01.x, r01.y, r23.x, r23.y}, im[4] = {i01.x, i01.y, i23.x, i23.y};
+                const int ri = rel[i];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int j = 4 * jg + jj;
+                    if (j > i) break;
+                    double* d = addr(ri, rel[j]);
+                    atomicAdd(d, re[jj]);
+                    atomicAdd(d + 64, im[jj]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    MF_PROF_MARK(2);
+    // original matrix entries of the pivot columns (added last: (a + b) + orig for every child order)
     const cplx* vals = tb.vals + (size_t)sys * tb.valStride;
     for (int e = tid; e < F.nOrig; e += NT) {
         const OrigEntry oe = tb.orig[F.origPtr + e];
@@ -188,34 +266,7 @@ mf_small_kernel(Tables tb, const int* __restrict__ list) {
         d[64] += v.y;
     }
     __syncthreads();
-    // extend-add of the children's update matrices (one child at a time: entries of one child never collide)
-    const double* carena = tb.arena[(F.depth + 1) & 1] + (size_t)sys * tb.arenaStride[(F.depth + 1) & 1];
-    for (int c = 0; c < F.nChild; ++c) {
-        const Front C = tb.fronts[tb.children[F.childPtr + c]];
-        const int ld = C.isBig ? C.sp + C.up : C.up, off = C.isBig ? C.sp : 0;
-        const double* U = carena + C.frontOff;
-        const int* rel = tb.rel + C.rowPtr;
-        const int ng = (C.u + 3) >> 2;
-        for (int idx = tid; idx < ng * C.up; idx += NT) {
-            const int jg = idx / C.up, i = idx - jg * C.up;
-            if (i >= C.u || i < 4 * jg) continue;
-            const double* pr = U + kg_off(ld, off + i, off + 4 * jg, 0);
-            const double* pi = U + kg_off(ld, off + i, off + 4 * jg, 1);
-            const double2 r01 = *reinterpret_cast<const double2*>(pr), r23 = *reinterpret_cast<const double2*>(pr + 2);
-            const double2 i01 = *reinterpret_cast<const double2*>(pi), i23 = *reinterpret_cast<const double2*>(pi + 2);
-            const double re[4] = {r01.x, r01.y, r23.x, r23.y}, im[4] = {i01.x, i01.y, i23.x, i23.y};
-            const int ri = rel[i];
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                const int j = 4 * jg + jj;
-                if (j > i) break;
-                double* d = addr(ri, rel[j]);
-                d[0] += re[jj];
-                d[64] += im[jj];
-            }
-        }
-        __syncthreads();
-    }
+    MF_PROF_MARK(1);
     // diagonal tiles: mirror the lower triangle
     for (int idx = tid; idx < nb * 64; idx += NT) {
         const int I = idx >> 6, r = (idx >> 3) & 7, c = idx & 7;
@@ -226,50 +277,40 @@ mf_small_kernel(Tables tb, const int* __restrict__ list) {
         }
     }
     __syncthreads();
+    MF_PROF_MARK(3);
     mf_sweep<NW>(tiles, raw, mm, nainv, fail, nb, npb);
+    MF_PROF_MARK(4);
     if (tid == 0 && *fail) tb.status[sys] = kErrSingular;
-    // outputs: G = -(pivot x pivot), M = update x pivot (factor arena), U = update x update (update arena, lower column groups)
+    // outputs, tile by tile: G = -(pivot x pivot), M = update x pivot (factor arena), U = update x update (update arena, lower tiles)
     const Chunk ch = tb.chunks[F.chunkPtr];
     double* fac = tb.fac + (size_t)sys * tb.facStride;
-    const int sp = F.sp, up = F.up;
+    const int sp = F.sp, up = F.up, nub = nb - npb;
+    auto tileP = [&](int I, int J) { return tiles + (size_t)(I * (I + 1) / 2 + J) * 128; };
     {
         double* G = fac + ch.gOff;
-        for (int idx = tid; idx < (sp >> 2) * sp; idx += NT) {
-            const int jg = idx / sp, i = idx - jg * sp;
-            double re[4], im[4];
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) { const cplx v = mf_tile_get(tiles, i, 4 * jg + jj); re[jj] = -v.x; im[jj] = -v.y; }
-            double* pr = G + kg_off(sp, i, 4 * jg, 0);
-            double* pi = G + kg_off(sp, i, 4 * jg, 1);
-            *reinterpret_cast<double2*>(pr) = make_double2(re[0], re[1]); *reinterpret_cast<double2*>(pr + 2) = make_double2(re[2], re[3]);
-            *reinterpret_cast<double2*>(pi) = make_double2(im[0], im[1]); *reinterpret_cast<double2*>(pi + 2) = make_double2(im[2], im[3]);
+        for (int q = warp; q < npb * npb; q += NW) {
+            const int I = q / npb, J = q - I * npb;
+            if (I >= J) mf_store_tile<false>(tileP(I, J), G, sp, I * 8, J * 8, -1.0, lane);
+            else mf_store_tile<true>(tileP(J, I), G, sp, I * 8, J * 8, -1.0, lane);
         }
     }
     if (up > 0) {
         double* M = fac + ch.mOff;
-        for (int idx = tid; idx < (sp >> 2) * up; idx += NT) {
-            const int jg = idx / up, i = idx - jg * up;
-            double re[4], im[4];
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) { const cplx v = mf_tile_get(tiles, sp + i, 4 * jg + jj); re[jj] = v.x; im[jj] = v.y; }
-            double* pr = M + kg_off(up, i, 4 * jg, 0);
-            double* pi = M + kg_off(up, i, 4 * jg, 1);
-            *reinterpret_cast<double2*>(pr) = make_double2(re[0], re[1]); *reinterpret_cast<double2*>(pr + 2) = make_double2(re[2], re[3]);
-            *reinterpret_cast<double2*>(pi) = make_double2(im[0], im[1]); *reinterpret_cast<double2*>(pi + 2) = make_double2(im[2], im[3]);
+        for (int q = warp; q < nub * npb; q += NW) {
+            const int I = q / npb, J = q - I * npb;
+            mf_store_tile<false>(tileP(npb + I, J), M, up, I * 8, J * 8, 1.0, lane);
         }
         double* U = tb.arena[F.depth & 1] + (size_t)sys * tb.arenaStride[F.depth & 1] + F.frontOff;
-        for (int idx = tid; idx < (up >> 2) * up; idx += NT) {
-            const int jg = idx / up, i = idx - jg * up;
-            if (i < 4 * jg) continue;
-            double re[4], im[4];
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) { const cplx v = mf_tile_get(tiles, sp + i, sp + 4 * jg + jj); re[jj] = v.x; im[jj] = v.y; }
-            double* pr = U + kg_off(up, i, 4 * jg, 0);
-            double* pi = U + kg_off(up, i, 4 * jg, 1);
-            *reinterpret_cast<double2*>(pr) = make_double2(re[0], re[1]); *reinterpret_cast<double2*>(pr + 2) = make_double2(re[2], re[3]);
-            *reinterpret_cast<double2*>(pi) = make_double2(im[0], im[1]); *reinterpret_cast<double2*>(pi + 2) = make_double2(im[2], im[3]);
+        int I = 0, J = warp;
+        while (J > I) { J -= I + 1; ++I; }
+        for (int L = warp; L < nub * (nub + 1) / 2; L += NW) {
+            mf_store_tile<false>(tileP(npb + I, npb + J), U, up, I * 8, J * 8, 1.0, lane);
+            J += NW;
+            while (J > I) { J -= I + 1; ++I; }
         }
     }
+    MF_PROF_MARK(5);
+    if (tb.prof && tid == 0) { atomicAdd(tb.prof + 6, 1ull); atomicAdd(tb.prof + 7, (unsigned long long)npb); }
 }
 
 // ------------------------------------------------------------------------------------------------------------------------
@@ -641,6 +682,99 @@ mf_bwd_kernel(Tables tb, SolveArgs sa, const int* __restrict__ list) {
     for (int i = tid; i < F.sp; i += kSolveMfThreads) {
         v[F.cbp + i] = xf[i];
         if (i < F.s) x[tb.pos2orig[F.cbp + i]] = xf[i];
+    }
+}
+
+
+// Small fronts (single chunk, fp <= kSolveSmallMax): one WARP per (front, right-hand side), eight fronts per CTA, warp-level
+// synchronisation only.  list[blockIdx.x * 8 + warp] = front id.
+constexpr int kSolveSmallMax = 144;
+constexpr int kSolveWarpsPerCta = 8;
+__global__ void __launch_bounds__(kSolveWarpsPerCta * 32)
+mf_fwd_warp_kernel(Tables tb, SolveArgs sa, const int* __restrict__ list, int n) {
+    __shared__ cplx wsh[kSolveWarpsPerCta][kSolveSmallMax];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int fi = blockIdx.x * kSolveWarpsPerCta + warp;
+    if (fi >= n) return;
+    const Front& F = tb.fronts[list[fi]];
+    const int vec = blockIdx.y, sys = vec / sa.nrhs;
+    const int sp = F.sp, up = F.up, fp = sp + up, fs = F.s, cbp = F.cbp;
+    cplx* w = wsh[warp];
+    const cplx* b = sa.B + (size_t)vec * sa.ldb;
+    cplx* v = sa.v + (size_t)vec * sa.Np;
+    cplx* upd = sa.upd + (size_t)vec * sa.updEntries;
+    for (int i = lane; i < fp; i += 32) w[i] = i < fs ? b[tb.pos2orig[cbp + i]] : mk(0.0, 0.0);
+    __syncwarp();
+    const int nChild = F.nChild, childPtr = F.childPtr;
+    for (int c = 0; c < nChild; ++c) {
+        const Front& C = tb.fronts[tb.children[childPtr + c]];
+        const int* rel = tb.rel + C.rowPtr;
+        const cplx* uv = upd + C.updOff;
+        const int cu = C.u;
+        for (int i = lane; i < cu; i += 32) w[rel[i]] += uv[i];
+        __syncwarp();
+    }
+    if (up > 0) {
+        const double* M = tb.fac + (size_t)sys * tb.facStride + tb.chunks[F.chunkPtr].mOff;
+        for (int i = lane; i < up; i += 32) {
+            cplx acc = mk(0.0, 0.0);
+            for (int kg = 0; kg < (sp >> 2); ++kg) {
+                const double* pr = M + kg_off(up, i, 4 * kg, 0);
+                const double* pi = M + kg_off(up, i, 4 * kg, 1);
+                const double2 r01 = *reinterpret_cast<const double2*>(pr), r23 = *reinterpret_cast<const double2*>(pr + 2);
+                const double2 i01 = *reinterpret_cast<const double2*>(pi), i23 = *reinterpret_cast<const double2*>(pi + 2);
+                const cplx* wk = w + 4 * kg;
+                cfma(acc, mk(r01.x, i01.x), wk[0]);
+                cfma(acc, mk(r01.y, i01.y), wk[1]);
+                cfma(acc, mk(r23.x, i23.x), wk[2]);
+                cfma(acc, mk(r23.y, i23.y), wk[3]);
+            }
+            upd[F.updOff + i] = w[sp + i] - acc;
+        }
+    }
+    for (int i = lane; i < sp; i += 32) v[cbp + i] = w[i];
+}
+
+__global__ void __launch_bounds__(kSolveWarpsPerCta * 32)
+mf_bwd_warp_kernel(Tables tb, SolveArgs sa, const int* __restrict__ list, int n) {
+    __shared__ cplx xsh[kSolveWarpsPerCta][kSolveSmallMax];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int fi = blockIdx.x * kSolveWarpsPerCta + warp;
+    if (fi >= n) return;
+    const Front& F = tb.fronts[list[fi]];
+    const int vec = blockIdx.y, sys = vec / sa.nrhs;
+    const int sp = F.sp, up = F.up, fp = sp + up, fs = F.s, fu = F.u, cbp = F.cbp;
+    cplx* xf = xsh[warp];
+    cplx* v = sa.v + (size_t)vec * sa.Np;
+    cplx* x = sa.X + (size_t)vec * sa.ldx;
+    const int* rows = tb.rows + F.rowPtr;
+    for (int i = lane; i < fp; i += 32) {
+        cplx val = mk(0.0, 0.0);
+        if (i < sp) val = v[cbp + i];
+        else if (i - sp < fu) val = v[rows[i - sp]];
+        xf[i] = val;
+    }
+    __syncwarp();
+    const Chunk ch = tb.chunks[F.chunkPtr];
+    const double* G = tb.fac + (size_t)sys * tb.facStride + ch.gOff;
+    const double* M = tb.fac + (size_t)sys * tb.facStride + ch.mOff;
+    // x1[k] = sum_j G[j][k] w1[j] - sum_i M[i][k] x2[i] : one lane per k (no reduction; four lanes share a 32-byte sector)
+    for (int k0 = 0; k0 < sp; k0 += 32) {
+        const int k = k0 + lane;
+        cplx acc = mk(0.0, 0.0);
+        if (k < sp) {
+            const double* gr = G + kg_off(sp, 0, k, 0);
+            const double* gi = G + kg_off(sp, 0, k, 1);
+            for (int j = 0; j < sp; ++j) cfma(acc, mk(gr[4 * j], gi[4 * j]), xf[j]);
+            const double* mr = M + kg_off(up, 0, k, 0);
+            const double* mi = M + kg_off(up, 0, k, 1);
+            for (int i = 0; i < up; ++i) cfma(acc, mk(-mr[4 * i], -mi[4 * i]), xf[sp + i]);
+        }
+        __syncwarp();
+        if (k < sp) {
+            v[cbp + k] = acc;
+            if (k < fs) x[tb.pos2orig[cbp + k]] = acc;
+        }
     }
 }
 

@@ -2,6 +2,7 @@
 #include "mf_solver.cuh"
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 #include "mf_kernels.cuh"
@@ -21,6 +22,7 @@ struct PerDeviceOnceMf {
     }
 };
 constexpr size_t kMaxSmem = 227 * 1024;
+constexpr int kTinyWarps = 2;       // warps per CTA for fronts with fp <= 48
 
 template <int NW>
 int launch_small(cudaStream_t st, const Tables& tb, const int* list, int n, int nsys, size_t smem) {
@@ -52,6 +54,15 @@ Solver* Solver::create(Symbolic&& S, int nsys, int maxRhs, int64_t valCount, int
 }
 
 Solver::~Solver() {
+    if (d_prof) {
+        unsigned long long h[8] = {};
+        cudaDeviceSynchronize();
+        cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost);
+        if (h[6])
+            fprintf(stderr, "[hmcmt_b200] mf_small_kernel phases, cycles per front (%llu fronts, %.2f pivot blocks each): zero %.0f  orig %.0f  children %.0f  "
+                    "mirror %.0f  sweep %.0f  output %.0f\n", h[6], (double)h[7] / h[6], (double)h[0] / h[6], (double)h[1] / h[6], (double)h[2] / h[6],
+                    (double)h[3] / h[6], (double)h[4] / h[6], (double)h[5] / h[6]);
+    }
     for (void* p : owned) cudaFree(p);
 }
 
@@ -79,6 +90,10 @@ int Solver::build(int nsys_, int maxRhs_, int64_t valCount_) {
     MF_TRY(dalloc((void**)&d_vals, (size_t)nsys * valCount * sizeof(cplx)));
     MF_TRY(dalloc((void**)&d_v, (size_t)nsys * maxRhs * S.Np * sizeof(cplx)));
     MF_TRY(dalloc((void**)&d_upd, (size_t)nsys * maxRhs * S.updEntries * sizeof(cplx)));
+    if (const char* e = std::getenv("HMCMT_MF_PROF"); e && std::atoi(e)) {
+        MF_TRY(dalloc((void**)&d_prof, 8 * sizeof(unsigned long long)));
+        cudaMemset(d_prof, 0, 8 * sizeof(unsigned long long));
+    }
 
     // launch schedule
     sched.assign(S.maxDepth + 1, DepthSchedule());
@@ -94,7 +109,8 @@ int Solver::build(int nsys_, int maxRhs_, int64_t valCount_) {
             int mx = 0;
             for (int k : sm) mx = std::max(mx, S.fronts[k].fp());
             D.smallSmem = mf_sweep_smem_bytes(mx / 8);
-            D.smallWarps = mx <= 64 ? 4 : (mx <= 104 ? 8 : 16);
+            const char* tw = std::getenv("HMCMT_MF_TINYWARPS");
+            D.smallWarps = mx <= 48 ? (tw ? std::atoi(tw) : kTinyWarps) : (mx <= 64 ? 4 : (mx <= 104 ? 8 : 16));
         }
         D.nBig = (int)bg.size();
         D.bigBytes = (size_t)S.bigDoublesAtDepth[d] * sizeof(double);
@@ -194,7 +210,7 @@ int Solver::factor(cudaStream_t st, int* dStatus, int64_t* nLaunches) {
     tb.fronts = d_fronts; tb.rows = d_rows; tb.rel = d_rel; tb.children = d_children; tb.orig = d_orig; tb.chunks = d_chunks;
     tb.pos2orig = d_pos2orig; tb.fac = d_fac; tb.arena[0] = d_arena[0]; tb.arena[1] = d_arena[1];
     tb.facStride = S.factorDoubles; tb.arenaStride[0] = S.arenaDoubles[0]; tb.arenaStride[1] = S.arenaDoubles[1];
-    tb.vals = d_vals; tb.valStride = valCount; tb.status = dStatus;
+    tb.vals = d_vals; tb.valStride = valCount; tb.status = dStatus; tb.prof = d_prof;
     static PerDeviceOnceMf once;
     if (once.need()) {
         HMCMT_CUDA_TRY(cudaFuncSetAttribute(mf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
@@ -206,7 +222,8 @@ int Solver::factor(cudaStream_t st, int* dStatus, int64_t* nLaunches) {
         const int par = d & 1;
         if (D.nSmall) {
             int rc = kOk;
-            if (D.smallWarps == 4) rc = launch_small<4>(st, tb, D.smallList, D.nSmall, nsys, D.smallSmem);
+            if (D.smallWarps == 2) rc = launch_small<2>(st, tb, D.smallList, D.nSmall, nsys, D.smallSmem);
+            else if (D.smallWarps == 4) rc = launch_small<4>(st, tb, D.smallList, D.nSmall, nsys, D.smallSmem);
             else if (D.smallWarps == 8) rc = launch_small<8>(st, tb, D.smallList, D.nSmall, nsys, D.smallSmem);
             else rc = launch_small<16>(st, tb, D.smallList, D.nSmall, nsys, D.smallSmem);
             if (rc) return rc;
@@ -252,7 +269,7 @@ int Solver::solve(cudaStream_t st, int nrhs, const cplx* B, int64_t ldb, cplx* X
     tb.fronts = d_fronts; tb.rows = d_rows; tb.rel = d_rel; tb.children = d_children; tb.orig = d_orig; tb.chunks = d_chunks;
     tb.pos2orig = d_pos2orig; tb.fac = d_fac; tb.arena[0] = d_arena[0]; tb.arena[1] = d_arena[1];
     tb.facStride = S.factorDoubles; tb.arenaStride[0] = S.arenaDoubles[0]; tb.arenaStride[1] = S.arenaDoubles[1];
-    tb.vals = d_vals; tb.valStride = valCount; tb.status = nullptr;
+    tb.vals = d_vals; tb.valStride = valCount; tb.status = nullptr; tb.prof = nullptr;
     SolveArgs sa{B, X, ldb, ldx, d_v, d_upd, (int64_t)S.Np, S.updEntries, nrhs};
     static PerDeviceOnceMf once;
     if (once.need()) {
@@ -263,15 +280,27 @@ int Solver::solve(cudaStream_t st, int nrhs, const cplx* B, int64_t ldb, cplx* X
     int64_t nl = 0;
     for (int d = S.maxDepth; d >= 0; --d) {
         const DepthSchedule& D = sched[d];
-        if (!D.nAll) continue;
-        mf_fwd_kernel<<<dim3(D.nAll, nvec), kSolveMfThreads, solveSmem, st>>>(tb, sa, D.allList);
-        ++nl;
+        if (D.nSmall) {
+            mf_fwd_warp_kernel<<<dim3((D.nSmall + kSolveWarpsPerCta - 1) / kSolveWarpsPerCta, nvec), kSolveWarpsPerCta * 32, 0, st>>>(
+                tb, sa, D.smallList, D.nSmall);
+            ++nl;
+        }
+        if (D.nBig) {
+            mf_fwd_kernel<<<dim3(D.nBig, nvec), kSolveMfThreads, solveSmem, st>>>(tb, sa, D.bigList);
+            ++nl;
+        }
     }
     for (int d = 0; d <= S.maxDepth; ++d) {
         const DepthSchedule& D = sched[d];
-        if (!D.nAll) continue;
-        mf_bwd_kernel<<<dim3(D.nAll, nvec), kSolveMfThreads, solveSmem, st>>>(tb, sa, D.allList);
-        ++nl;
+        if (D.nSmall) {
+            mf_bwd_warp_kernel<<<dim3((D.nSmall + kSolveWarpsPerCta - 1) / kSolveWarpsPerCta, nvec), kSolveWarpsPerCta * 32, 0, st>>>(
+                tb, sa, D.smallList, D.nSmall);
+            ++nl;
+        }
+        if (D.nBig) {
+            mf_bwd_kernel<<<dim3(D.nBig, nvec), kSolveMfThreads, solveSmem, st>>>(tb, sa, D.bigList);
+            ++nl;
+        }
     }
     HMCMT_CUDA_TRY(cudaGetLastError());
     if (nLaunches) *nLaunches += nl;

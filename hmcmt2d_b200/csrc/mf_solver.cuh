@@ -83,6 +83,7 @@ class Solver {
     double* d_arena[2] = {nullptr, nullptr};
     cplx *d_vals = nullptr, *d_v = nullptr, *d_upd = nullptr;
     size_t solveSmem = 0;
+    unsigned long long* d_prof = nullptr;      // HMCMT_MF_PROF=1: phase cycle counters of mf_small_kernel
 };
 
 }  // namespace mf

@@ -161,6 +161,19 @@ def stage_cfg4():
         traceback.print_exc()
 
 
+def stage_sweep():
+    for leaf in (8, 16, 24, 32, 48, 64):
+        os.environ["HMCMT_MF_LEAF"] = str(leaf)
+        try:
+            _, _, i4 = plan_eval(800, 300, 8, None, nrx=40, reps=3)
+            _, _, i2 = plan_eval(200, 100, 30, "mf", nrx=40, reps=5)
+            print(f"[sweep] leaf {leaf}: cfg4x16 {i4['eval_s'] * 1e3:.2f} ms (factor {i4['factor_MB']:.0f} MB, {i4['flops']:.3e} flop)   "
+                  f"cfg2-mf {i2['eval_s'] * 1e3:.2f} ms (factor {i2['factor_MB']:.1f} MB, {i2['flops']:.3e} flop)", flush=True)
+        except Exception:
+            traceback.print_exc()
+    os.environ.pop("HMCMT_MF_LEAF", None)
+
+
 if __name__ == "__main__":
     stages = sys.argv[1:] or ["shim", "plan_small", "cfg2", "cfg4"]
     for s in stages:
