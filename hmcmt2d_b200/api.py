@@ -73,6 +73,7 @@ class MT2DFwdData:
     AinvTE: object
     AinvTM: object
     linearSolver: str = "b200"
+    generation: int = -1        # evaluation counter of the plan when these fields / factors were produced
 
 
 def setActiveElement(sigma, sigFix, fixIndex=None):
@@ -135,6 +136,7 @@ class Plan:
             raise NotImplementedError("only DataType Impedance reaches the gradient in the reference "
                                       "('Rho_Pha' vs 'Rho_Phs', compJacTMatVec.jl:104)")
         self.L = _lib.load()
+        self.generation = 0
         ny, nz = mtMesh.gridSize
         self.ny, self.nz = int(ny), int(nz)
         self.nChains = int(nChains)
@@ -206,6 +208,7 @@ class Plan:
         return m
 
     def forward(self, m=None, sigma=None, fields=True):
+        self.generation = getattr(self, "generation", 0) + 1       # MT2DFwdData handles of earlier evaluations become stale
         pred = np.zeros((self.nChains, self.nData), dtype=np.complex128)
         ex = np.zeros((self.nChains, self.nFreq, self.nNode), dtype=np.complex128) if (fields and self.compTE) else None
         hx = np.zeros((self.nChains, self.nFreq, self.nNode), dtype=np.complex128) if (fields and self.compTM) else None
@@ -225,6 +228,7 @@ class Plan:
         return g
 
     def forward_gradient(self, m):
+        self.generation = getattr(self, "generation", 0) + 1
         mm = self._m(m)
         pred = np.zeros((self.nChains, self.nData), dtype=np.complex128)
         phi = np.zeros(self.nChains)
@@ -271,7 +275,11 @@ class Plan:
         _lib.check(self.L.hmcmt_kernel_time(self.h, int(reset), C.byref(ms), C.byref(n)), "hmcmt_kernel_time")
         return float(ms.value), int(n.value)
 
-    def run_chain(self, dt, nsamples, rhoref, z_init, intsteps, u_accept, z_mom, reuse_last_forward=True):
+    def status(self) -> int:
+        """Device error flags of everything queued so far (synchronises, clears): 0, -10 singular pivot, -21 bounds."""
+        return int(self.L.hmcmt_status(self.h))
+
+    def run_chain(self, dt, nsamples, rhoref, z_init, intsteps, u_accept, z_mom, reuse_last_forward=True, m_start=None):
         nc = self.nChains
         z_init = np.ascontiguousarray(z_init, dtype=np.float64).reshape(nc, self.nAC)
         intsteps = np.ascontiguousarray(intsteps, dtype=np.int32).reshape(nsamples)
@@ -281,7 +289,9 @@ class Plan:
         stats = np.zeros((nc, nsamples + 1, 4))
         acc = np.zeros((nc, nsamples), dtype=np.int32)
         data = np.zeros((nc, nsamples + 1, self.nData), dtype=np.complex128)
-        _lib.check(self.L.hmcmt_run_chain(self.h, float(dt), int(nsamples), float(rhoref), _lib.f64(z_init), _lib.i32(intsteps),
+        ms = None if m_start is None else np.ascontiguousarray(m_start, dtype=np.float64).reshape(nc, self.nAC)
+        _lib.check(self.L.hmcmt_run_chain(self.h, float(dt), int(nsamples), float(rhoref), None if ms is None else _lib.f64(ms),
+                                          _lib.f64(z_init), _lib.i32(intsteps),
                                           _lib.f64(u_accept), _lib.f64(z_mom), int(bool(reuse_last_forward)), _lib.f64(model),
                                           _lib.f64(stats), _lib.i32(acc), data.ctypes.data_as(C.POINTER(C.c_double))),
                    "hmcmt_run_chain")
@@ -419,13 +429,35 @@ def _plan_for(mtMesh, mtData, invParam, hmcprior, nChains=1, device=0) -> Plan:
 
 
 def _forward_only_plan(mtMesh, mtData, device=0) -> Plan:
+    """Plan without observations for `MT2DFwdSolver(mtMesh, mtData)`.  For "Rho_Pha" data the plan is built on the impedance
+    bookkeeping of the modes present (one component per mode, every (freq, rx) pair) and switched to apparent resistivity /
+    phase responses; the reference's interleaving and dataID mask are applied by the caller."""
     cache = mtData.__dict__.setdefault("_fwd_plans", {})
     key = (id(mtMesh), device)
     if key not in cache:
-        nData = int(np.count_nonzero(mtData.dataID))
+        md = mtData
+        if "Rho_Pha" in mtData.dataType:
+            comps = (["ZXY"] if mtData.compTE else []) + (["ZYX"] if mtData.compTM else [])
+            nF, nRx, nC = len(mtData.freqs), np.asarray(mtData.rxLoc).shape[0], len(comps)
+            f, r, c = np.meshgrid(np.arange(1, nF + 1), np.arange(1, nRx + 1), np.arange(1, nC + 1), indexing="ij")
+            md = MTData(np.asarray(mtData.rxLoc), np.asarray(mtData.freqs), "Impedance", comps, r.reshape(-1).astype(np.int64),
+                        f.reshape(-1).astype(np.int64), c.reshape(-1).astype(np.int64), np.ones(nF * nRx * nC, dtype=bool),
+                        mtData.compTE, mtData.compTM)
+        nData = int(np.count_nonzero(md.dataID))
         inv = setupInverseDataModel(mtMesh, [1e-8], 0.0, 0.0, np.zeros(nData, dtype=np.complex128), np.ones(nData))
-        cache[key] = Plan(mtMesh, mtData, inv, HMCPrior(), 1, device)
+        pl = Plan(mtMesh, md, inv, HMCPrior(), 1, device)
+        if "Rho_Pha" in mtData.dataType:
+            _lib.check(pl.L.hmcmt_set_response_kind(pl.h, 1), "hmcmt_set_response_kind")
+        cache[key] = pl
     return cache[key]
+
+
+class FactorHandle:
+    """What `MT2DFwdData.AinvTE / AinvTM` carry here: the device-resident plan that owns the factors, and the evaluation they
+    belong to (the reference stores one MUMPS handle per frequency, MT2DFwdSolver.jl:119-120)."""
+
+    def __init__(self, plan: Plan, generation: int):
+        self.plan, self.generation = plan, generation
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -433,27 +465,45 @@ def _forward_only_plan(mtMesh, mtData, device=0) -> Plan:
 
 
 def MT2DFwdSolver(mtMesh: TensorMesh2D, mtData: MTData, linearSolver: str = "b200", plan: Optional[Plan] = None):
-    """`MT2DFwdSolver(mtMesh, mtData; linearSolver)` (MT2DFwdSolver.jl:74-216) -> (predData, MT2DFwdData)."""
+    """`MT2DFwdSolver(mtMesh, mtData; linearSolver)` (MT2DFwdSolver.jl:74-216) -> (predData, MT2DFwdData).
+    DataType "Impedance": complex predData; "Rho_Pha": real [rho_a, phase] pairs interleaved per (freq, rx) as
+    MT2DFwdSolver.jl:191-205 does, masked by dataID."""
     pl = plan or _forward_only_plan(mtMesh, mtData)
     pred, ex, hx = pl.forward(sigma=np.asarray(mtMesh.sigma))
     nNode, nF = pl.nNode, pl.nFreq
     exte = ex[0].T.copy() if ex is not None else np.zeros((nNode, nF), dtype=np.complex128)
     hxtm = hx[0].T.copy() if hx is not None else np.zeros((nNode, nF), dtype=np.complex128)
-    return pred[0], MT2DFwdData(exte, hxtm, pl, pl, "b200")
+    h = FactorHandle(pl, pl.generation)
+    if "Rho_Pha" in mtData.dataType:
+        nC = int(pl.compTE) + int(pl.compTM)
+        out = np.zeros((pl.nChains, pl.nFreq, np.asarray(mtData.rxLoc).shape[0], nC, 2))
+        _lib.check(pl.L.hmcmt_get_responses(pl.h, _lib.f64(out)), "hmcmt_get_responses")
+        # per (freq, rx): [rhoTE, phsTE, rhoTM, phsTM]  (vec of vcat(transpose(respTE), transpose(respTM)), :199-203)
+        predData = out[0].reshape(-1)[np.asarray(mtData.dataID, dtype=bool)]
+        return predData, MT2DFwdData(exte, hxtm, h, h, "b200", pl.generation)
+    return pred[0], MT2DFwdData(exte, hxtm, h, h, "b200", pl.generation)
 
 
 def compJacTMatVec(exTE, hxTM, datVec, mt2dMesh, mtData, activeCell=None, AinvTE=None, AinvTM=None, linSolver: str = "b200"):
-    """`compJacTMatVec` (compJacTMatVec.jl:8-329): real(J^T v) over the active cells.  The fields and
-    factors live on the device inside the plan carried by AinvTE/AinvTM (as returned by MT2DFwdSolver)."""
-    pl = AinvTE if isinstance(AinvTE, Plan) else AinvTM
-    if not isinstance(pl, Plan):
+    """`compJacTMatVec` (compJacTMatVec.jl:8-329): real(J^T v) over the active cells.  The fields and factors live on the
+    device inside the plan carried by AinvTE/AinvTM (as returned by MT2DFwdSolver) and are reused for the adjoint solves
+    (compJacTMatVec.jl:220-224); a handle of an earlier evaluation of the same plan is refused instead of silently returning
+    the gradient at another model."""
+    h = AinvTE if isinstance(AinvTE, FactorHandle) else AinvTM
+    if not isinstance(h, FactorHandle):
         raise ValueError("compJacTMatVec needs the factor handle returned by MT2DFwdSolver (AinvTE/AinvTM)")
+    pl = h.plan
+    if h.generation != pl.generation:
+        raise RuntimeError("compJacTMatVec: the factors of this MT2DFwdData were overwritten by a later evaluation on the same "
+                           "mesh / survey; call MT2DFwdSolver again (one set of factors is kept resident per plan)")
+    if "Rho_Pha" in mtData.dataType:
+        raise NotImplementedError("the reference never forms sVec for 'Rho_Pha' data ('Rho_Phs', compJacTMatVec.jl:104,189,260)")
     g = pl.jtvec(datVec)[0]
-    if activeCell is not None and activeCell.shape[1] != pl.nAC:
-        # the plan's active set is 'all non-air cells'; restrict / expand to the caller's selector
+    if activeCell is not None:
+        # map by cell index, whatever the caller's selector looks like (the plan's active set is 'all non-air cells')
         full = np.zeros(pl.nCell)
         full[pl._keep["act"]] = g
-        return activeCell.T @ full
+        return np.asarray(activeCell.T @ full).reshape(-1)
     return g
 
 
@@ -521,10 +571,11 @@ def runHMCSampler(mtMesh, mtData, invParam: InvDataModel, hmcprior: HMCPrior, st
     rhoref = float(np.round(rho0 * 0.5 + (rho0 * 1.5 - rho0 * 0.5) * streams.u_start))
     print(f"Homogeneous starting model with a resistivity of {rhoref} Ωm is used.")
     start = np.log(np.ones(nparam) / rhoref)
+    m_file = np.array(invParam.strModel, dtype=np.float64)        # hmcParamCurrent.rhomodel = copy(invParam.strModel) (:87)
     invParam.strModel = start.copy()
     invParam.refModel = start.copy()
     model, stats, acc, data = pl.run_chain(hmcprior.dt, nsamples, rhoref, streams.z_init, streams.intsteps[:nsamples],
-                                           streams.u_accept[:nsamples], streams.z_momentum[:nsamples], reuse_last_forward)
+                                           streams.u_accept[:nsamples], streams.z_momentum[:nsamples], reuse_last_forward, m_start=m_file)
     hmcprior.nfevals += int(np.sum(streams.intsteps[:nsamples]) + nsamples)
     st = HMCStatus(int(acc[0].sum()), int(nsamples - acc[0].sum()), acc[0].astype(bool), stats[0].T.copy())
     return model[0].T.copy(), st, data[0].T.copy()
@@ -566,25 +617,40 @@ def outputHMCSamples(hmcmodel, hmcstats: HMCStatus, hmcdata, ichain: int = 1, cp
 
 
 def parallelHMCSampler(mtMesh, mtData, invParam, hmcprior, pids: List[int], seeds: Optional[List[int]] = None,
-                       nsamples: Optional[int] = None, outdir: Optional[str] = None):
-    """`parallelHMCSampler` (parallelHMC.jl:10-49): one independent chain per entry of `pids`.  Under
-    torchrun (one process per GPU) rank r runs chains r, r+world, ... on its own device with no data-path
-    communication (replicas only) and rank 0 gathers the samples; in a single process `pids` are CUDA
-    device ordinals used one after the other."""
+                       nsamples: Optional[int] = None, outdir: Optional[str] = "."):
+    """`parallelHMCSampler` (parallelHMC.jl:10-49): one independent chain per entry of `pids`; like the reference, the
+    hmcsamples_id*/hmcstatistics_id* files of every chain are written (to `outdir`, default the working directory,
+    parallelHMC.jl:41-45; None disables).  Under torchrun (one process per GPU) rank r runs chains r, r+world, ... on its
+    own device with no data-path communication (replicas only) and rank 0 gathers the samples.  In a single process the
+    chains run one after the other and `pids` — Julia worker ids in the reference (workers() starts at 2) — are mapped to
+    CUDA devices by POSITION: chain k runs on device k mod (number of visible devices)."""
     import copy
     import time
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
-    device = int(os.environ.get("LOCAL_RANK", "0")) if world > 1 else None
+    if world > 1:
+        import torch.distributed as dist
+        if not dist.is_available() or not dist.is_initialized():
+            raise RuntimeError("parallelHMCSampler: WORLD_SIZE > 1 but torch.distributed is not initialised "
+                               "(call torch.distributed.init_process_group first, e.g. under torchrun)")
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+        ndev = 1
+    else:
+        device = None
+        try:
+            import torch
+            ndev = max(1, torch.cuda.device_count())
+        except Exception:
+            ndev = 1
     seeds = seeds or list(range(1, len(pids) + 1))
     results = {}
-    for k, pid in enumerate(pids):
+    for k, _pid in enumerate(pids):
         if world > 1 and k % world != rank:
             continue
         inv_k, prior_k = copy.copy(invParam), copy.copy(hmcprior)
         inv_k.__dict__.pop("_plans", None)
         t0 = time.time()
         out = runHMCSampler(mtMesh, mtData, inv_k, prior_k, nsamples=nsamples, seed=seeds[k],
-                            device=device if device is not None else int(pid))
+                            device=device if device is not None else k % ndev)
         results[k] = (out, time.time() - t0)
     if world > 1:
         import torch.distributed as dist

@@ -17,6 +17,7 @@ enum Status : int {
     kErrAlloc = -13,
     kErrNotPosDef = -40,
     kErrArg = -3,
+    kErrBounds = -21,      // checkParameterBound!: a bound could not be met in 500 reflections (HMCSampler.jl:546-548)
     kErrCuda = -99,
     kErrNoDevice = -98,
 };

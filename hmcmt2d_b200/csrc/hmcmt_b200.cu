@@ -57,7 +57,8 @@ struct hmcmt_plan {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> factorEvents;
     size_t factorEventsUsed = 0;
     int64_t launches = 0, factorLaunches = 0;
-    bool haveForward = false, sigmaDirect = false, useMf = false, timeFactor = false;
+    bool haveForward = false, haveSens = false, sigmaDirect = false, useMf = false, timeFactor = false;
+    int respKind = 0;                               // 0 impedance, 1 apparent resistivity / phase (forward only)
     // host copies
     std::vector<double> h_yLen, h_zLen, h_freqs;
     std::vector<int> h_packed2full;      // [nData] full index (without chain) of each packed datum
@@ -65,7 +66,7 @@ struct hmcmt_plan {
     DevBuf<double> yLen, zLen, zNode, freqs, fdy1, fdy2, wL, wR, bg, wmVal, wd, m, p, mref, sigma, meanSig, planes;
     DevBuf<double> xbuf, Gpart, phiPart, phi, gsig, gdata, gtotal, energies, panels, curM, curP, chainScal, zmom;
     DevBuf<int> fid, iL, iR, cell2act, act2cell, wmPtr, wmIdx, status, driftFlag, packed2full, Lsteps;
-    DevBuf<cplx> obs, bc, bcs, rhs, x, F, lam, Lam, srows, qrow, scratch, predFull, ainvz, zadj, vin, predPacked, wexp, conCols;
+    DevBuf<cplx> obs, bc, bcs, rhs, x, F, lam, Lam, srows, qrow, scratch, predFull, ainvz, zadj, vin, predPacked, wexp, conCols, respFull;
     DevBuf<BandSys> sysDesc;
     DevBuf<SolveJob> jobs, fwdJobs;                 // fwdJobs: back-substitution sweeps of the fused forward systems (split systems)
     // wide meshes (half-bandwidth > 104): nested-dissection multifrontal solver (mf_solver.cuh) instead of the band kernels
@@ -319,12 +320,28 @@ int ensure_pin(hmcmt_plan* pl, size_t bytes) {
     return kOk;
 }
 
-// One evaluation of the hot path for the device-resident model pl->m:
-//   forward (all chains x modes x freqs) [+ adjoint gradient + prior gradient].
-int compute_step(hmcmt_plan* pl, bool wantAdjoint, const cplx* vin) {
+// layered-earth sensitivity scalars (depend on sigma only) on the side stream: they overlap the factorisation and are joined
+// before the contraction
+int launch_sens_side(hmcmt_plan* pl) {
+    const MeshDev& M = pl->M;
+    HMCMT_CUDA_TRY(cudaEventRecord(pl->evFork, pl->stream));
+    HMCMT_CUDA_TRY(cudaStreamWaitEvent(pl->side, pl->evFork, 0));
+    k_row_mean<<<dim3(M.nz, pl->nChains), 128, 0, pl->side>>>(M.ny, M.nz, pl->sigma.p, pl->meanSig.p);
+    LAUNCH_CHECK(pl);
+    k_sens_scalars<<<(pl->nSys * 3 + 63) / 64, 64, 0, pl->side>>>(M, pl->sm, pl->nSys, pl->freqs.p, pl->sigma.p, pl->meanSig.p, pl->scratch.p, pl->bcs.p);
+    LAUNCH_CHECK(pl);
+    HMCMT_CUDA_TRY(cudaEventRecord(pl->evJoin, pl->side));
+    pl->haveSens = true;
+    return kOk;
+}
+
+// forward part: sigma, stencil, boundary values, right-hand sides, factorisation + forward solve, node-ordered fields
+int forward_phase(hmcmt_plan* pl, bool wantAdjoint) {
     const MeshDev& M = pl->M;
     cudaStream_t st = pl->stream;
     const int nSys = pl->nSys, nCh = pl->nChains;
+    pl->haveForward = false;
+    pl->haveSens = false;
     if (!pl->sigmaDirect) {
         k_model_transform<<<dim3((M.nCell + 255) / 256, nCh), 256, 0, st>>>(M.nCell, pl->nAC, pl->cell2act.p, pl->bg.p, pl->m.p, pl->sigma.p);
         LAUNCH_CHECK(pl);
@@ -342,15 +359,8 @@ int compute_step(hmcmt_plan* pl, bool wantAdjoint, const cplx* vin) {
     k_rhs<<<dim3((M.N + 255) / 256, nSys), 256, 0, st>>>(M, pl->sm, pl->sigma.p, pl->bc.p, pl->rhs.p);
     LAUNCH_CHECK(pl);
     if (wantAdjoint) {
-        // the layered-earth sensitivity scalars depend on sigma only: run them on the side stream, on the SMs the
-        // 60-CTA factorisation leaves idle, and join before the contraction
-        HMCMT_CUDA_TRY(cudaEventRecord(pl->evFork, st));
-        HMCMT_CUDA_TRY(cudaStreamWaitEvent(pl->side, pl->evFork, 0));
-        k_row_mean<<<dim3(M.nz, nCh), 128, 0, pl->side>>>(M.ny, M.nz, pl->sigma.p, pl->meanSig.p);
-        LAUNCH_CHECK(pl);
-        k_sens_scalars<<<(nSys * 3 + 63) / 64, 64, 0, pl->side>>>(M, pl->sm, nSys, pl->freqs.p, pl->sigma.p, pl->meanSig.p, pl->scratch.p, pl->bcs.p);
-        LAUNCH_CHECK(pl);
-        HMCMT_CUDA_TRY(cudaEventRecord(pl->evJoin, pl->side));
+        int rc = launch_sens_side(pl);
+        if (rc) return rc;
     }
     // factorisation + forward solve (timed with CUDA events only when the caller asked for it: hmcmt_kernel_time(reset=1))
     {
@@ -384,14 +394,31 @@ int compute_step(hmcmt_plan* pl, bool wantAdjoint, const cplx* vin) {
     }
     k_node_field<<<dim3((M.nNode + 255) / 256, nSys), 256, 0, st>>>(M, pl->x.p, pl->bc.p, pl->F.p);
     LAUNCH_CHECK(pl);
-    size_t rxSmem = (size_t)(6 * (M.ny + 1) + 3 * M.ny) * sizeof(cplx);
-    k_rx_adjoint<<<nSys, kRxThreads, rxSmem, st>>>(M, pl->rx, pl->sm, pl->freqs.p, pl->sigma.p, pl->F.p, pl->obs.p, pl->wd.p, vin,
-                                                   pl->predFull.p, pl->phiPart.p, pl->srows.p, pl->qrow.p, pl->lam.p, wantAdjoint ? 1 : 0);
-    LAUNCH_CHECK(pl);
-    k_reduce_phi<<<nCh, 32, 0, st>>>(pl->nSysPerChain, pl->phiPart.p, pl->phi.p);
-    LAUNCH_CHECK(pl);
     pl->haveForward = true;
-    if (!wantAdjoint) return kOk;
+    return kOk;
+}
+
+// receiver functional: responses, residual, misfit partial and (wantAdjoint) the adjoint sources for the data vector vin
+// (null: v = Wd^2 (pred - obs))
+int rx_phase(hmcmt_plan* pl, bool wantAdjoint, const cplx* vin) {
+    const MeshDev& M = pl->M;
+    cudaStream_t st = pl->stream;
+    size_t rxSmem = (size_t)(6 * (M.ny + 1) + 3 * M.ny) * sizeof(cplx);
+    k_rx_adjoint<<<pl->nSys, kRxThreads, rxSmem, st>>>(M, pl->rx, pl->sm, pl->freqs.p, pl->sigma.p, pl->F.p, pl->obs.p, pl->wd.p, vin,
+                                                       pl->predFull.p, pl->phiPart.p, pl->srows.p, pl->qrow.p, pl->lam.p, wantAdjoint ? 1 : 0,
+                                                       pl->respKind, pl->respFull.p);
+    LAUNCH_CHECK(pl);
+    k_reduce_phi<<<pl->nChains, 32, 0, st>>>(pl->nSysPerChain, pl->phiPart.p, pl->phi.p);
+    LAUNCH_CHECK(pl);
+    return kOk;
+}
+
+// adjoint part: one solve per system with the factors of the forward phase (A symmetric: no transposition,
+// compJacTMatVec.jl:220-224), contraction into the gradient, prior gradient
+int adjoint_phase(hmcmt_plan* pl) {
+    const MeshDev& M = pl->M;
+    cudaStream_t st = pl->stream;
+    const int nSys = pl->nSys, nCh = pl->nChains;
     int rc;                                                            // lam <- A^{-1} s[ii]  (in place)
     if (pl->useMf) rc = pl->mfs->solve(st, 1, pl->lam.p, M.N, pl->lam.p, M.N, &pl->launches);
     else {
@@ -415,11 +442,32 @@ int compute_step(hmcmt_plan* pl, bool wantAdjoint, const cplx* vin) {
     return kOk;
 }
 
+// One evaluation of the hot path for the device-resident model pl->m:
+//   forward (all chains x modes x freqs) [+ adjoint gradient + prior gradient].
+int compute_step(hmcmt_plan* pl, bool wantAdjoint, const cplx* vin) {
+    int rc = forward_phase(pl, wantAdjoint);
+    if (rc) return rc;
+    rc = rx_phase(pl, wantAdjoint, vin);
+    if (rc || !wantAdjoint) return rc;
+    return adjoint_phase(pl);
+}
+
+// Device error flags of the work queued so far (synchronises).  The flags are cleared after reading, so a failure is reported
+// once, by the call that caused it, and does not poison later evaluations of the (cached) plan.
 int check_status(hmcmt_plan* pl) {
     std::vector<int> h(pl->nSys);
-    HMCMT_CUDA_TRY(cudaMemcpy(h.data(), pl->status.p, sizeof(int) * pl->nSys, cudaMemcpyDeviceToHost));
-    for (int v : h) if (v) return v;
-    return kOk;
+    int drift = 0;
+    HMCMT_CUDA_TRY(cudaMemcpyAsync(h.data(), pl->status.p, sizeof(int) * pl->nSys, cudaMemcpyDeviceToHost, pl->stream));
+    HMCMT_CUDA_TRY(cudaMemcpyAsync(&drift, pl->driftFlag.p, sizeof(int), cudaMemcpyDeviceToHost, pl->stream));
+    HMCMT_CUDA_TRY(cudaStreamSynchronize(pl->stream));
+    int rc = kOk;
+    for (int v : h) if (v) { rc = v; break; }
+    if (rc == kOk && drift) rc = kErrBounds;
+    if (rc != kOk) {
+        HMCMT_CUDA_TRY(cudaMemsetAsync(pl->status.p, 0, sizeof(int) * pl->nSys, pl->stream));
+        HMCMT_CUDA_TRY(cudaMemsetAsync(pl->driftFlag.p, 0, sizeof(int), pl->stream));
+    }
+    return rc;
 }
 
 int drift(hmcmt_plan* pl, double dt) {
@@ -564,7 +612,7 @@ int hmcmt_plan_create(const hmcmt_problem* pr, hmcmt_plan** out) {
     ok(pl->Gpart.alloc(nSys * M.nCell)); ok(pl->phiPart.alloc(nSys)); ok(pl->phi.alloc(nCh));
     ok(pl->gsig.alloc(nCh * pr->nAC)); ok(pl->gdata.alloc(nCh * pr->nAC)); ok(pl->gtotal.alloc(nCh * pr->nAC)); ok(pl->xbuf.alloc((size_t)nCh * (pl->nAC + 1))); ok(pl->energies.alloc(nCh * 2));
     ok(pl->chainScal.alloc(nCh * 4));
-    ok(pl->predFull.alloc(nCh * pl->nFull)); ok(pl->vin.alloc(nCh * pl->nFull)); ok(pl->predPacked.alloc(nCh * pr->nData));
+    ok(pl->predFull.alloc(nCh * pl->nFull)); ok(pl->respFull.alloc(nCh * pl->nFull)); ok(pl->vin.alloc(nCh * pl->nFull)); ok(pl->predPacked.alloc(nCh * pr->nData));
     ok(pl->panels.alloc(nSys * (size_t)pl->S * panel_doubles(pl->T)));
     ok(pl->ainvz.alloc(nSys * (size_t)pl->S * AZ)); ok(pl->zadj.alloc(nSys * (size_t)pl->S * 8));
     const size_t wexpN = split_scratch_entries(TS * pl->T);
@@ -686,7 +734,7 @@ void hmcmt_destroy(hmcmt_plan* pl) {
     pl->driftFlag.release(); pl->packed2full.release(); pl->Lsteps.release(); pl->obs.release(); pl->bc.release(); pl->bcs.release();
     pl->rhs.release(); pl->x.release(); pl->F.release(); pl->lam.release(); pl->Lam.release(); pl->srows.release(); pl->qrow.release();
     pl->scratch.release(); pl->predFull.release(); pl->ainvz.release(); pl->zadj.release(); pl->vin.release();
-    pl->predPacked.release(); pl->conCols.release(); pl->xbuf.release(); pl->wexp.release(); pl->mfSys.release(); delete pl->mfs; pl->mfs = nullptr; pl->fwdJobs.release(); pl->sysDesc.release(); pl->jobs.release();
+    pl->predPacked.release(); pl->conCols.release(); pl->xbuf.release(); pl->wexp.release(); pl->respFull.release(); pl->mfSys.release(); delete pl->mfs; pl->mfs = nullptr; pl->fwdJobs.release(); pl->sysDesc.release(); pl->jobs.release();
     if (pl->pin) cudaFreeHost(pl->pin);
     delete pl;
 }
@@ -714,6 +762,24 @@ int64_t hmcmt_plan_info(const hmcmt_plan* pl, int what) {
 
 int hmcmt_sync(hmcmt_plan* pl) {
     if (!pl) return kErrArg;
+    HMCMT_CUDA_TRY(cudaStreamSynchronize(pl->stream));
+    return kOk;
+}
+int hmcmt_status(hmcmt_plan* pl) {
+    if (!pl) return kErrArg;
+    HMCMT_CUDA_TRY(cudaSetDevice(pl->device));
+    return check_status(pl);
+}
+int hmcmt_set_response_kind(hmcmt_plan* pl, int32_t kind) {
+    if (!pl || kind < 0 || kind > 1) return kErrArg;
+    pl->respKind = kind;
+    return kOk;
+}
+int hmcmt_get_responses(hmcmt_plan* pl, double* out) {
+    if (!pl || !out || !pl->haveForward) return kErrArg;
+    HMCMT_CUDA_TRY(cudaSetDevice(pl->device));
+    const cplx* src = pl->respKind == 1 ? pl->respFull.p : pl->predFull.p;
+    HMCMT_CUDA_TRY(cudaMemcpyAsync(out, src, sizeof(cplx) * (size_t)pl->nChains * pl->nFull, cudaMemcpyDeviceToHost, pl->stream));
     HMCMT_CUDA_TRY(cudaStreamSynchronize(pl->stream));
     return kOk;
 }
@@ -808,8 +874,14 @@ int hmcmt_jtvec(hmcmt_plan* pl, const double* v, double* gsig) {
             full[(size_t)ch * pl->nFull + pl->h_packed2full[i]] = mk(v[2 * ((size_t)ch * pl->nData + i)], v[2 * ((size_t)ch * pl->nData + i) + 1]);
     HMCMT_CUDA_TRY(cudaMemcpyAsync(pl->vin.p, full.data(), sizeof(cplx) * full.size(), cudaMemcpyHostToDevice, pl->stream));
     HMCMT_CUDA_TRY(cudaStreamSynchronize(pl->stream));
-    // re-evaluates the forward for the resident model (same factors) and contracts with the supplied v
-    int rc = compute_step(pl, true, pl->vin.p);
+    // the factors, fields and boundary values of the last forward evaluation are still on the device (the reference's AinvTE /
+    // AinvTM, compJacTMatVec.jl:220-224): only the adjoint sources for v, one solve per system and the contraction run here
+    int rc = kOk;
+    if (!pl->haveSens) rc = launch_sens_side(pl);
+    if (rc) return rc;
+    rc = rx_phase(pl, true, pl->vin.p);
+    if (rc) return rc;
+    rc = adjoint_phase(pl);
     if (rc) return rc;
     HMCMT_CUDA_TRY(cudaMemcpyAsync(gsig, pl->gsig.p, sizeof(double) * (size_t)pl->nChains * pl->nAC, cudaMemcpyDeviceToHost, pl->stream));
     HMCMT_CUDA_TRY(cudaStreamSynchronize(pl->stream));
@@ -852,12 +924,12 @@ int hmcmt_get_state(hmcmt_plan* pl, double* m, double* p) {
     return kOk;
 }
 
-static int trajectory_device(hmcmt_plan* pl, double dt, int Lmax) {
-    // proposeLeapfrog HMCSampler.jl:206-269 (per-chain step counts in pl->Lsteps)
+static int trajectory_device(hmcmt_plan* pl, double dt, int Lmax, const int* dL) {
+    // proposeLeapfrog HMCSampler.jl:206-269 (per-chain step counts in dL, device memory)
     dim3 g((pl->nAC + 255) / 256, pl->nChains);
     int rc = compute_step(pl, true, nullptr);
     if (rc) return rc;
-    k_kick_masked<<<g, 256, 0, pl->stream>>>(pl->nAC, dt, 0, pl->Lsteps.p, pl->gtotal.p, pl->p.p);
+    k_kick_masked<<<g, 256, 0, pl->stream>>>(pl->nAC, dt, 0, dL, pl->gtotal.p, pl->p.p);
     LAUNCH_CHECK(pl);
     for (int k = 1; k <= Lmax; ++k) {
         // chains that already finished (k > L) are frozen by a zero drift: handled through dt masking below
@@ -865,7 +937,7 @@ static int trajectory_device(hmcmt_plan* pl, double dt, int Lmax) {
         LAUNCH_CHECK(pl);
         rc = compute_step(pl, true, nullptr);
         if (rc) return rc;
-        k_kick_masked<<<g, 256, 0, pl->stream>>>(pl->nAC, dt, k, pl->Lsteps.p, pl->gtotal.p, pl->p.p);
+        k_kick_masked<<<g, 256, 0, pl->stream>>>(pl->nAC, dt, k, dL, pl->gtotal.p, pl->p.p);
         LAUNCH_CHECK(pl);
     }
     return kOk;
@@ -885,7 +957,7 @@ int hmcmt_leapfrog_trajectory(hmcmt_plan* pl, double dt, const int32_t* intstep,
     std::vector<int> L(intstep, intstep + pl->nChains);
     HMCMT_CUDA_TRY(cudaMemcpyAsync(pl->Lsteps.p, L.data(), sizeof(int) * pl->nChains, cudaMemcpyHostToDevice, pl->stream));
     HMCMT_CUDA_TRY(cudaStreamSynchronize(pl->stream));
-    int rc = trajectory_device(pl, dt, Lmax);
+    int rc = trajectory_device(pl, dt, Lmax, pl->Lsteps.p);
     if (rc) return rc;
     k_energies<<<pl->nChains, kHmcThreads, 0, pl->stream>>>(pl->nAC, pl->m.p, pl->mref.p, pl->p.p, pl->wmPtr.p, pl->wmIdx.p, pl->wmVal.p,
                                                             pl->beta, pl->energies.p);
@@ -950,37 +1022,59 @@ int hmcmt_step_finish(hmcmt_plan* pl, double dt) {
     return kOk;
 }
 
-int hmcmt_run_chain(hmcmt_plan* pl, double dt, int32_t nsamples, double rhoref, const double* z_init, const int32_t* intsteps,
-                    const double* u_accept, const double* z_mom, int32_t reuse_last_forward, double* hmcmodel, double* hmstats,
-                    int32_t* accept, double* hmcdata) {
+int hmcmt_run_chain(hmcmt_plan* pl, double dt, int32_t nsamples, double rhoref, const double* m_start, const double* z_init,
+                    const int32_t* intsteps, const double* u_accept, const double* z_mom, int32_t reuse_last_forward, double* hmcmodel,
+                    double* hmstats, int32_t* accept, double* hmcdata) {
     // rhoref = round(unirandDouble(0.5 rho0, 1.5 rho0)), rho0 = 1/exp(strModel[1]) (HMCSampler.jl:100-105), drawn by the caller.
     if (!pl || nsamples < 1 || !z_init || !intsteps || !u_accept || !z_mom) return kErrArg;
     HMCMT_CUDA_TRY(cudaSetDevice(pl->device));
     const int nCh = pl->nChains, nAC = pl->nAC, nData = pl->nData;
+    const size_t nState = (size_t)nCh * nAC;
     cudaStream_t st = pl->stream;
     pl->sigmaDirect = false;
-    DevBuf<double> dModel, dStats, dUacc;
-    DevBuf<int> dAcc;
+    // momentum draws travel in chunks through a two-slot device ring filled by a copy stream, so the sampling loop never
+    // synchronises the compute stream with the host; everything else is uploaded once
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)nsamples, ((size_t)64 << 20) / (nState * sizeof(double))));
+    DevBuf<double> dModel, dStats, dUacc, dZ;
+    DevBuf<int> dAcc, dL;
     DevBuf<cplx> dData;
+    cudaStream_t copy = nullptr;
+    cudaEvent_t evCopied[2] = {nullptr, nullptr}, evFree[2] = {nullptr, nullptr};
     int rc = kOk;
     auto ok = [&](int r) { if (r && !rc) rc = r; };
     ok(dModel.alloc((size_t)nCh * nsamples * nAC)); ok(dStats.alloc((size_t)nCh * (nsamples + 1) * 4));
     ok(dUacc.upload(u_accept, (size_t)nCh * nsamples)); ok(dAcc.alloc((size_t)nCh * nsamples));
     ok(dData.alloc((size_t)nCh * (nsamples + 1) * nData));
-    auto cleanup = [&]() { dModel.release(); dStats.release(); dUacc.release(); dAcc.release(); dData.release(); };
+    ok(dZ.alloc(2 * (size_t)chunk * nState));
+    {
+        std::vector<int> Lall((size_t)nsamples * nCh);
+        for (int it = 0; it < nsamples; ++it)
+            for (int ch = 0; ch < nCh; ++ch) Lall[(size_t)it * nCh + ch] = intsteps[it];
+        ok(dL.upload(Lall.data(), Lall.size()));
+    }
+    auto cleanup = [&]() {
+        cudaStreamSynchronize(st);
+        if (copy) { cudaStreamSynchronize(copy); cudaStreamDestroy(copy); }
+        for (int q = 0; q < 2; ++q) { if (evCopied[q]) cudaEventDestroy(evCopied[q]); if (evFree[q]) cudaEventDestroy(evFree[q]); }
+        dModel.release(); dStats.release(); dUacc.release(); dAcc.release(); dData.release(); dZ.release(); dL.release();
+    };
     if (rc) { cleanup(); return rc; }
     dim3 g((nAC + 255) / 256, nCh);
 #define RC_TRY(x) do { int _r = (x); if (_r) { cleanup(); return _r; } } while (0)
 #define RC_CUDA(x) do { if ((x) != cudaSuccess) { cleanup(); return kErrCuda; } } while (0)
-    // start model: homogeneous rhoref (HMCSampler.jl:100-109), m = mref = log(1/rhoref)
+    RC_CUDA(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
+    for (int q = 0; q < 2; ++q) {
+        RC_CUDA(cudaEventCreateWithFlags(&evCopied[q], cudaEventDisableTiming));
+        RC_CUDA(cudaEventCreateWithFlags(&evFree[q], cudaEventDisableTiming));
+    }
+    // homogeneous rhoref model (HMCSampler.jl:100-109): invParam.strModel = invParam.refModel = log(1/rhoref)
     double mstart = std::log(1.0 / rhoref);
-    k_fill<<<(unsigned)(((size_t)nCh * nAC + 255) / 256), 256, 0, st>>>((size_t)nCh * nAC, mstart, pl->m.p);
-    k_fill<<<(unsigned)(((size_t)nCh * nAC + 255) / 256), 256, 0, st>>>((size_t)nCh * nAC, mstart, pl->mref.p);
-    RC_CUDA(cudaMemcpyAsync(pl->curM.p, pl->m.p, sizeof(double) * (size_t)nCh * nAC, cudaMemcpyDeviceToDevice, st));
-    RC_CUDA(cudaMemcpyAsync(pl->zmom.p, z_init, sizeof(double) * (size_t)nCh * nAC, cudaMemcpyHostToDevice, st));
+    k_fill<<<(unsigned)((nState + 255) / 256), 256, 0, st>>>(nState, mstart, pl->m.p);
+    k_fill<<<(unsigned)((nState + 255) / 256), 256, 0, st>>>(nState, mstart, pl->mref.p);
+    RC_CUDA(cudaMemcpyAsync(pl->zmom.p, z_init, sizeof(double) * nState, cudaMemcpyHostToDevice, st));
     k_clip_momentum<<<g, 256, 0, st>>>(nAC, pl->zmom.p, pl->p.p);
     pl->launches += 3;
-    // Hamiltonian at the start (getHamiltonian HMCSampler.jl:113-115)
+    // Hamiltonian at the start (getHamiltonian HMCSampler.jl:113-115): forward for the homogeneous model, mnorm = 0
     RC_TRY(compute_step(pl, false, nullptr));
     k_energies<<<nCh, kHmcThreads, 0, st>>>(nAC, pl->m.p, pl->mref.p, pl->p.p, pl->wmPtr.p, pl->wmIdx.p, pl->wmVal.p, pl->beta, pl->energies.p);
     k_pack_pred<<<dim3((nData + 255) / 256, nCh), 256, 0, st>>>(nData, pl->nFull, pl->packed2full.p, pl->predFull.p, pl->predPacked.p);
@@ -998,23 +1092,39 @@ int hmcmt_run_chain(hmcmt_plan* pl, double dt, int32_t nsamples, double rhoref, 
                                     sizeof(cplx) * nData, cudaMemcpyDeviceToDevice, st));
         }
         RC_CUDA(cudaMemcpyAsync(pl->chainScal.p, sc.data(), sizeof(double) * sc.size(), cudaMemcpyHostToDevice, st));
+        // the first trajectory starts from hmcParamCurrent.rhomodel = the model-file strModel, copied BEFORE strModel / refModel
+        // were replaced by the homogeneous model (HMCSampler.jl:87 vs :100-109); m_start == NULL keeps the homogeneous model
+        if (m_start) RC_CUDA(cudaMemcpyAsync(pl->m.p, m_start, sizeof(double) * nState, cudaMemcpyHostToDevice, st));
+        RC_CUDA(cudaMemcpyAsync(pl->curM.p, pl->m.p, sizeof(double) * nState, cudaMemcpyDeviceToDevice, st));
         RC_CUDA(cudaStreamSynchronize(st));
     }
+    auto stage_chunk = [&](int c) -> int {           // z_mom layout: [sample][chain][nAC]
+        const int slot = c & 1, first = c * chunk, cnt = std::min(chunk, nsamples - first);
+        if (c >= 2 && cudaStreamWaitEvent(copy, evFree[slot], 0) != cudaSuccess) return kErrCuda;
+        if (cudaMemcpyAsync(dZ.p + (size_t)slot * chunk * nState, z_mom + (size_t)first * nState, sizeof(double) * (size_t)cnt * nState,
+                            cudaMemcpyHostToDevice, copy) != cudaSuccess || cudaEventRecord(evCopied[slot], copy) != cudaSuccess)
+            return kErrCuda;
+        return kOk;
+    };
+    const int nChunks = (nsamples + chunk - 1) / chunk;
+    RC_TRY(stage_chunk(0));
     for (int it = 1; it <= nsamples; ++it) {
-        int L = intsteps[it - 1];
-        std::vector<int> Lv(nCh, L);
-        RC_CUDA(cudaMemcpyAsync(pl->Lsteps.p, Lv.data(), sizeof(int) * nCh, cudaMemcpyHostToDevice, st));
-        RC_CUDA(cudaStreamSynchronize(st));
-        RC_TRY(trajectory_device(pl, dt, L));
+        const int c = (it - 1) / chunk, slot = c & 1, inChunk = (it - 1) % chunk;
+        if (inChunk == 0) {
+            RC_CUDA(cudaStreamWaitEvent(st, evCopied[slot], 0));
+            if (c + 1 < nChunks) RC_TRY(stage_chunk(c + 1));          // the next chunk travels while this one is sampled
+        }
+        const int L = intsteps[it - 1];
+        RC_TRY(trajectory_device(pl, dt, L, dL.p + (size_t)(it - 1) * nCh));
         if (!reuse_last_forward) RC_TRY(compute_step(pl, false, nullptr));       // the reference's redundant forward sweep
         k_energies<<<nCh, kHmcThreads, 0, st>>>(nAC, pl->m.p, pl->mref.p, pl->p.p, pl->wmPtr.p, pl->wmIdx.p, pl->wmVal.p, pl->beta, pl->energies.p);
         k_pack_pred<<<dim3((nData + 255) / 256, nCh), 256, 0, st>>>(nData, pl->nFull, pl->packed2full.p, pl->predFull.p, pl->predPacked.p);
-        // z_mom layout: [sample][chain][nAC]
-        RC_CUDA(cudaMemcpyAsync(pl->zmom.p, z_mom + (size_t)(it - 1) * nCh * nAC, sizeof(double) * (size_t)nCh * nAC, cudaMemcpyHostToDevice, st));
-        k_accept<<<nCh, kHmcThreads, 0, st>>>(nAC, nData, it, nsamples, dUacc.p, pl->phi.p, pl->energies.p, pl->zmom.p, pl->m.p, pl->p.p,
+        const double* zsrc = dZ.p + ((size_t)slot * chunk + inChunk) * nState;
+        k_accept<<<nCh, kHmcThreads, 0, st>>>(nAC, nData, it, nsamples, dUacc.p, pl->phi.p, pl->energies.p, zsrc, pl->m.p, pl->p.p,
                                               pl->curM.p, pl->chainScal.p, pl->predPacked.p, dModel.p, dStats.p, dAcc.p, dData.p);
         pl->launches += 3;
         if (cudaGetLastError() != cudaSuccess) { cleanup(); return kErrCuda; }
+        if (inChunk == chunk - 1 || it == nsamples) RC_CUDA(cudaEventRecord(evFree[slot], st));
     }
     RC_CUDA(cudaMemcpyAsync(hmcmodel, dModel.p, sizeof(double) * dModel.n, cudaMemcpyDeviceToHost, st));
     RC_CUDA(cudaMemcpyAsync(hmstats, dStats.p, sizeof(double) * dStats.n, cudaMemcpyDeviceToHost, st));

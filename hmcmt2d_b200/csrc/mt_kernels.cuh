@@ -291,7 +291,8 @@ __global__ void __launch_bounds__(kRxThreads)
 k_rx_adjoint(MeshDev M, RxDev rx, SysMap sm, const double* __restrict__ freqs, const double* __restrict__ sigma,
              const cplx* __restrict__ F, const cplx* __restrict__ obs, const double* __restrict__ wd,
              const cplx* __restrict__ vin, cplx* __restrict__ pred, double* __restrict__ phiPart,
-             cplx* __restrict__ srows, cplx* __restrict__ qrow, cplx* __restrict__ adjrhs, int wantAdjoint) {
+             cplx* __restrict__ srows, cplx* __restrict__ qrow, cplx* __restrict__ adjrhs, int wantAdjoint, int respKind,
+             cplx* __restrict__ resp) {
     extern __shared__ __align__(16) unsigned char smraw[];
     const int ny = M.ny;
     cplx* F0 = reinterpret_cast<cplx*>(smraw);        // ny+1
@@ -365,6 +366,8 @@ k_rx_adjoint(MeshDev M, RxDev rx, SysMap sm, const double* __restrict__ freqs, c
             cplx Z = numF / denF;
             size_t di = (((size_t)ch * nFreq + f) * rx.nRx + r) * sm.nModes + mi;
             pred[di] = Z;
+            // apparent resistivity and phase (compMTRespTE mt2DTE.jl:253-256, compMTRespTM mt2DTM.jl:236-239): forward only
+            if (respKind == 1) resp[di] = mk(cabs2(Z) / (omega * kMu0), atan2(Z.y, Z.x) * 180.0 / kPi);
             size_t dob = ((size_t)f * rx.nRx + r) * sm.nModes + mi;     // obs / weights are shared by all chains
             double w = wd[dob];
             cplx res = w * (Z - obs[dob]);

@@ -19,7 +19,7 @@ class HmcmtError(RuntimeError):
     """Raised for negative status codes (MUMPS convention, MUMPSfuncs.jl:59-73)."""
 
     MESSAGES = {-10: "numerically singular matrix", -13: "memory allocation error", -40: "matrix is not positive definite",
-                -3: "bad argument", -98: "no CUDA device (there is no CPU fallback)", -99: "CUDA error"}
+                -3: "bad argument", -21: "a parameter bound could not be met within 500 reflections", -98: "no CUDA device (there is no CPU fallback)", -99: "CUDA error"}
 
     def __init__(self, code: int, where: str):
         self.code = code
@@ -59,7 +59,11 @@ def load() -> C.CDLL:
     lib.hmcmt_plan_info.argtypes = [vp, C.c_int]
     lib.hmcmt_plan_info.restype = C.c_int64
     lib.hmcmt_forward.argtypes = [vp, _f64p, _f64p, _f64p, _f64p]
+    lib.hmcmt_forward_sigma.argtypes = [vp, _f64p, _f64p, _f64p, _f64p]
     lib.hmcmt_jtvec.argtypes = [vp, _f64p, _f64p]
+    lib.hmcmt_status.argtypes = [vp]
+    lib.hmcmt_set_response_kind.argtypes = [vp, C.c_int32]
+    lib.hmcmt_get_responses.argtypes = [vp, _f64p]
     lib.hmcmt_forward_gradient.argtypes = [vp, _f64p, _f64p, _f64p, _f64p]
     lib.hmcmt_set_state.argtypes = [vp, _f64p, _f64p, _f64p]
     lib.hmcmt_get_state.argtypes = [vp, _f64p, _f64p]
@@ -72,7 +76,7 @@ def load() -> C.CDLL:
     lib.hmcmt_timer_start.argtypes = [vp]
     lib.hmcmt_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
     lib.hmcmt_kernel_time.argtypes = [vp, C.c_int, C.POINTER(C.c_float), _i64p]
-    lib.hmcmt_run_chain.argtypes = [vp, C.c_double, C.c_int32, C.c_double, _f64p, _i32p, _f64p, _f64p, C.c_int32,
+    lib.hmcmt_run_chain.argtypes = [vp, C.c_double, C.c_int32, C.c_double, _f64p, _f64p, _i32p, _f64p, _f64p, C.c_int32,
                                     _f64p, _f64p, _i32p, _f64p]
     lib.hmcmt_export_system.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, _i64p, _i64p, _f64p, _f64p, _f64p]
     for name in ("factor_mumps_cmplx_", "factor_mumps_"):
@@ -98,7 +102,8 @@ def load() -> C.CDLL:
 EXPORTED_SYMBOLS = [
     "factor_mumps_cmplx_", "factor_mumps_", "solve_mumps_cmplx_", "solve_mumps_", "solve_mumps_sparse_rhs_",
     "solve_mumps_cmplx_sparse_rhs_", "destroy_mumps_", "destroy_mumps_cmplx_",
-    "hmcmt_plan_create", "hmcmt_destroy", "hmcmt_plan_info", "hmcmt_forward", "hmcmt_jtvec", "hmcmt_forward_gradient",
+    "hmcmt_plan_create", "hmcmt_destroy", "hmcmt_plan_info", "hmcmt_forward", "hmcmt_forward_sigma", "hmcmt_jtvec",
+    "hmcmt_forward_gradient", "hmcmt_status", "hmcmt_set_response_kind", "hmcmt_get_responses",
     "hmcmt_set_state", "hmcmt_get_state", "hmcmt_leapfrog_trajectory", "hmcmt_leapfrog_steps_device", "hmcmt_sync",
     "hmcmt_step_partial", "hmcmt_exchange_buffer", "hmcmt_step_finish",
     "hmcmt_timer_start", "hmcmt_timer_stop", "hmcmt_kernel_time", "hmcmt_run_chain", "hmcmt_export_system", "hmcmt_version",

@@ -6,7 +6,8 @@
  *  Level 1 — the eight Fortran-style symbols the reference's Julia wrapper `ccall`s in
  *            MUMPS/src/MUMPSfuncs.jl (library path MUMPS/src/MUMPS.jl:14).  Every argument is
  *            passed by pointer, integers are int64, matrices are full 1-based CSC.  With this
- *            library symlinked to MUMPS/lib/MUMPS the unmodified reference runs on the GPU solver.
+ *            library symlinked to MUMPS/lib/MUMPS the unmodified reference runs on the GPU solver
+ *            (symmetric matrices only: sym = 1 or 2, which is all the hot path passes).
  *
  *  Level 2 — fused entry points mirroring the reference's sampler-facing functions
  *            (MT2DFwdSolver, compJacTMatVec, compDataGradient, proposeLeapfrog, runHMCSampler).
@@ -34,9 +35,10 @@ extern "C" {
 /* factorMUMPS(A::SparseMatrixCSC{ComplexF64},sym,ooc)  MUMPSfuncs.jl:24-39 (ccall :32-35).
  * sym: 0 unsymmetric, 1 "SPD", 2 general symmetric (:25-26).  Only symmetric matrices are
  * supported (the hot path passes sym=1 for a complex-symmetric matrix, mt2DTE.jl:51); the
- * matrix is factorised as pivot-free block LDL^T without conjugation (banded: half-bandwidth <= 104
- * in registers, 105..320 through a global-memory window; wider matrices return -3).  Returns an
- * opaque handle; *status < 0 on error. */
+ * matrix is factorised pivot-free without conjugation.  Like MUMPS the library picks its own elimination order: a
+ * half-bandwidth <= 104 in the caller's numbering goes to the register-window band kernel, everything else (e.g. the
+ * reference's y-fastest Aii, the 3-D div-grad matrices of MUMPS/test) is ordered by nested dissection and factorised by
+ * the multifrontal kernels; the analysis is cached per sparsity pattern.  Returns an opaque handle; *status < 0 on error. */
 int64_t factor_mumps_cmplx_(const int64_t* n, const int64_t* sym, const int64_t* ooc, const double* nzval,
                             const int64_t* rowval, const int64_t* colptr, int64_t* status);
 /* factorMUMPS(A::SparseMatrixCSC{Float64},...)  MUMPSfuncs.jl:41-56 (ccall :49-52) */
@@ -104,7 +106,9 @@ int hmcmt_plan_create(const hmcmt_problem* prob, hmcmt_plan** out);
 void hmcmt_destroy(hmcmt_plan* plan);
 /* sizes derived by the plan: n=0 N (unknowns/system), 1 nNode, 2 nCell, 3 nb, 4 half-bandwidth,
  * 5 tile-window T, 6 macro-steps S, 7 systems per chain, 8 receiver node row zid (0-based),
- * 9 factor bytes per system, 10 kernel launches issued so far (of this library) */
+ * 9 factor bytes per system, 10 kernel launches issued so far (of this library), 11 solver of the plan (0 register-window
+ * band kernel, 1 nested-dissection multifrontal), 12 real flops of one factorisation of one system in the implemented
+ * ordering, 13 two CTAs per system (band kernel only) */
 int64_t hmcmt_plan_info(const hmcmt_plan* plan, int what);
 
 /* MT2DFwdSolver(mtMesh, mtData)  MT2DFwdSolver.jl:74-216 with sigma = activeCell*exp(m)+bg
@@ -117,7 +121,9 @@ int hmcmt_forward(hmcmt_plan* plan, const double* m, double* pred, double* exTE,
 int hmcmt_forward_sigma(hmcmt_plan* plan, const double* sigma, double* pred, double* exTE, double* hxTM);
 
 /* compJacTMatVec(exTE,hxTM,datVec,...)  compJacTMatVec.jl:8-329 for the state left by the last
- * hmcmt_forward: v [nChains][nData] complex -> gsig [nChains][nAC] = real(J^T v) w.r.t. conductivity. */
+ * hmcmt_forward: v [nChains][nData] complex -> gsig [nChains][nAC] = real(J^T v) w.r.t. conductivity.
+ * Reuses the factors, fields and boundary values still resident from that forward evaluation (the reference's AinvTE /
+ * AinvTM, compJacTMatVec.jl:220-224, 291-295): only the adjoint sources, one solve per system and the contraction run. */
 int hmcmt_jtvec(hmcmt_plan* plan, const double* v, double* gsig);
 
 /* compDataGradient(mtMesh,mtData,invParam,hmcprior)  HMCSampler.jl:277-330:
@@ -153,6 +159,19 @@ int hmcmt_exchange_buffer(hmcmt_plan* plan, void** device_ptr, int64_t* count);
 int hmcmt_step_finish(hmcmt_plan* plan, double dt);
 /* blocks until all work queued on the plan's stream has finished */
 int hmcmt_sync(hmcmt_plan* plan);
+/* Device error flags of everything queued so far (synchronises): 0, or -10 (a singular / non-finite pivot block in some
+ * system), or -21 (checkParameterBound!: a bound could not be met within 500 reflections, HMCSampler.jl:546-548, where the
+ * reference prints a message and loops forever).  Reading clears the flags.  The asynchronous entry points
+ * (hmcmt_leapfrog_steps_device, hmcmt_step_partial / _finish) do not check: call this after them. */
+int hmcmt_status(hmcmt_plan* plan);
+/* Response type of the forward evaluation (compMTRespTE mt2DTE.jl:240-259, compMTRespTM mt2DTM.jl:224-242):
+ * kind 0 = impedance, 1 = apparent resistivity rho_a = |Z|^2/(omega mu0) and phase atan2(Im Z, Re Z) in degrees
+ * ("Rho_Pha" data).  Forward only: the reference's own sensitivity code never reaches that data type
+ * ("Rho_Pha" in readMT2DData.jl:87 / MT2DFwdSolver.jl:191 vs "Rho_Phs" in compJacTMatVec.jl:104), so gradients stay impedance-only.
+ * hmcmt_get_responses copies the responses of the last forward evaluation, unmasked:
+ * out [nChains][nFreq][nRx][nComp][2] doubles = (Re Z, Im Z) or (rho_a, phase). */
+int hmcmt_set_response_kind(hmcmt_plan* plan, int32_t kind);
+int hmcmt_get_responses(hmcmt_plan* plan, double* out);
 /* CUDA-event bracket on the plan's stream: start / stop (returns elapsed ms through *ms) */
 int hmcmt_timer_start(hmcmt_plan* plan);
 int hmcmt_timer_stop(hmcmt_plan* plan, float* ms);
@@ -162,15 +181,18 @@ int hmcmt_kernel_time(hmcmt_plan* plan, int reset, float* factor_ms, int64_t* fa
 /* runHMCSampler(mtMesh,mtData,invParam,hmcprior)  HMCSampler.jl:72-196 for all chains of the plan with injected
  * random draws in the reference's draw order:
  *   rhoref = round(unirandDouble(0.5 rho0, 1.5 rho0)) with rho0 = 1/exp(strModel[1]) (HMCSampler.jl:100-105,
- *   the homogeneous start/reference model, drawn by the caller), z_init [nChains][nAC], then per sample
+ *   the homogeneous model that becomes invParam.strModel / refModel and defines the start Hamiltonian, drawn by the caller),
+ *   m_start [nChains][nAC] = the model-file strModel: the reference copies it into hmcParamCurrent.rhomodel BEFORE replacing
+ *   strModel (HMCSampler.jl:87 vs :100-109), so the first trajectory starts there (NULL: start from the homogeneous model),
+ *   z_init [nChains][nAC], then per sample
  *   intsteps[i] (shared by the chains of this plan), u_accept [nChains][nsamples], z_mom [nsamples][nChains][nAC].
  * Outputs (leading dimension nChains): hmcmodel [nsamples][nAC] (sample-major = Julia's column-major
  *          nparam x nsamples), hmstats [nsamples+1][4] (Julia 4 x (nsamples+1)), accept [nsamples] (0/1),
- *          hmcdata [nsamples+1][nData] complex.  The Metropolis test runs on the device; the host never
- *          synchronises inside the sampling loop.
+ *          hmcdata [nsamples+1][nData] complex.  The Metropolis test and the sample bookkeeping run on the device; all
+ *          random draws are uploaded once before the loop, which then enqueues without any host synchronisation.
  * reuse_last_forward != 0 drops the reference's redundant getHamiltonian forward sweep (the proposal's
  * misfit equals the last leapfrog step's); 0 re-runs the forward exactly as the reference does. */
-int hmcmt_run_chain(hmcmt_plan* plan, double dt, int32_t nsamples, double rhoref, const double* z_init,
+int hmcmt_run_chain(hmcmt_plan* plan, double dt, int32_t nsamples, double rhoref, const double* m_start, const double* z_init,
                     const int32_t* intsteps, const double* u_accept, const double* z_mom, int32_t reuse_last_forward,
                     double* hmcmodel, double* hmstats, int32_t* accept, double* hmcdata);
 

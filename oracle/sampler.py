@@ -186,6 +186,8 @@ def runHMCSampler(mesh, data, inv: InvDataModel, prior: HMCPrior, streams: Rando
     """`runHMCSampler` HMCSampler.jl:72-196 -> (hmcmodel[nparam,nsamples], stats dict, hmcdata)."""
     nparam, ndata = len(inv.strModel), len(inv.obsData)
     nsamples = prior.totalsamples if nsamples is None else nsamples
+    cur_m = np.array(inv.strModel, dtype=float).copy()      # hmcParamCurrent.rhomodel = copy(invParam.strModel) (:87): the
+    #                                                         model-file model, taken BEFORE strModel is replaced below (:100-109)
     cur_p = clip_momentum(streams.z_init)
     sigma0 = inv.strModel[0]          # unique(strModel)[1]: Julia's unique keeps first-appearance order (:100-101)
     rho0 = 1.0 / np.exp(sigma0)
@@ -193,7 +195,6 @@ def runHMCSampler(mesh, data, inv: InvDataModel, prior: HMCPrior, streams: Rando
     strModel = np.log(np.ones(nparam) / rhoref)
     inv.strModel = strModel.copy()
     inv.refModel = strModel.copy()
-    cur_m = strModel.copy()
     mesh.sigma = inv.activeCell @ np.exp(inv.strModel) + inv.bgModel       # updateStartModel :834-849
     startD, startK, startH, startM, pred = getHamiltonian(data, mesh, inv, prior, cur_p, factor_fn)
     hmcmodel = np.zeros((nparam, nsamples))

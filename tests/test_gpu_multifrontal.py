@@ -1,6 +1,7 @@
-"""Large-bandwidth path (half-bandwidth 105..320, band_big.cuh) and the frequency-sharded step on the GPU.
-Solver boundary: the reference's own criterion (MUMPS/test/testDivGrad.jl: relative residual < 1e-14).
-Full path: a mesh wider than the register-window kernel against the CPU oracle at 1e-9 (north_star)."""
+"""Nested-dissection multifrontal solver (mf_symbolic.h / mf_kernels.cuh) on the GPU, and the frequency-sharded step.
+Solver boundary: the reference's own criterion (MUMPS/test/testDivGrad.jl: relative residual < 1e-14) on matrices the
+register-window band kernel cannot take.  Full path: meshes wider than 104 unknowns per line against the CPU oracle at 1e-9
+(north_star)."""
 import numpy as np
 import pytest
 import scipy.sparse as sp
@@ -12,21 +13,42 @@ def relres(A, x, b):
     return np.linalg.norm(A @ x - b) / np.linalg.norm(b)
 
 
-def test_stencil_systems_up_to_b320():
+def _stencil(nl, nf, rng):
+    N = nl * nf
+    d = 4 + rng.random(N) + 1j * rng.random(N)
+    e1, e2 = -rng.random(N), -rng.random(N)
+    e1[np.arange(N) % nf == 0] = 0
+    return sp.diags([d, e1[1:], e1[1:], e2[nf:], e2[nf:]], [0, -1, 1, -nf, nf], format="csc")
+
+
+def test_wide_stencil_systems():
     from hmcmt2d_b200 import lib
     rng = np.random.default_rng(2)
-    for nl, nf in [(4, 105), (7, 130), (5, 200), (4, 299), (3, 320)]:
-        N = nl * nf
-        d = 4 + rng.random(N) + 1j * rng.random(N)
-        e1, e2 = -rng.random(N), -rng.random(N)
-        e1[np.arange(N) % nf == 0] = 0
-        A = sp.diags([d, e1[1:], e1[1:], e2[nf:], e2[nf:]], [0, -1, 1, -nf, nf], format="csc")
-        rhs = rng.standard_normal(N) + 1j * rng.standard_normal(N)
+    for nl, nf in [(4, 105), (7, 130), (5, 200), (4, 299), (3, 320), (40, 500), (300, 130)]:
+        A = _stencil(nl, nf, rng)
+        rhs = rng.standard_normal(A.shape[0]) + 1j * rng.standard_normal(A.shape[0])
         assert relres(A, lib.solveMUMPS(A, rhs, 1), rhs) < 1e-14, (nl, nf)
 
 
+@pytest.mark.parametrize("fsmall,leaf", [(144, 16), (0, 16), (48, 8), (144, 1), (80, 64)])
+def test_front_size_classes(fsmall, leaf, monkeypatch):
+    """Every kernel family: all fronts in shared memory, all fronts through the global-memory path (assembly, diagonal-block
+    inversion, DMMA GEMMs, chunked pivots), mixed; single-node and 64-node leaves.  Forced onto matrices the band kernel would
+    otherwise take."""
+    from hmcmt2d_b200 import lib
+    monkeypatch.setenv("HMCMT_SHIM_SOLVER", "mf")
+    monkeypatch.setenv("HMCMT_MF_FSMALL", str(fsmall))
+    monkeypatch.setenv("HMCMT_MF_LEAF", str(leaf))
+    rng = np.random.default_rng(5)
+    for nl, nf in [(1, 1), (5, 3), (3, 8), (20, 13), (64, 64), (130, 97)]:
+        A = _stencil(nl, nf, rng) if nl * nf > 1 else sp.csc_matrix(np.array([[2.0 + 1.0j]]))
+        rhs = rng.standard_normal((A.shape[0], 3)) + 1j * rng.standard_normal((A.shape[0], 3))
+        x = lib.solveMUMPS(A, rhs, 2)
+        assert max(relres(A, x[:, i], rhs[:, i]) for i in range(3)) < 1e-14, (nl, nf)
+
+
 def test_full_band_matrix_and_ragged_size():
-    """Dense band (every diagonal populated), N not a multiple of the 32-column panel, several right-hand sides, real twin."""
+    """Dense band (every diagonal populated: fronts far denser than a grid's), ragged N, several right-hand sides, real twin."""
     from hmcmt2d_b200 import lib
     rng = np.random.default_rng(3)
     N, b = 1003, 120
@@ -43,15 +65,39 @@ def test_full_band_matrix_and_ragged_size():
     assert xr.dtype == np.float64 and relres(Ar, xr, rhs[:, 0].real) < 1e-14
 
 
+def test_disconnected_and_arrow_patterns():
+    """Graphs the level-set bisection must survive: two disconnected grids in one matrix, and an arrow matrix (one dense row)."""
+    from hmcmt2d_b200 import lib
+    rng = np.random.default_rng(6)
+    A = sp.block_diag([_stencil(30, 20, rng), _stencil(12, 45, rng)], format="csc")
+    rhs = rng.standard_normal(A.shape[0]) + 1j * rng.standard_normal(A.shape[0])
+    import os
+    os.environ["HMCMT_SHIM_SOLVER"] = "mf"
+    try:
+        assert relres(A, lib.solveMUMPS(A, rhs, 1), rhs) < 1e-14
+        n = 400
+        B = sp.lil_matrix((n, n), dtype=complex)
+        B.setdiag(4.0 + rng.random(n) + 1j * rng.random(n))
+        B[0, 0] = 400.0
+        B[n - 1, :n - 1] = -rng.random(n - 1) * 0.01
+        B[:n - 1, n - 1] = B[n - 1, :n - 1].T
+        B[n - 1, n - 1] = 8.0
+        B = B.tocsc()
+        rhs = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+        assert relres(B, lib.solveMUMPS(B, rhs, 2), rhs) < 1e-14
+    finally:
+        os.environ.pop("HMCMT_SHIM_SOLVER", None)
+
+
 def test_wide_mesh_parity_with_oracle():
-    """ny-1 = 123, nz-1 = 117 > 104: the plan takes the large-bandwidth path (window T = 20)."""
+    """ny-1 = 123, nz-1 = 117 > 104: the plan takes the multifrontal solver."""
     from hmcmt2d_b200 import api, synthetic
     from oracle import sampler as osamp
     from tests.helpers import to_oracle
     mesh, data, inv, prior = synthetic.make_problem(124, 118, 2, nRx=10)
     m = synthetic.stress_model(inv)
     pl = api.Plan(mesh, data, inv, prior)
-    assert pl.info(4) == 117 and pl.info(5) == 20
+    assert pl.info(4) == 117 and pl.info(5) == 0 and pl.info(11) == 1
     pred, phi, g = pl.forward_gradient(m)
     om, od, oi, op = to_oracle(mesh, data, inv, prior)
     oi.strModel = m.copy()
@@ -60,6 +106,25 @@ def test_wide_mesh_parity_with_oracle():
     assert abs(phi[0] - ophi) / abs(ophi) < 1e-9
     assert np.abs(g[0] - og).max() / np.abs(og).max() < 1e-9
     pl.close()
+
+
+def test_multifrontal_equals_band_kernel(monkeypatch):
+    """The two solvers on the same narrow mesh: identical responses / gradient to round-off, batched chains included."""
+    from hmcmt2d_b200 import api, synthetic
+    mesh, data, inv, prior = synthetic.make_problem(60, 40, 3, nRx=8)
+    ms = np.stack([synthetic.stress_model(inv, seed=s) for s in (1, 2)])
+    pb = api.Plan(mesh, data, inv, prior, nChains=2)
+    assert pb.info(11) == 0
+    pred0, phi0, g0 = pb.forward_gradient(ms)
+    pb.close()
+    monkeypatch.setenv("HMCMT_SOLVER", "mf")
+    pm = api.Plan(mesh, data, inv, prior, nChains=2)
+    assert pm.info(11) == 1
+    pred1, phi1, g1 = pm.forward_gradient(ms)
+    pm.close()
+    assert (np.abs(pred1 - pred0) / np.abs(pred0)).max() < 1e-11
+    assert np.abs(phi1 - phi0).max() / np.abs(phi0).max() < 1e-10
+    assert np.abs(g1 - g0).max() / np.abs(g0).max() < 1e-10
 
 
 def test_frequency_sharded_steps_match_unsharded():

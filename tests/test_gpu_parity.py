@@ -228,3 +228,63 @@ def test_tiny_problem_against_committed_fixture():
     assert np.abs(g - ref["g"]).max() / np.abs(ref["g"]).max() < TOL
     m2, p2 = api.proposeLeapfrog(api.HMCParameter(len(ref["m"]), ref["m"].copy(), ref["p0"].copy()), pm, pd, pi, pp, intstep=2)
     assert np.abs(m2 - ref["m2"]).max() < TOL and np.abs(p2 - ref["p2"]).max() < TOL * max(1.0, np.abs(ref["p2"]).max())
+
+
+def test_rho_phase_responses_forward_only():
+    """DataType Rho_Pha: apparent resistivity and phase (compMTRespTE mt2DTE.jl:240-259, compMTRespTM mt2DTM.jl:224-242), interleaved
+    and masked as MT2DFwdSolver.jl:191-205 does.  Forward only — the reference's sensitivity code tests "Rho_Phs" and never
+    reaches that data type (compJacTMatVec.jl:104), so the gradient refuses it."""
+    from hmcmt2d_b200 import api, fileio
+    from oracle import fileio as ofio
+    from oracle import forward as ofwd
+    mesh, data, inv, prior = tiny_problem(seed=17)
+    nF, nRx = len(data.freqs), data.rxLoc.shape[0]
+    comps = ["RhoXY", "PhsXY", "RhoYX", "PhsYX"]
+    f, r, c = np.meshgrid(np.arange(1, nF + 1), np.arange(1, nRx + 1), np.arange(1, 5), indexing="ij")
+    keep = np.random.default_rng(3).random(nF * nRx * 4) > 0.25                      # ragged: some rows absent
+    od = ofio.MTData(data.rxLoc, data.freqs, "Rho_Pha", comps, r.ravel()[keep].astype(np.int64), f.ravel()[keep].astype(np.int64),
+                     c.ravel()[keep].astype(np.int64), keep.copy(), True, True)
+    opred, _ = ofwd.MT2DFwdSolver(mesh, od)
+    pm, _, _, _ = to_product(mesh, data, inv, prior)
+    pd = fileio.MTData(np.array(od.rxLoc), np.array(od.freqs), "Rho_Pha", comps, np.array(od.rxID), np.array(od.freqID),
+                       np.array(od.dtID), np.array(od.dataID), True, True)
+    pred, fwd = api.MT2DFwdSolver(pm, pd)
+    assert pred.dtype == np.float64 and pred.shape == opred.shape == (int(keep.sum()),)
+    assert np.abs(pred - opred).max() / np.abs(opred).max() < TOL
+    assert (np.abs(pred - opred) / np.maximum(np.abs(opred), 1e-30)).max() < 1e-8           # phases near 0 / 180 included
+    with pytest.raises(NotImplementedError):
+        api.compJacTMatVec(fwd.exTE, fwd.hxTM, np.zeros(len(pred)), pm, pd, None, fwd.AinvTE, fwd.AinvTM)
+    # TE-only survey: [rho, phs] pairs
+    te = np.isin(od.dtID, (1, 2))
+    od1 = ofio.MTData(data.rxLoc, data.freqs, "Rho_Pha", comps[:2], od.rxID[te], od.freqID[te], od.dtID[te],
+                      keep.reshape(nF, nRx, 4)[:, :, :2].reshape(-1).copy(), True, False)
+    opred1, _ = ofwd.MT2DFwdSolver(mesh, od1)
+    pd1 = fileio.MTData(np.array(od1.rxLoc), np.array(od1.freqs), "Rho_Pha", comps[:2], np.array(od1.rxID), np.array(od1.freqID),
+                        np.array(od1.dtID), np.array(od1.dataID), True, False)
+    pred1, _ = api.MT2DFwdSolver(pm, pd1)
+    assert np.abs(pred1 - opred1).max() / np.abs(opred1).max() < TOL
+
+
+def test_stale_factor_handle_is_refused():
+    """One set of factors is resident per plan: the MT2DFwdData of an earlier evaluation must not silently return the
+    gradient at a later model (the reference's MT2DFwdData owns its factors, MT2DFwdSolver.jl:44-53)."""
+    from hmcmt2d_b200 import api
+    mesh, data, inv, prior = tiny_problem(seed=8)
+    pm, pd, pi, pp = to_product(mesh, data, inv, prior)
+    pred_a, fwd_a = api.MT2DFwdSolver(pm, pd)
+    sig_a = pm.sigma.copy()
+    v = np.ones(len(pred_a), dtype=complex)
+    g_a = api.compJacTMatVec(fwd_a.exTE, fwd_a.hxTM, v, pm, pd, pi.activeCell, fwd_a.AinvTE, fwd_a.AinvTM)
+    pm.sigma = sig_a * 1.3
+    pred_b, fwd_b = api.MT2DFwdSolver(pm, pd)
+    with pytest.raises(RuntimeError):
+        api.compJacTMatVec(fwd_a.exTE, fwd_a.hxTM, v, pm, pd, pi.activeCell, fwd_a.AinvTE, fwd_a.AinvTM)
+    g_b = api.compJacTMatVec(fwd_b.exTE, fwd_b.hxTM, v, pm, pd, pi.activeCell, fwd_b.AinvTE, fwd_b.AinvTM)
+    assert np.abs(g_b - g_a).max() > 1e-6 * np.abs(g_a).max()
+    # a selector with the same number of columns but other cells is mapped by cell index, not by shape
+    import scipy.sparse as sp
+    nAC = pi.activeCell.shape[1]
+    perm = np.random.default_rng(0).permutation(nAC)
+    P2 = sp.csr_matrix(pi.activeCell.tocsc()[:, perm])
+    g_p = api.compJacTMatVec(fwd_b.exTE, fwd_b.hxTM, v, pm, pd, P2, fwd_b.AinvTE, fwd_b.AinvTM)
+    assert np.array_equal(g_p, g_b[perm])
