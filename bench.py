@@ -4,21 +4,25 @@
     python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
     python bench.py --impl reference --gpus N --steps K --warmup W
 
-One "step" = one leapfrog step of the reference sampler (HMCSampler.jl:235-265): position drift with step
-clipping and bound reflection, one compDataGradient-equivalent evaluation (forward + adjoint over all
-frequencies x TE/TM), prior gradient, momentum kick.  Workload = BASELINE.json configs[1]/[2]: synthetic
-200x100-cell mesh, 30 frequencies, TE+TM, one independent chain per GPU (weak scaling, no data-path
-collective: "replicas only", as parallelHMC.jl).
+One "step" = one leapfrog step of the reference sampler (HMCSampler.jl:235-265): position drift with step clipping and bound
+reflection, one compDataGradient-equivalent evaluation (forward + adjoint over all frequencies x TE/TM), prior gradient,
+momentum kick.
 
-    python bench.py --config cfg4 --gpus N [--nfreq F]       (BASELINE.json configs[3]; not the driver's default line)
-the 800x300-cell mesh with 60 frequencies, frequency-sharded over N >= 2 GPUs (strong scaling; the 120 factors need
-154 GB, so N = 1 only runs with a reduced --nfreq), one NCCL all-reduce of [gradient | misfit] per leapfrog step.
+Headline workload = BASELINE.json configs[1]/[2] ("cfg2"): synthetic 200x100-cell mesh, 30 frequencies, TE+TM, one independent
+chain per GPU (weak scaling, no data-path collective: "replicas only", as parallelHMC.jl).  Observations = forward(true model)
+(1 + 5 % noise), evaluation model = the stress model of SURVEY.md 8(d).
 
-`value` : steps/s with the chain state resident in HBM (hmcmt_leapfrog_steps_device), CUDA events on the
-          library's stream, max over ranks.
-`e2e`   : the same step through the reference-facing call (compDataGradient-equivalent through the C ABI)
-          with HOST buffers: the model goes host->device and predicted data / misfit / gradient come back
-          every step; drift and kick run on the host exactly as the reference's proposeLeapfrog does.
+`value` : steps/s with the chain state resident in HBM (hmcmt_leapfrog_steps_device), CUDA events on the library's stream,
+          max over ranks.
+`e2e`   : the same step through the reference-facing call (compDataGradient-equivalent through the C ABI) with HOST buffers:
+          the model goes host->device and predicted data / misfit / gradient come back every step; drift and kick run on the host
+          exactly as the reference's proposeLeapfrog does.
+`validated` : the device loop's error flags are clear, its states are finite, a 3-step device loop and a 3-step host loop from
+          the same (m0, p0) agree to 1e-9, and the final states of the two timed arms (W+K steps each) agree.
+`strong_scaling` : the SAME json line also carries BASELINE.json configs[3] ("cfg4": 800x300 cells, 60 frequencies, one chain,
+          the 120 (frequency, mode) systems sharded over the N GPUs, one ncclAllReduce of [gradient | misfit] per step issued by
+          the library on its own stream) with its own value / e2e / roofline / clocks, so that the driver's 1/2/4/8-GPU runs hold
+          a strong-scaling curve next to the weak-scaling one.   `--config cfg4` prints that record as the main line instead.
 """
 from __future__ import annotations
 
@@ -35,16 +39,15 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-CFG4 = dict(workload="cfg4: synthetic 800x300-cell mesh, 60 frequencies, TE+TM, 1 HMC chain, frequencies sharded over the GPUs "
-                     "(one NCCL sum-all-reduce of [gradient | misfit] per step)",
-            ny=800, nz=300, nfreq=60, nrx=40, modes="TE+TM", chains_per_gpu=1)
 METRIC = "leapfrog_steps_per_sec"
 UNIT = "steps/s"
 WORKLOAD = dict(workload="cfg2: synthetic 200x100-cell mesh, 30 frequencies, TE+TM, 1 HMC chain per GPU",
                 ny=200, nz=100, nfreq=30, nrx=40, modes="TE+TM", chains_per_gpu=1)
-# dram__bytes_read + dram__bytes_write of the factorisation group per step: FM_OWN capture (24.3 MB + 2.251 GB,
-# profiles/r01_final_factor_own_ncu.txt) + its back-substitution sweep, which streams the factor once exactly like the
-# captured solve sweep (2.279 GB + 23.6 MB, profiles/r01_final_solve_own_ncu.txt); FM_SEP (13 of 2476 macro-steps) neglected
+CFG4 = dict(workload="cfg4: synthetic 800x300-cell mesh, 60 frequencies, TE+TM, 1 HMC chain, the 120 (frequency, mode) systems "
+                     "sharded over the GPUs (one NCCL sum-all-reduce of [gradient | misfit] per step)",
+            ny=800, nz=300, nfreq=60, nrx=40, modes="TE+TM", chains_per_gpu=1)
+# dram__bytes_read + dram__bytes_write of the factorisation group per step at cfg2 (band kernel): FM_OWN capture + its
+# back-substitution sweep, ncu --set full (profiles/r01_final_factor_own_ncu.txt, profiles/r01_final_solve_own_ncu.txt)
 NCU_FACTOR_DRAM_BYTES = (24.28e6 + 2.250943e9) + (2.278771e9 + 23.64e6)
 FP64_DMMA_PEAK_TFLOPS = 37.1     # measured on this pool's B200 with DMMA.8x8x4 (profiles/r01_fp64_peak_ubench.txt)
 
@@ -121,138 +124,157 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
-def build_problem(cfg=None):
-    from hmcmt2d_b200 import synthetic
-    cfg = cfg or WORKLOAD
+# ------------------------------------------------------------------------------------------------------
+# workload: mesh / survey of SURVEY.md 8(d); observations = forward(true model) (1 + 0.05 N), err = 0.05 |Z|
+
+def build_problem_gpu(cfg, device):
+    """Problem with true-model observations; the forward of the true model runs on this GPU through the library."""
+    from hmcmt2d_b200 import api, synthetic
     mesh, data, inv, prior = synthetic.make_problem(cfg["ny"], cfg["nz"], cfg["nfreq"], cfg["nrx"])
-    return mesh, data, inv, prior
+    truth = synthetic.true_model(mesh)
+    mesh_t = type(mesh)(mesh.yLen, mesh.zLen, mesh.airLayer, mesh.gridSize, mesh.origin, truth)
+    pl0 = api._forward_only_plan(mesh_t, data, device)
+    pred_true, _ = api.MT2DFwdSolver(mesh_t, data, plan=pl0)
+    pl0.close()
+    data.__dict__.pop("_fwd_plans", None)
+    obs, err = synthetic.true_model_data(data, pred_true)
+    return synthetic.make_problem(cfg["ny"], cfg["nz"], cfg["nfreq"], cfg["nrx"], obs=obs, err=err)
 
 
 # ------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle (restated reference algorithm, SciPy SuperLU in place of UMFPACK/MUMPS) on host cores.
 
+def _best_cpu_factor(A):
+    """SuperLU with the settings that measured fastest on these complex-symmetric systems (symmetric-mode minimum degree on
+    A^T + A, no diagonal pivoting: 0.11-0.15 s vs 0.16-0.18 s per factorisation with the default COLAMD at cfg2)."""
+    import scipy.sparse.linalg as spla
+    return spla.splu(A.tocsc(), permc_spec="MMD_AT_PLUS_A", diag_pivot_thresh=0.0, options=dict(SymmetricMode=True))
+
+
+_JOB_CACHE = {}
+
+
 def _cpu_freq_job(args):
-    """forward + adjoint for ONE frequency (TE+TM) of the workload — the unit the host cores are farmed over."""
+    """forward + adjoint for ONE frequency (TE+TM) of the workload — the unit the host cores are farmed over.  The problem
+    of a frequency (mesh, survey row subset, true-model observations) is set up once per worker and cached: untimed."""
     fidx, seed, cfg = args
     sys.path.insert(0, ROOT)
     from hmcmt2d_b200 import synthetic
     from oracle import fileio as ofio
+    from oracle import forward as ofwd
     from oracle import sampler as osamp
-    mesh, data, inv, prior = build_problem(cfg)
-    keep = data.freqID == fidx + 1
-    omesh = ofio.TensorMesh2D(mesh.yLen, mesh.zLen, mesh.airLayer, mesh.gridSize, mesh.origin, mesh.sigma)
-    od = ofio.MTData(data.rxLoc, data.freqs[fidx:fidx + 1], data.dataType, data.dataComp, data.rxID[keep],
-                     np.ones(int(keep.sum()), np.int64), data.dtID[keep], np.ones(int(keep.sum()), bool), True, True)
-    oinv = osamp.setupInverseDataModel(omesh, [1e-8], inv.obsData[keep], inv.dataErr[keep])
-    oinv.strModel = synthetic.stress_model(inv, seed)
+    key = (fidx, cfg["ny"], cfg["nz"], cfg["nfreq"])
+    if key not in _JOB_CACHE:
+        mesh, data, inv, prior = synthetic.make_problem(cfg["ny"], cfg["nz"], cfg["nfreq"], cfg["nrx"])
+        keep = data.freqID == fidx + 1
+        od = ofio.MTData(data.rxLoc, data.freqs[fidx:fidx + 1], data.dataType, data.dataComp, data.rxID[keep],
+                         np.ones(int(keep.sum()), np.int64), data.dtID[keep], np.ones(int(keep.sum()), bool), True, True)
+        tmesh = ofio.TensorMesh2D(mesh.yLen, mesh.zLen, mesh.airLayer, mesh.gridSize, mesh.origin, synthetic.true_model(mesh))
+        pred_true, _ = ofwd.MT2DFwdSolver(tmesh, od, _best_cpu_factor)
+        noise = np.random.default_rng(7).standard_normal(len(data.freqID))[keep]         # the rows of synthetic.true_model_data
+        obs, err = pred_true * (1.0 + 0.05 * noise), 0.05 * np.abs(pred_true)
+        omesh = ofio.TensorMesh2D(mesh.yLen, mesh.zLen, mesh.airLayer, mesh.gridSize, mesh.origin, mesh.sigma)
+        oinv = osamp.setupInverseDataModel(omesh, [1e-8], obs, err)
+        oinv.strModel = synthetic.stress_model(inv, seed)
+        _JOB_CACHE[key] = (omesh, od, oinv)
+    omesh, od, oinv = _JOB_CACHE[key]
     t0 = time.perf_counter()
-    osamp.compDataGradient(omesh, od, oinv, ofio.HMCPrior())
+    osamp.compDataGradient(omesh, od, oinv, ofio.HMCPrior(), factor_fn=_best_cpu_factor)
     return time.perf_counter() - t0
 
 
-def cpu_steps_per_sec(nworkers: int, nfreq_sample: int, repeats: int = 1, cfg=None):
-    """Times `nfreq_sample` of the 30 frequencies farmed over `nworkers` processes and extrapolates to the full
-    step (frequencies are independent and cost the same: identical sparsity pattern)."""
+def _pool(nworkers):
     import multiprocessing as mp
     # one process per core, ONE thread per process: the workers inherit these (spawn) before they import numpy / scipy —
     # without them every worker starts a full BLAS / OpenMP team and the oversubscribed host takes minutes per sample
     for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
         os.environ[var] = "1"
-    cfg = cfg or WORKLOAD
-    freqs = list(np.linspace(0, cfg["nfreq"] - 1, nfreq_sample).astype(int))
-    ctx = mp.get_context("spawn")
-    times = []
-    with ctx.Pool(nworkers) as pool:
-        if cfg["ny"] * cfg["nz"] < 100000:
-            pool.map(_cpu_freq_job, [(freqs[0], 1, cfg)] * nworkers)   # warm the workers (imports, operator setup)
-        for r in range(repeats):
-            t0 = time.perf_counter()
-            pool.map(_cpu_freq_job, [(int(f), 1, cfg) for f in freqs])
-            times.append(time.perf_counter() - t0)
-    t = min(times)
-    step_time = t * cfg["nfreq"] / nfreq_sample
-    return 1.0 / step_time, t
+    return mp.get_context("spawn").Pool(nworkers)
+
+
+def cpu_one_core_sample(cfg):
+    """One frequency (TE+TM forward + adjoint) on one host core -> steps/s of the whole step by multiplication."""
+    with _pool(1) as pool:
+        pool.map(_cpu_freq_job, [(0, 1, cfg)])                        # set-up + warm-up of the worker
+        t0 = time.perf_counter()
+        pool.map(_cpu_freq_job, [(0, 1, cfg)])
+        wall = time.perf_counter() - t0
+    return 1.0 / (wall * cfg["nfreq"]), wall
 
 
 def run_reference(args, rank):
+    """Reference arm: WHOLE steps of the workload (all frequencies, TE+TM, forward + adjoint) on all host cores, frequencies
+    farmed over one single-threaded process per core — the fairest stand-in available for the reference's MUMPS + OpenMP path
+    (neither Julia nor MUMPS exists on the box).  `steps` is what was actually run: as many of the requested K as fit a
+    ~150 s budget."""
     if rank != 0:
         return
+    cfg = WORKLOAD
     cores = os.cpu_count() or 1
-    nsample = min(WORKLOAD["nfreq"], cores)
-    vals = []
-    # every "step" of this arm is one bounded sample (nsample frequencies farmed over all host cores, extrapolated to the
-    # full step); at most three samples, whatever --steps says, so that the arm ends within a minute or two
-    for _ in range(max(1, min(args.steps, 3))):
-        v, wall = cpu_steps_per_sec(cores, nsample)
-        vals.append(v)
-    value = float(np.median(vals))
-    sample = (f"{nsample} of {WORKLOAD['nfreq']} frequencies (TE+TM forward+adjoint each) farmed over {cores} host processes, "
-              f"extrapolated x{WORKLOAD['nfreq'] / nsample:.2f}; restated CPU path (SciPy SuperLU), not MUMPS/UMFPACK")
-    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                ms_per_step=1000.0 / value, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64 (complex128)",
-                data="synthetic", config=WORKLOAD, impl="reference",
-                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port", sample=sample),
+    nw = min(cores, cfg["nfreq"])
+    jobs = [(f, 1, cfg) for f in range(cfg["nfreq"])]
+    times = []
+    with _pool(nw) as pool:
+        pool.map(_cpu_freq_job, jobs)                                 # untimed: per-frequency problem set-up (cached) + warm-up step
+        t_start = time.perf_counter()
+        for _ in range(max(1, args.steps)):
+            t0 = time.perf_counter()
+            pool.map(_cpu_freq_job, jobs)
+            times.append(time.perf_counter() - t0)
+            if time.perf_counter() - t_start + times[-1] > 150.0:
+                break
+    step = float(np.mean(times))
+    value = 1.0 / step
+    sample = (f"{len(times)} whole steps: all {cfg['nfreq']} frequencies (TE+TM forward + adjoint each) farmed over {nw} single-threaded "
+              f"host processes ({cores} cores; {-(-cfg['nfreq'] // nw)} wave(s) per step), no extrapolation; restated CPU path (oracle, SciPy "
+              f"SuperLU with symmetric-mode MMD ordering, the fastest of the SuperLU settings tried) — not MUMPS / UMFPACK, not Julia")
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=len(times), warmup=1,
+                ms_per_step=1000.0 * step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64 (complex128)",
+                data="synthetic", config=dict(WORKLOAD), impl="reference",
+                cpu_baseline=dict(value=value, unit=UNIT, cores=nw, kind="port", sample=sample),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------------
 
-def run_gpu(args, rank, world, local_rank):
-    import torch
-    import torch.distributed as dist
-    from hmcmt2d_b200 import api, synthetic
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device — hmcmt2d_b200 has no CPU path")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+class Dist:
+    """torch.distributed plumbing: barrier + max over ranks."""
 
-    def barrier():
+    def __init__(self, rank, world, local_rank):
+        import torch
+        self.torch, self.rank, self.world = torch, rank, world
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device — hmcmt2d_b200 has no CPU path")
+        torch.cuda.set_device(local_rank)
         if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+            import torch.distributed as dist
+            self.dist = dist
+            dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
 
-    def max_over_ranks(x):
-        if world == 1:
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max(self, x):
+        if self.world == 1:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-    mesh, data, inv, prior = build_problem()
-    pl = api.Plan(mesh, data, inv, prior, nChains=1, device=local_rank)
-    rng = np.random.default_rng(100 + rank)
-    m0 = synthetic.stress_model(inv, seed=1 + rank)            # chains differ per GPU (seeds 1..N, cfg3)
-    p0 = np.clip(rng.standard_normal(len(m0)), -2.5, 2.5)
-    dt = prior.dt
-    K, W = args.steps, max(3, args.warmup)
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
 
-    # ---------------- device-resident arm (`value`) ----------------
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    pl.set_state(m0, p0, m0)
-    pl.leapfrog_steps_device(dt, W)
-    pl.sync()
-    pl.kernel_time(reset=True)
-    launches0 = pl.info(10)
-    barrier()
-    sampler.mark()
-    pl.timer_start()
-    pl.leapfrog_steps_device(dt, K)
-    ms = pl.timer_stop()
-    barrier()
-    clocks = sampler.stop()
-    launches = pl.info(10) - launches0
-    factor_ms, factor_n = pl.kernel_time(reset=True)
-    ms = max_over_ranks(ms)
-    value = world * K / (ms * 1e-3)
 
-    # ---------------- end-to-end arm through the host-buffer C ABI ----------------
+def host_stepper(evaluate, inv, prior, m0, dt):
+    """The reference's proposeLeapfrog inner step on the host (HMCSampler.jl:235-265) around a host-buffer gradient call."""
     lo, hi = np.log(prior.sigBounds[0]), np.log(prior.sigBounds[1])
     Wm, beta = inv.Wm, prior.regParam
 
-    def host_step(m, p):
+    def step(m, p):
         dm = dt * p
         mx = np.abs(dm).max()
         if mx > 3.0:
@@ -265,104 +287,145 @@ def run_gpu(args, rank, world, local_rank):
             m = np.where(low, 2 * lo - m, m); p = np.where(low, -p, p)
             high = m > hi
             m = np.where(high, 2 * hi - m, m); p = np.where(high, -p, p)
-        pred, phi, g = pl.forward_gradient(m)                  # H2D m ; D2H pred, phi, grad  (pinned staging inside)
-        p = p - dt * (g[0] + beta * (Wm @ (m - m0)))
-        return m, p, float(phi[0])
+        pred, phi, g = evaluate(m)                             # H2D m ; D2H pred, phi, grad  (pinned staging inside)
+        p = p - dt * (g + beta * (Wm @ (m - m0)))
+        return m, p, phi
+    return step
 
+
+def factor_roofline(pl, factor_ms, factor_n, step_ms, peaks, peak_src):
+    """Roofline record of the factorisation phase (the dominant kernel group), timed with CUDA events inside the library."""
+    N, b, nsys, mf = pl.info(0), pl.info(4), pl.info(7), pl.info(11)
+    fac_ms = factor_ms / max(1, factor_n)
+    band_flops = (4.0 * N * b * b + 16.0 * N * b) * nsys            # SURVEY.md 8(d): banded LDL^T + fused forward solve
+    if mf:
+        flops = float(pl.info(12)) * nsys                             # counted from the symbolic structure of the ordering used
+        fbytes = 2.0 * pl.info(9) * nsys                              # factor written once + read once by the forward solve
+        kernel = ("factorisation of this rank's systems on the nested-dissection multifrontal path: mf_small_kernel (shared-memory fronts), "
+                  "mf_asm_*/mf_inv_kernel/mf_gemm_kernel (DMMA.8x8x4 64x64x16 tiles) per depth and pivot chunk, + the forward solve "
+                  "(mf_fwd_*/mf_bwd_*), timed as one unit")
+        traffic, tsrc = None, None
+    else:
+        flops, fbytes = band_flops, 2.0 * 16.0 * N * (b + 1) * nsys
+        kernel = ("factorisation of the systems = band_factor_kernel<14> FM_OWN + FM_SEP (FP64 DMMA.8x8x4 block LDL^T, fused assembly + "
+                  "forward elimination) + band_solve_kernel<14> SM_BACKZ_OWN (its back-substitution), timed as one unit")
+        traffic = NCU_FACTOR_DRAM_BYTES
+        tsrc = ("dram__bytes_read.sum + dram__bytes_write.sum of ncu --set full captures at this workload: FM_OWN launch "
+                "(profiles/r01_final_factor_own_ncu.txt) + one factor-streaming sweep (profiles/r01_final_solve_own_ncu.txt)")
+    achieved = flops / (fac_ms * 1e-3) / 1e12
+    return dict(bound="tensor", kernel=kernel, achieved=achieved, peak=FP64_DMMA_PEAK_TFLOPS, unit="TFLOP/s",
+                frac=achieved / FP64_DMMA_PEAK_TFLOPS,
+                peak_source="measured FP64 DMMA m8n8k4 rate on this pool's B200 (profiles/r01_fp64_peak_ubench.txt); "
+                            "MEASURED_PEAKS.json holds only bf16/HBM peaks: " + peak_src,
+                traffic=traffic, traffic_source=tsrc, algorithmic_flops_per_launch=flops,
+                banded_count_flops_per_launch=band_flops, banded_count_frac=band_flops / (fac_ms * 1e-3) / 1e12 / FP64_DMMA_PEAK_TFLOPS,
+                algorithmic_bytes_per_launch=fbytes, hbm_achieved_gbs=fbytes / (fac_ms * 1e-3) / 1e9, hbm_peak_gbs=peaks.get("hbm_gbs"),
+                avg_launch_ms=fac_ms, launches_timed=factor_n, share_of_step=fac_ms / step_ms,
+                ordering="nested dissection (multifrontal)" if mf else "band, short axis fastest, two halves per system")
+
+
+def rel_diff(a, b):
+    return float(np.abs(np.asarray(a) - np.asarray(b)).max() / max(1e-300, np.abs(np.asarray(b)).max()))
+
+
+def run_cfg2(args, D, local_rank):
+    """Weak scaling: one chain of the cfg2 workload per GPU."""
+    from hmcmt2d_b200 import api, synthetic
+    rank, world = D.rank, D.world
+    mesh, data, inv, prior = build_problem_gpu(WORKLOAD, local_rank)
+    pl = api.Plan(mesh, data, inv, prior, nChains=1, device=local_rank)
+    rng = np.random.default_rng(100 + rank)
+    m0 = synthetic.stress_model(inv, seed=1 + rank)            # chains differ per GPU (seeds 1..N, cfg3)
+    p0 = np.clip(rng.standard_normal(len(m0)), -2.5, 2.5)
+    dt = prior.dt
+    K, W = args.steps, max(3, args.warmup)
+    step = host_stepper(lambda m: (lambda r: (r[0], float(r[1][0]), r[2][0]))(pl.forward_gradient(m)), inv, prior, m0, dt)
+
+    # ---------------- validation (untimed): 3 device-resident steps vs 3 host-loop steps from the same state ----------------
+    pl.set_state(m0, p0, m0)
+    pl.leapfrog_steps_device(dt, 3)
+    status3 = pl.status()
+    md3, pd3 = pl.get_state()
+    m, p = m0.copy(), p0.copy()
+    for _ in range(3):
+        m, p, _ = step(m, p)
+    short_diff = max(rel_diff(md3[0], m), rel_diff(pd3[0], p))
+
+    # ---------------- device-resident arm (`value`) ----------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    pl.set_state(m0, p0, m0)
+    pl.leapfrog_steps_device(dt, W)
+    pl.sync()
+    pl.kernel_time(reset=True)
+    launches0 = pl.info(10)
+    D.barrier()
+    sampler.mark()
+    pl.timer_start()
+    pl.leapfrog_steps_device(dt, K)
+    ms = pl.timer_stop()
+    D.barrier()
+    clocks = sampler.stop()
+    launches = pl.info(10) - launches0
+    factor_ms, factor_n = pl.kernel_time(reset=True)
+    status = pl.status()                                       # device error flags of the whole timed loop
+    m_dev, p_dev = pl.get_state()
+    ms = D.max(ms)
+    value = world * K / (ms * 1e-3)
+
+    # ---------------- end-to-end arm through the host-buffer C ABI ----------------
     m, p = m0.copy(), p0.copy()
     for _ in range(W):
-        m, p, _ = host_step(m, p)
-    barrier()
+        m, p, _ = step(m, p)
+    D.barrier()
     t0 = time.perf_counter()
     for _ in range(K):
-        m, p, phi = host_step(m, p)
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    barrier()
+        m, p, phi = step(m, p)
+    D.torch.cuda.synchronize()
+    e2e_s = D.max(time.perf_counter() - t0)
+    D.barrier()
     e2e_value = world * K / e2e_s
     h2d = pl.nAC * 8
     d2h = pl.nData * 16 + 8 + pl.nAC * 8
+    # both arms integrated W+K steps from (m0, p0): their end states agree up to the round-off the dynamics amplify
+    final_diff = max(rel_diff(m_dev[0], m), rel_diff(p_dev[0], p))
+    finite = bool(np.isfinite(m_dev).all() and np.isfinite(p_dev).all() and np.isfinite(m).all() and np.isfinite(phi))
+    validated = bool(status == 0 and status3 == 0 and finite and short_diff < 1e-9 and final_diff < 1e-5)
+    validated = bool(D.max(0.0 if validated else 1.0) == 0.0)
 
-    # ---------------- roofline of the dominant kernel (band_factor_kernel) ----------------
     peaks, peak_src = load_peaks()
-    N, b, nsys = pl.info(0), pl.info(4), pl.info(7)
-    # algorithmic work per launch: factor 4 N b^2 real flops per system + the fused forward
-    # elimination / back-substitution 16 N b ; bytes: factor written once + read once by the fused back-substitution
-    flops_launch = (4.0 * N * b * b + 16.0 * N * b) * nsys
-    bytes_launch = 2.0 * 16.0 * N * (b + 1) * nsys
-    fac_ms = factor_ms / max(1, factor_n)
-    achieved = flops_launch / (fac_ms * 1e-3) / 1e12
-    roofline = dict(bound="tensor", kernel="factorisation of the 60 systems = band_factor_kernel<14> FM_OWN + FM_SEP (FP64 DMMA.8x8x4 block LDL^T, "
-                    "fused assembly + forward elimination) + band_solve_kernel<14> SM_BACKZ_OWN (its back-substitution), timed as one unit",
-                    achieved=achieved, peak=FP64_DMMA_PEAK_TFLOPS, unit="TFLOP/s", frac=achieved / FP64_DMMA_PEAK_TFLOPS,
-                    peak_source="measured FP64 DMMA m8n8k4 rate on this pool's B200 (profiles/r01_fp64_peak_ubench.txt); "
-                                "MEASURED_PEAKS.json holds only bf16/HBM peaks: " + peak_src,
-                    traffic=NCU_FACTOR_DRAM_BYTES, traffic_source="dram__bytes_read.sum + dram__bytes_write.sum of ncu --set full captures at this workload: FM_OWN launch "
-                                   "(profiles/r01_final_factor_own_ncu.txt) + one factor-streaming sweep (profiles/r01_final_solve_own_ncu.txt)",
-                    algorithmic_flops_per_launch=flops_launch, algorithmic_bytes_per_launch=bytes_launch,
-                    hbm_achieved_gbs=bytes_launch / (fac_ms * 1e-3) / 1e9, hbm_peak_gbs=peaks.get("hbm_gbs"),
-                    avg_launch_ms=fac_ms, launches_timed=factor_n, share_of_step=fac_ms / (ms / K))
-
+    roofline = factor_roofline(pl, factor_ms, factor_n, ms / K, peaks, peak_src)
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=ms / K,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64 (complex128)", data="synthetic",
-                config=dict(WORKLOAD, l2_policy="inputs larger than L2: each step streams the 2.3 GB block-LDL^T factor of the "
-                                                "60 systems (written once, read 3x) through the 126 MB L2",
-                            parallelism=f"chains x{world} (replicas only, no data-path collective)"),
+                config=dict(WORKLOAD),
+                l2_policy=f"inputs larger than L2: each step streams the {pl.info(9) * pl.info(7) / 1e9:.2f} GB factor of the "
+                          f"{pl.info(7)} systems (written once, read 3x) through the 126 MB L2",
+                parallelism=f"chains x{world} (replicas only, no data-path collective)",
+                solver="multifrontal" if pl.info(11) else "band",
                 e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=1000 * e2e_s / K),
-                gpu_launches=int(launches), clocks=clocks, roofline=roofline)
-
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        v1, wall1 = cpu_steps_per_sec(1, 1)
-        line["cpu_baseline"] = dict(value=v1, unit=UNIT, cores=1, kind="port",
-                                    sample=f"1 of {WORKLOAD['nfreq']} frequencies (TE+TM forward+adjoint, {wall1:.2f} s) on one host core, "
-                                           f"extrapolated x{WORKLOAD['nfreq']}; restated CPU path (oracle, SciPy SuperLU), not MUMPS. "
-                                           f"All-core figure: run `bench.py --impl reference` ({cores} cores on this box)")
-    if rank == 0:
-        print(json.dumps(line), flush=True)
+                gpu_launches=int(launches), clocks=clocks, roofline=roofline, validated=validated,
+                validation=dict(device_status=int(status), states_finite=finite, three_step_device_vs_host_rel=short_diff,
+                                final_state_device_vs_host_rel=final_diff, steps_compared=W + K,
+                                observations="forward(true model) x (1 + 0.05 N), err = 0.05 |Z| (SURVEY.md 8d)"))
     pl.close()
-    if world > 1:
-        dist.destroy_process_group()
+    return line
 
 
-# ------------------------------------------------------------------------------------------------------
-# cfg4: one chain, frequencies sharded over the ranks, one NCCL all-reduce per step (strong scaling)
-
-def run_gpu_cfg4(args, rank, world, local_rank):
-    import torch
-    import torch.distributed as dist
+def run_cfg4(args, D, local_rank, nfreq=0):
+    """Strong scaling: one chain of the cfg4 workload, its (frequency, mode) systems sharded over the ranks."""
     from hmcmt2d_b200 import api, synthetic
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device — hmcmt2d_b200 has no CPU path")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
+    rank, world = D.rank, D.world
     cfg = dict(CFG4)
-    if args.nfreq:
-        cfg["nfreq"] = args.nfreq
-        cfg["workload"] += f" [reduced to {args.nfreq} frequencies]"
-    if world == 1 and cfg["nfreq"] > 48:
-        raise SystemExit("bench.py --config cfg4: the 120 factors (1.28 GB each) do not fit one GPU; use --gpus >= 2 or --nfreq <= 48")
-    mesh, data, inv, prior = build_problem(cfg)
+    if nfreq:
+        cfg["nfreq"] = nfreq
+        cfg["workload"] += f" [reduced to {nfreq} frequencies]"
+    mesh, data, inv, prior = synthetic.make_problem(cfg["ny"], cfg["nz"], cfg["nfreq"], cfg["nrx"])
     sp = api.FreqShardedPlan(mesh, data, inv, prior, rank, world, device=local_rank)
     pl = sp.plan
     m0 = synthetic.stress_model(inv, seed=1)                                   # the same chain state on every rank
     p0 = np.clip(np.random.default_rng(100).standard_normal(len(m0)), -2.5, 2.5)
     dt = prior.dt
-    K, W = args.steps, max(3, args.warmup)
+    K, W = max(3, min(args.steps, 10)), 3
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -371,76 +434,54 @@ def run_gpu_cfg4(args, rank, world, local_rank):
     sp.sync()
     pl.kernel_time(reset=True)
     launches0 = pl.info(10)
-    barrier()
+    D.barrier()
     sampler.mark()
     pl.timer_start()
     sp.leapfrog_steps_device(dt, K)
     ms = pl.timer_stop()
-    barrier()
+    D.barrier()
     clocks = sampler.stop()
     launches = pl.info(10) - launches0
     factor_ms, factor_n = pl.kernel_time(reset=True)
-    ms = max_over_ranks(ms)
+    status = pl.status()
+    ms = D.max(ms)
     value = K / (ms * 1e-3)
-    m_end, _ = sp.get_state()
-    drift_between_ranks = max_over_ranks(float(np.abs(m_end).sum())) - (-max_over_ranks(-float(np.abs(m_end).sum())))
+    m_end, p_end = sp.get_state()
+    csum = float(np.abs(m_end).sum())
+    spread = D.max(csum) - (-D.max(-csum))
 
     # end to end: compDataGradient through host buffers (H2D model, D2H data / misfit / gradient, all-reduce) + host leapfrog
-    lo, hi = np.log(prior.sigBounds[0]), np.log(prior.sigBounds[1])
-    Wm, beta = inv.Wm, prior.regParam
-
-    def host_step(m, p):
-        dm = dt * p
-        mx = np.abs(dm).max()
-        if mx > 3.0:
-            dm = dm / mx * 3.0
-        m = np.clip(m + dm, lo, hi)
-        pred, phi, g = sp.forward_gradient(m)
-        return m, p - dt * (g + beta * (Wm @ (m - m0))), phi
-
+    step = host_stepper(lambda m: sp.forward_gradient(m), inv, prior, m0, dt)
     Ke = max(1, min(K, 5))
     m, p = m0.copy(), p0.copy()
-    m, p, _ = host_step(m, p)
-    barrier()
+    m, p, _ = step(m, p)
+    D.barrier()
     t0 = time.perf_counter()
     for _ in range(Ke):
-        m, p, phi = host_step(m, p)
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    barrier()
+        m, p, phi = step(m, p)
+    D.torch.cuda.synchronize()
+    e2e_s = D.max(time.perf_counter() - t0)
+    D.barrier()
+    finite = bool(np.isfinite(m_end).all() and np.isfinite(p_end).all() and np.isfinite(phi))
+    validated = bool(D.max(0.0 if (status == 0 and finite and spread == 0.0) else 1.0) == 0.0)
 
-    N, b, nsys = pl.info(0), pl.info(4), pl.info(7)
-    flops_launch = (4.0 * N * b * b + 16.0 * N * b) * nsys
-    bytes_launch = 2.0 * 16.0 * N * (b + 1) * nsys
-    fac_ms = factor_ms / max(1, factor_n)
-    achieved = flops_launch / (fac_ms * 1e-3) / 1e12
     peaks, peak_src = load_peaks()
-    roofline = dict(bound="tensor", kernel="large-bandwidth factorisation of this rank's systems: bigband_panel_kernel + "
-                    "bigband_update_kernel (DMMA.8x8x4) per 32 columns + backward sweep (band_big.cuh)",
-                    achieved=achieved, peak=FP64_DMMA_PEAK_TFLOPS, unit="TFLOP/s", frac=achieved / FP64_DMMA_PEAK_TFLOPS,
-                    peak_source="measured FP64 DMMA m8n8k4 rate on this pool's B200 (profiles/r01_fp64_peak_ubench.txt); " + peak_src,
-                    traffic=None, algorithmic_flops_per_launch=flops_launch, algorithmic_bytes_per_launch=bytes_launch,
-                    hbm_achieved_gbs=bytes_launch / (fac_ms * 1e-3) / 1e9, hbm_peak_gbs=peaks.get("hbm_gbs"),
-                    avg_launch_ms=fac_ms, launches_timed=factor_n, share_of_step=fac_ms / (ms / K),
-                    note="latency-bound: ~7.5k stream-ordered panel/update launch pairs per factorisation")
+    roofline = factor_roofline(pl, factor_ms, factor_n, ms / K, peaks, peak_src)
+    nsys = int(pl.info(7))
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=ms / K, higher_is_better=True,
-                scaling="strong", vs_baseline=None, dtype="f64 (complex128)", data="synthetic",
-                config=dict(cfg, systems_per_gpu=int(nsys), l2_policy="inputs larger than L2: each rank streams its 1.28 GB-per-system factors",
-                            parallelism=f"frequencies x{world} (NCCL sum-all-reduce of [gdata | phi_d], {8 * (pl.nAC + 1)} B per step)",
-                            state_spread_between_ranks=drift_between_ranks),
+                scaling="strong", vs_baseline=None, dtype="f64 (complex128)", data="synthetic", config=cfg,
+                systems_per_gpu=nsys, factor_gb_per_gpu=pl.info(9) * nsys / 1e9,
+                l2_policy="inputs larger than L2: each rank streams the multifrontal factors of its systems",
+                parallelism=(f"(frequency, mode) systems x{world}; one sum-all-reduce of [gdata | phi_d] = {8 * (pl.nAC + 1)} B per step, "
+                             + ("ncclAllReduce issued by the library on its own stream" if sp.in_library_nccl else
+                                "single GPU: no exchange" if world == 1 else "torch.distributed all_reduce")),
+                state_spread_between_ranks=spread, solver="multifrontal" if pl.info(11) else "band",
                 e2e=dict(value=Ke / e2e_s, unit=UNIT, h2d_bytes_per_step=pl.nAC * 8, d2h_bytes_per_step=pl.nData * 16 + 8 + pl.nAC * 8,
                          ms_per_step=1000 * e2e_s / Ke, steps=Ke),
-                gpu_launches=int(launches), clocks=clocks, roofline=roofline)
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v1, wall1 = cpu_steps_per_sec(1, 1, cfg=cfg)
-        line["cpu_baseline"] = dict(value=v1, unit=UNIT, cores=1, kind="port",
-                                    sample=f"1 of {cfg['nfreq']} frequencies (TE+TM forward+adjoint, {wall1:.1f} s) on one host core, extrapolated; "
-                                           "matrix-free restatement (the reference's dense dBC needs 8.4 GB per system at this size)")
-    if rank == 0:
-        print(json.dumps(line), flush=True)
+                gpu_launches=int(launches), clocks=clocks, roofline=roofline, validated=validated,
+                validation=dict(device_status=int(status), states_finite=finite, observations="analytic half-space + 5 % noise"))
     sp.close()
-    if world > 1:
-        dist.destroy_process_group()
+    return line
 
 
 def main():
@@ -450,6 +491,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong-scaling", action="store_true", help="skip the cfg4 record appended to the cfg2 line")
     ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg4"])
     ap.add_argument("--nfreq", type=int, default=0, help="cfg4 only: reduced number of frequencies (testing)")
     args = ap.parse_args()
@@ -464,11 +506,28 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                "--master-port", "29511", os.path.abspath(__file__), "--gpus", str(args.gpus), "--steps", str(args.steps),
                "--warmup", str(args.warmup), "--config", args.config, "--nfreq", str(args.nfreq)]
+        cmd += ["--no-strong-scaling"] if args.no_strong_scaling else []
         raise SystemExit(subprocess.call(cmd))
+    D = Dist(rank, world, local_rank)
     if args.config == "cfg4":
-        run_gpu_cfg4(args, rank, world, local_rank)
-        return
-    run_gpu(args, rank, world, local_rank)
+        line = run_cfg4(args, D, local_rank, args.nfreq)
+    else:
+        line = run_cfg2(args, D, local_rank)
+        if not args.no_strong_scaling:
+            try:
+                line["strong_scaling"] = run_cfg4(args, D, local_rank, args.nfreq)
+            except Exception as e:                                   # never lose the headline line to the second workload
+                line["strong_scaling"] = dict(error=repr(e))
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cfg = line["config"]
+        v1, wall1 = cpu_one_core_sample(cfg)
+        line["cpu_baseline"] = dict(value=v1, unit=UNIT, cores=1, kind="port",
+                                    sample=f"1 of {cfg['nfreq']} frequencies (TE+TM forward+adjoint, {wall1:.2f} s) on one host core, "
+                                           f"multiplied by {cfg['nfreq']}; restated CPU path (oracle, SciPy SuperLU symmetric-mode MMD), not MUMPS. "
+                                           f"All-core figure: `bench.py --impl reference` ({os.cpu_count()} cores on this box)")
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    D.close()
 
 
 if __name__ == "__main__":

@@ -353,17 +353,59 @@ def shard_frequencies(mtData: MTData, invParam: InvDataModel, rank: int, world: 
     return sub, inv, rows
 
 
-class FreqShardedPlan:
-    """One rank's share of a frequency-sharded problem.  `group` is a torch.distributed process group (NCCL on GPUs); the
-    only data-path collective is one sum-all-reduce of [gdata | phi_d] per evaluation."""
+def shard_systems(mtData: MTData, invParam: InvDataModel, rank: int, world: int):
+    """Balanced partition of the (frequency, mode) SYSTEMS: with an even number of ranks and a TE + TM survey the first half of
+    the ranks takes the TE systems and the second half the TM systems, frequencies round-robin inside each half (120 systems
+    over 8 ranks = 15 each at cfg4, instead of 8 / 7 frequencies x 2 modes).  Otherwise falls back to `shard_frequencies`.
+    -> (MTData of this rank, InvDataModel with its observation rows, `rows` = their positions in the full data vector)."""
+    two_modes = bool(mtData.compTE and mtData.compTM) and len(mtData.dataComp) == 2
+    if world < 2 or world % 2 or not two_modes:
+        return shard_frequencies(mtData, invParam, rank, world)
+    half = world // 2
+    mode = 0 if rank < half else 1                              # 0: ZXY (TE), 1: ZYX (TM)
+    nF = len(mtData.freqs)
+    mine = np.arange(rank % half, nF, half)
+    if len(mine) == 0:
+        raise ValueError(f"rank {rank} of {world} owns no system (nFreq = {nF})")
+    newid = np.zeros(nF + 1, dtype=np.int64)
+    newid[mine + 1] = np.arange(1, len(mine) + 1)
+    fid, did = np.asarray(mtData.freqID), np.asarray(mtData.dtID)
+    rows = np.nonzero((newid[fid] > 0) & (did == mode + 1))[0]
+    nRx, nDt = np.asarray(mtData.rxLoc).shape[0], len(mtData.dataComp)
+    mask = np.asarray(mtData.dataID, dtype=bool).reshape(nF, nRx, nDt)[mine][:, :, mode].reshape(-1)
+    sub = MTData(np.array(mtData.rxLoc), np.array(mtData.freqs)[mine], mtData.dataType, [mtData.dataComp[mode]],
+                 np.asarray(mtData.rxID)[rows], newid[fid[rows]], np.ones(len(rows), dtype=np.int64), mask, mode == 0, mode == 1)
+    dataW = np.asarray(invParam.dataW)[rows]
+    inv = InvDataModel(np.asarray(invParam.obsData)[rows], dataW, np.array(invParam.strModel), np.array(invParam.refModel),
+                       invParam.activeCell, np.array(invParam.bgModel), invParam.Wm, 1.0 / dataW)
+    return sub, inv, rows
 
-    def __init__(self, mtMesh, mtData, invParam, hmcprior, rank: int, world: int, device: int = 0, group=None):
+
+class FreqShardedPlan:
+    """One rank's share of a system-sharded problem.  `group` is a torch.distributed process group used for the
+    plumbing (rendezvous, host-buffer evaluations); the data-path collective of the device-resident leapfrog steps — one
+    sum-all-reduce of [gdata | phi_d] per step — is issued by the library itself through NCCL on the plan's stream when the
+    group's backend is NCCL (`in_library_nccl`), else by torch.distributed on the exchange buffer."""
+
+    def __init__(self, mtMesh, mtData, invParam, hmcprior, rank: int, world: int, device: int = 0, group=None, balance="systems"):
         self.rank, self.world, self.group = int(rank), int(world), group
         self.nDataFull = len(np.asarray(invParam.obsData))
-        sub, inv, self.rows = shard_frequencies(mtData, invParam, rank, world)
+        shard = shard_systems if balance == "systems" else shard_frequencies
+        sub, inv, self.rows = shard(mtData, invParam, rank, world)
         self.plan = Plan(mtMesh, sub, inv, hmcprior, nChains=1, device=device)
         self.nAC, self.device = self.plan.nAC, int(device)
         self._xt = None
+        self.in_library_nccl = False
+        if self.world > 1:
+            import torch.distributed as dist
+            if dist.is_initialized() and dist.get_backend(group) == "nccl":
+                uid = C.create_string_buffer(128)
+                if self.rank == 0:
+                    _lib.check(self.plan.L.hmcmt_nccl_unique_id(uid), "hmcmt_nccl_unique_id")
+                box = [uid.raw]
+                dist.broadcast_object_list(box, src=0, group=group)
+                _lib.check(self.plan.L.hmcmt_nccl_init(self.plan.h, box[0], self.rank, self.world), "hmcmt_nccl_init")
+                self.in_library_nccl = True
 
     # host-buffer evaluation: compDataGradient over all frequencies
     def forward_gradient(self, m):
@@ -382,7 +424,7 @@ class FreqShardedPlan:
         nAC = self.nAC
         return packed[nAC + 1:].view(np.complex128), float(packed[nAC]), packed[:nAC]
 
-    # device-resident leapfrog steps with one NCCL all-reduce per step
+    # device-resident leapfrog steps with one all-reduce per step
     def _exchange_tensor(self):
         import torch
         if self._xt is None:
@@ -394,15 +436,20 @@ class FreqShardedPlan:
         return self._xt
 
     def leapfrog_steps_device(self, dt, nsteps):
+        if self.world == 1:
+            self.plan.leapfrog_steps_device(dt, nsteps)
+            return
+        if self.in_library_nccl:
+            _lib.check(self.plan.L.hmcmt_leapfrog_steps_sharded(self.plan.h, float(dt), int(nsteps)), "hmcmt_leapfrog_steps_sharded")
+            return
         import torch
         import torch.distributed as dist
-        xt = self._exchange_tensor() if self.world > 1 else None
+        xt = self._exchange_tensor()
         for _ in range(int(nsteps)):
             self.plan.step_partial(dt)
-            if self.world > 1:
-                self.plan.sync()                                   # the plan's stream is not torch's
-                dist.all_reduce(xt, op=dist.ReduceOp.SUM, group=self.group)
-                torch.cuda.current_stream(self.device).synchronize()
+            self.plan.sync()                                   # the plan's stream is not torch's
+            dist.all_reduce(xt, op=dist.ReduceOp.SUM, group=self.group)
+            torch.cuda.current_stream(self.device).synchronize()
             self.plan.step_finish(dt)
 
     def set_state(self, m=None, p=None, mref=None):

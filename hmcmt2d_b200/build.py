@@ -51,7 +51,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 sys.stderr.write(res.stderr)
     objs = [_obj(s) for s in SOURCES]
     if todo or _newer(LIB, objs):
-        res = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs, capture_output=True, text=True)
+        res = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-ldl"], capture_output=True, text=True)
         if res.returncode != 0:
             sys.stderr.write(res.stdout + res.stderr)
             raise RuntimeError("nvcc failed linking libhmcmt_b200.so")

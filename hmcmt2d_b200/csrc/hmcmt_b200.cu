@@ -1,5 +1,8 @@
 // libhmcmt_b200.so — plan, step orchestration and the Level-2 C ABI (include/hmcmt_b200.h).
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -72,6 +75,9 @@ struct hmcmt_plan {
     // wide meshes (half-bandwidth > 104): nested-dissection multifrontal solver (mf_solver.cuh) instead of the band kernels
     mf::Solver* mfs = nullptr;
     DevBuf<mf::MtValSys> mfSys;
+    // frequency-sharded steps: NCCL communicator over the ranks that share this chain (hmcmt_nccl_init)
+    ncclComm_t comm = nullptr;
+    int commWorld = 1;
     // pinned staging for the host-buffer entry points
     double* pin = nullptr;
     size_t pinBytes = 0;
@@ -478,6 +484,38 @@ int drift(hmcmt_plan* pl, double dt) {
 
 }  // namespace
 
+// ---- NCCL inside the library: the sum over the ranks' frequency shards is one ncclAllReduce on the plan's own
+// stream, between the contraction and the kick — no host round trip, no PyTorch on the data path.  libnccl is resolved at run
+// time (dlopen by SONAME: a process that already loaded NCCL, e.g. through torch.distributed, shares that copy).
+namespace {
+struct NcclApi {
+    void* handle = nullptr;
+    decltype(&ncclGetUniqueId) getUniqueId = nullptr;
+    decltype(&ncclCommInitRank) commInitRank = nullptr;
+    decltype(&ncclAllReduce) allReduce = nullptr;
+    decltype(&ncclCommDestroy) commDestroy = nullptr;
+    decltype(&ncclGetErrorString) getErrorString = nullptr;
+};
+NcclApi* nccl_api() {
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        api.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (api.handle) {
+            api.getUniqueId = (decltype(api.getUniqueId))dlsym(api.handle, "ncclGetUniqueId");
+            api.commInitRank = (decltype(api.commInitRank))dlsym(api.handle, "ncclCommInitRank");
+            api.allReduce = (decltype(api.allReduce))dlsym(api.handle, "ncclAllReduce");
+            api.commDestroy = (decltype(api.commDestroy))dlsym(api.handle, "ncclCommDestroy");
+            api.getErrorString = (decltype(api.getErrorString))dlsym(api.handle, "ncclGetErrorString");
+        }
+    }
+    const bool ok = api.handle && api.getUniqueId && api.commInitRank && api.allReduce && api.commDestroy;
+    if (!ok) fprintf(stderr, "[hmcmt_b200] libnccl.so.2 could not be loaded: %s\n", api.handle ? "missing symbols" : dlerror());
+    return ok ? &api : nullptr;
+}
+}  // namespace
+
 extern "C" {
 
 const char* hmcmt_version(void) { return "hmcmt_b200 0.1 (sm_100a; DMMA.8x8x4 tile-window band LDL^T; no CPU fallback)"; }
@@ -718,6 +756,11 @@ int hmcmt_plan_create(const hmcmt_problem* pr, hmcmt_plan** out) {
 void hmcmt_destroy(hmcmt_plan* pl) {
     if (!pl) return;
     cudaSetDevice(pl->device);
+    if (pl->comm) {
+        if (pl->stream) cudaStreamSynchronize(pl->stream);
+        if (NcclApi* a = nccl_api()) a->commDestroy(pl->comm);
+        pl->comm = nullptr;
+    }
     if (pl->stream) { cudaStreamSynchronize(pl->stream); cudaStreamDestroy(pl->stream); }
     if (pl->side) { cudaStreamSynchronize(pl->side); cudaStreamDestroy(pl->side); }
     if (pl->evFork) cudaEventDestroy(pl->evFork);
@@ -988,6 +1031,55 @@ int hmcmt_leapfrog_steps_device(hmcmt_plan* pl, double dt, int32_t nsteps) {
         if (rc) return rc;
         k_kick<<<pl->nChains, 1024, 0, pl->stream>>>(pl->nAC, dt, pl->gtotal.p, pl->p.p);
         LAUNCH_CHECK(pl);
+    }
+    return kOk;
+}
+
+int hmcmt_nccl_unique_id(char* out128) {
+    NcclApi* a = nccl_api();
+    if (!a || !out128) return kErrArg;
+    ncclUniqueId id;
+    if (a->getUniqueId(&id) != ncclSuccess) return kErrCuda;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    std::memcpy(out128, &id, 128);
+    return kOk;
+}
+
+int hmcmt_nccl_init(hmcmt_plan* pl, const char* id128, int32_t rank, int32_t world) {
+    NcclApi* a = nccl_api();
+    if (!a || !pl || !id128 || world < 1 || rank < 0 || rank >= world) return kErrArg;
+    HMCMT_CUDA_TRY(cudaSetDevice(pl->device));
+    if (pl->comm) { a->commDestroy(pl->comm); pl->comm = nullptr; }
+    ncclUniqueId id;
+    std::memcpy(&id, id128, 128);
+    ncclResult_t r = a->commInitRank(&pl->comm, world, id, rank);
+    if (r != ncclSuccess) {
+        fprintf(stderr, "[hmcmt_b200] ncclCommInitRank failed: %s\n", a->getErrorString ? a->getErrorString(r) : "?");
+        pl->comm = nullptr;
+        return kErrCuda;
+    }
+    pl->commWorld = world;
+    return kOk;
+}
+
+// nsteps leapfrog steps of a frequency-sharded chain, entirely enqueued on the plan's stream:
+//   drift + reflect, forward + adjoint over THIS rank's systems, [gdata | phi_d] packed, ncclAllReduce(SUM), prior gradient, kick.
+int hmcmt_leapfrog_steps_sharded(hmcmt_plan* pl, double dt, int32_t nsteps) {
+    if (!pl || nsteps < 0) return kErrArg;
+    NcclApi* a = pl->comm ? nccl_api() : nullptr;
+    if (!a) {
+        fprintf(stderr, "[hmcmt_b200] hmcmt_leapfrog_steps_sharded needs hmcmt_nccl_init first\n");
+        return kErrArg;
+    }
+    HMCMT_CUDA_TRY(cudaSetDevice(pl->device));
+    const size_t count = (size_t)pl->nChains * (pl->nAC + 1);
+    for (int k = 0; k < nsteps; ++k) {
+        int rc = hmcmt_step_partial(pl, dt);
+        if (rc) return rc;
+        if (a->allReduce(pl->xbuf.p, pl->xbuf.p, count, ncclFloat64, ncclSum, pl->comm, pl->stream) != ncclSuccess) return kErrCuda;
+        ++pl->launches;
+        rc = hmcmt_step_finish(pl, dt);
+        if (rc) return rc;
     }
     return kOk;
 }

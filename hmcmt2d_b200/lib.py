@@ -73,6 +73,9 @@ def load() -> C.CDLL:
     lib.hmcmt_exchange_buffer.argtypes = [vp, C.POINTER(vp), _i64p]
     lib.hmcmt_step_finish.argtypes = [vp, C.c_double]
     lib.hmcmt_sync.argtypes = [vp]
+    lib.hmcmt_nccl_unique_id.argtypes = [C.c_char_p]
+    lib.hmcmt_nccl_init.argtypes = [vp, C.c_char_p, C.c_int32, C.c_int32]
+    lib.hmcmt_leapfrog_steps_sharded.argtypes = [vp, C.c_double, C.c_int32]
     lib.hmcmt_timer_start.argtypes = [vp]
     lib.hmcmt_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
     lib.hmcmt_kernel_time.argtypes = [vp, C.c_int, C.POINTER(C.c_float), _i64p]
@@ -105,7 +108,8 @@ EXPORTED_SYMBOLS = [
     "hmcmt_plan_create", "hmcmt_destroy", "hmcmt_plan_info", "hmcmt_forward", "hmcmt_forward_sigma", "hmcmt_jtvec",
     "hmcmt_forward_gradient", "hmcmt_status", "hmcmt_set_response_kind", "hmcmt_get_responses",
     "hmcmt_set_state", "hmcmt_get_state", "hmcmt_leapfrog_trajectory", "hmcmt_leapfrog_steps_device", "hmcmt_sync",
-    "hmcmt_step_partial", "hmcmt_exchange_buffer", "hmcmt_step_finish",
+    "hmcmt_step_partial", "hmcmt_exchange_buffer", "hmcmt_step_finish", "hmcmt_nccl_unique_id", "hmcmt_nccl_init",
+    "hmcmt_leapfrog_steps_sharded",
     "hmcmt_timer_start", "hmcmt_timer_stop", "hmcmt_kernel_time", "hmcmt_run_chain", "hmcmt_export_system", "hmcmt_version",
 ]
 

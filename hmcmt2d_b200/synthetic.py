@@ -78,3 +78,11 @@ def stress_model(inv: InvDataModel, seed: int = 1) -> np.ndarray:
     """Evaluation model for timing: ln sigma = ln 0.01 + 0.7 N(0,1) i.i.d. per earth cell."""
     rng = np.random.default_rng(seed)
     return np.log(0.01) + 0.7 * rng.standard_normal(len(inv.strModel))
+
+
+def true_model_data(data: MTData, pred_true, noise: float = 0.05, seed: int = 7):
+    """Observations of SURVEY.md 8(d): data = forward(true model) (1 + 0.05 N), err = 0.05 |Z|.  `pred_true` is the forward
+    response of `true_model(mesh)` in the data ordering, computed by whichever engine the caller runs."""
+    rng = np.random.default_rng(seed)
+    z = np.asarray(pred_true)
+    return z * (1.0 + noise * rng.standard_normal(len(z))), noise * np.abs(z)

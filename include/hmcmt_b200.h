@@ -157,6 +157,16 @@ int hmcmt_leapfrog_steps_device(hmcmt_plan* plan, double dt, int32_t nsteps);
 int hmcmt_step_partial(hmcmt_plan* plan, double dt);
 int hmcmt_exchange_buffer(hmcmt_plan* plan, void** device_ptr, int64_t* count);
 int hmcmt_step_finish(hmcmt_plan* plan, double dt);
+/* The same step with the exchange inside the library: NCCL over NVLink / NVSwitch on the plan's own stream (no host round
+ * trip, no framework on the data path).  libnccl.so.2 is resolved at run time (dlopen by SONAME, so a process that already
+ * loaded NCCL shares that copy).
+ *   hmcmt_nccl_unique_id          rank 0: 128-byte ncclUniqueId, to be broadcast to the other ranks by the caller's own means
+ *   hmcmt_nccl_init               every rank: communicator of `world` ranks bound to this plan's device
+ *   hmcmt_leapfrog_steps_sharded  nsteps x { drift, forward + adjoint over this rank's systems, ncclAllReduce(SUM) of
+ *                                 [gdata | phi_d], prior gradient, kick }, enqueued without synchronisation */
+int hmcmt_nccl_unique_id(char* out128);
+int hmcmt_nccl_init(hmcmt_plan* plan, const char* id128, int32_t rank, int32_t world);
+int hmcmt_leapfrog_steps_sharded(hmcmt_plan* plan, double dt, int32_t nsteps);
 /* blocks until all work queued on the plan's stream has finished */
 int hmcmt_sync(hmcmt_plan* plan);
 /* Device error flags of everything queued so far (synchronises): 0, or -10 (a singular / non-finite pivot block in some

@@ -50,7 +50,7 @@ def _worker(rank, world, port):
     try:
         mesh, data, inv, prior = _problem()
         m = np.linspace(-5.0, -4.0, len(inv.strModel))
-        sp = api.FreqShardedPlan(mesh, data, inv, prior, rank, world)
+        sp = api.FreqShardedPlan(mesh, data, inv, prior, rank, world, balance="frequencies")
         assert list(sp.plan.data.freqs) == list(data.freqs[rank::world])
         assert sp.plan.data.freqID.min() == 1 and sp.plan.data.freqID.max() == len(data.freqs[rank::world])
         pred, phi, g = sp.forward_gradient(m)
@@ -66,6 +66,46 @@ def _worker(rank, world, port):
 
 def test_frequency_shards_world2():
     mp.spawn(_worker, args=(2, _free_port()), nprocs=2, join=True)
+
+
+def _worker_systems(rank, world, port):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    real = api.Plan
+    api.Plan = _FakePlan
+    try:
+        mesh, data, inv, prior = _problem()
+        m = np.linspace(-5.0, -4.0, len(inv.strModel))
+        sp = api.FreqShardedPlan(mesh, data, inv, prior, rank, world)            # default: balanced (frequency, mode) systems
+        assert not sp.in_library_nccl                                             # gloo group: the exchange stays with torch.distributed
+        assert sp.plan.data.dataComp == [data.dataComp[rank]] and list(sp.plan.data.freqs) == list(data.freqs)
+        assert (sp.plan.data.dtID == 1).all() and len(sp.rows) == len(inv.obsData) // 2
+        pred, phi, g = sp.forward_gradient(m)
+        assert np.count_nonzero(pred) == len(inv.obsData)                         # every observation row filled by exactly one rank
+    finally:
+        api.Plan = real
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_system_shards_world2():
+    mp.spawn(_worker_systems, args=(2, _free_port()), nprocs=2, join=True)
+
+
+def test_system_partition_is_balanced_and_complete():
+    mesh, data, inv, prior = synthetic.make_problem(24, 20, 6, nRx=3)
+    for world in (2, 4, 6):
+        seen = np.zeros(len(inv.obsData), int)
+        counts = []
+        for rank in range(world):
+            sub, sinv, rows = api.shard_systems(data, inv, rank, world)
+            seen[rows] += 1
+            counts.append(len(sub.freqs) * len(sub.dataComp))
+            assert np.array_equal(sinv.obsData, inv.obsData[rows]) and len(sub.dataID) == len(sub.freqs) * 3
+            assert np.array_equal(sub.freqs[sub.freqID - 1], data.freqs[data.freqID[rows] - 1])
+        assert (seen == 1).all() and max(counts) - min(counts) <= (0 if 12 % world == 0 else 1)
+    sub, sinv, rows = api.shard_systems(data, inv, 1, 3)                          # odd world: frequency round-robin
+    assert list(sub.freqs) == list(data.freqs[1::3]) and len(sub.dataComp) == 2
 
 
 def test_partition_covers_every_observation_once():
