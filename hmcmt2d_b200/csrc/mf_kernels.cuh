@@ -45,15 +45,18 @@ struct Tables {
     int* status;            // [nsys]
     unsigned long long* prof;   // optional (HMCMT_MF_PROF=1): per-phase cycle totals of mf_small_kernel, thread 0 of every CTA
 };
-#define MF_PROF_MARK(slot) do { if (tb.prof && threadIdx.x == 0) { const long long _t = clock64(); atomicAdd(tb.prof + (slot), (unsigned long long)(_t - _t0)); _t0 = _t; } } while (0)
+#define MF_PROF_MARK(slot) do { if (tb.prof && threadIdx.x == 0) { const long long _t = clock64(); atomicAdd(tb.prof + _pc * 8 + (slot), (unsigned long long)(_t - _t0)); _t0 = _t; } } while (0)
 
 // ------------------------------------------------------------------------------------------------------------------------
 // block sweep of the first npb pivot blocks of an nb x nb tile matrix held in shared memory (lower-triangle tiles, 128 doubles
-// each: [plane][8][8]; diagonal tiles full).  On return: pivot x pivot tiles hold -G, rest x pivot tiles hold M, rest x rest U.
+// each: [plane][8][8]; of a diagonal tile only the lower triangle is meaningful: it is always read mirrored).  On return: pivot x pivot tiles hold -G, rest x pivot tiles hold M, rest x rest U.
 template <int NW>
 __device__ __forceinline__ void mf_sweep(double* __restrict__ tiles, double* __restrict__ raw, double* __restrict__ mm,
-                                         double* __restrict__ nainv, int* __restrict__ fail, const int nb, const int npb) {
+                                         double* __restrict__ nainv, int* __restrict__ fail, const int nb, const int npb,
+                                         unsigned long long* __restrict__ prof = nullptr) {
     const int tid = threadIdx.x, lane = tid & 31;
+    long long _s0 = prof ? clock64() : 0;
+#define MF_SWEEP_MARK(slot) do { if (prof && tid == 0) { const long long _t = clock64(); atomicAdd(prof + (slot), (unsigned long long)(_t - _s0)); _s0 = _t; } } while (0)
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int g = lane >> 2, t = lane & 3;
     const int R = nb * 8;
@@ -66,10 +69,16 @@ __device__ __forceinline__ void mf_sweep(double* __restrict__ tiles, double* __r
         // (a) column block kb of the symmetric matrix as an operand panel: raw_I = A[I][kb]  (one tile per warp and trip)
         for (int I = warp; I < nb; I += NW) {
             double2 v01, v23;
-            if (I >= kb) {
+            if (I > kb) {
                 const double* src = tileP(I, kb) + cpl * 64 + crow * 8 + ckk * 4;
                 v01 = *reinterpret_cast<const double2*>(src);
                 v23 = *reinterpret_cast<const double2*>(src + 2);
+            } else if (I == kb) {          // diagonal tile: only its lower triangle is maintained -> mirrored read
+                const double* D = tileP(kb, kb) + cpl * 64;
+                const int c0 = ckk * 4;
+                auto sym = [&](int r, int c) { return r >= c ? D[r * 8 + c] : D[c * 8 + r]; };
+                v01 = make_double2(sym(crow, c0), sym(crow, c0 + 1));
+                v23 = make_double2(sym(crow, c0 + 2), sym(crow, c0 + 3));
             } else {
                 const double* src = tileP(kb, I) + cpl * 64 + (ckk * 4) * 8 + crow;
                 v01 = make_double2(src[0], src[8]);
@@ -84,9 +93,9 @@ __device__ __forceinline__ void mf_sweep(double* __restrict__ tiles, double* __r
         if (warp == 0) {
             __syncwarp();
             double* D = tileP(kb, kb);
-            const double2 vre = *reinterpret_cast<const double2*>(D + g * 8 + 2 * t);
-            const double2 vim = *reinterpret_cast<const double2*>(D + 64 + g * 8 + 2 * t);
-            cplx a0 = mk(vre.x, vim.x), a1 = mk(vre.y, vim.y);
+            auto symre = [&](int r, int c) { return r >= c ? D[r * 8 + c] : D[c * 8 + r]; };
+            auto symim = [&](int r, int c) { return r >= c ? D[64 + r * 8 + c] : D[64 + c * 8 + r]; };
+            cplx a0 = mk(symre(g, 2 * t), symim(g, 2 * t)), a1 = mk(symre(g, 2 * t + 1), symim(g, 2 * t + 1));
             bool bad = false;
             gj_invert8<true>(a0, a1, bad, g, t);
             if (__any_sync(0xffffffffu, bad) && lane == 0) *fail = 1;
@@ -94,7 +103,9 @@ __device__ __forceinline__ void mf_sweep(double* __restrict__ tiles, double* __r
             *reinterpret_cast<double2*>(nainv + ((0 * 2 + (j0 >> 2)) * 8 + g) * 4 + (j0 & 3)) = make_double2(-a0.x, -a1.x);
             *reinterpret_cast<double2*>(nainv + ((1 * 2 + (j0 >> 2)) * 8 + g) * 4 + (j0 & 3)) = make_double2(-a0.y, -a1.y);
         }
+        MF_SWEEP_MARK(0);
         __syncthreads();
+        MF_SWEEP_MARK(1);
         if (warp == 0) {       // the raw copy of the diagonal tile is complete: the tile itself may now take -P
             double* D = tileP(kb, kb);
             const int j0 = 2 * t;
@@ -122,9 +133,33 @@ __device__ __forceinline__ void mf_sweep(double* __restrict__ tiles, double* __r
             *reinterpret_cast<double2*>(opnd(mm, 1, t >> 1, r) + (t & 1) * 2) = make_double2(mim[0], mim[1]);
         }
         __syncthreads();
-        // (d) A[I][J] += m_I raw_J^T for I,J != kb ;  (e) column kb <- raw P = -m.   Lower tiles dealt round-robin to the warps.
+        MF_SWEEP_MARK(2);
+        // (d) A[I][J] += m_I raw_J^T for I,J != kb ;  (e) column kb <- raw P = -m.   Lower tiles dealt round-robin to the warps;
+        // trailing updates are issued two tiles at a time (16 independent DMMAs in flight: their latency is ~138 cycles).
+        auto upd_load = [&](double* T, double (&cre)[2], double (&cim)[2]) {
+            const double2 cr = *reinterpret_cast<const double2*>(T + g * 8 + 2 * t);
+            const double2 ci = *reinterpret_cast<const double2*>(T + 64 + g * 8 + 2 * t);
+            cre[0] = cr.x; cre[1] = cr.y; cim[0] = ci.x; cim[1] = ci.y;
+        };
+        auto upd_mma = [&](int I_, int J_, double (&cre)[2], double (&cim)[2], double (&t1)[2], double (&t2)[2]) {
+            const int ra = I_ * 8 + g, rb = J_ * 8 + g;
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+                const double are = opnd(mm, 0, kk, ra)[t], aim = opnd(mm, 1, kk, ra)[t];
+                const double bre = opnd(raw, 0, kk, rb)[t], bim = opnd(raw, 1, kk, rb)[t];
+                dmma884(cre, are, bre);
+                dmma884(cim, are, bim);
+                dmma884(t1, -aim, bim);
+                dmma884(t2, aim, bre);
+            }
+        };
+        auto upd_store = [&](double* T, const double (&cre)[2], const double (&cim)[2], const double (&t1)[2], const double (&t2)[2]) {
+            *reinterpret_cast<double2*>(T + g * 8 + 2 * t) = make_double2(cre[0] + t1[0], cre[1] + t1[1]);
+            *reinterpret_cast<double2*>(T + 64 + g * 8 + 2 * t) = make_double2(cim[0] + t2[0], cim[1] + t2[1]);
+        };
         int I = 0, J = warp;
         while (J > I) { J -= I + 1; ++I; }
+        int pI = -1, pJ = -1;          // pending trailing-update tile (waiting for a partner)
         for (int L = warp; L < nT; L += NW) {
             double* T = tileP(I, J);
             if (I == kb && J == kb) {
@@ -139,28 +174,33 @@ __device__ __forceinline__ void mf_sweep(double* __restrict__ tiles, double* __r
                     T[g * 8 + 2 * t + e] = -opnd(mm, 0, g >> 2, J * 8 + 2 * t + e)[g & 3];
                     T[64 + g * 8 + 2 * t + e] = -opnd(mm, 1, g >> 2, J * 8 + 2 * t + e)[g & 3];
                 }
+            } else if (pI < 0) {
+                pI = I; pJ = J;
             } else {
-                const double2 cr = *reinterpret_cast<const double2*>(T + g * 8 + 2 * t);
-                const double2 ci = *reinterpret_cast<const double2*>(T + 64 + g * 8 + 2 * t);
-                double cre[2] = {cr.x, cr.y}, cim[2] = {ci.x, ci.y}, t1[2] = {0.0, 0.0}, t2[2] = {0.0, 0.0};
-                const int ra = I * 8 + g, rb = J * 8 + g;
-#pragma unroll
-                for (int kk = 0; kk < 2; ++kk) {
-                    const double are = opnd(mm, 0, kk, ra)[t], aim = opnd(mm, 1, kk, ra)[t];
-                    const double bre = opnd(raw, 0, kk, rb)[t], bim = opnd(raw, 1, kk, rb)[t];
-                    dmma884(cre, are, bre);
-                    dmma884(cim, are, bim);
-                    dmma884(t1, -aim, bim);
-                    dmma884(t2, aim, bre);
-                }
-                *reinterpret_cast<double2*>(T + g * 8 + 2 * t) = make_double2(cre[0] + t1[0], cre[1] + t1[1]);
-                *reinterpret_cast<double2*>(T + 64 + g * 8 + 2 * t) = make_double2(cim[0] + t2[0], cim[1] + t2[1]);
+                double* T0 = tileP(pI, pJ);
+                double c0r[2], c0i[2], c1r[2], c1i[2], a1[2] = {0.0, 0.0}, a2[2] = {0.0, 0.0}, b1[2] = {0.0, 0.0}, b2[2] = {0.0, 0.0};
+                upd_load(T0, c0r, c0i);
+                upd_load(T, c1r, c1i);
+                upd_mma(pI, pJ, c0r, c0i, a1, a2);
+                upd_mma(I, J, c1r, c1i, b1, b2);
+                upd_store(T0, c0r, c0i, a1, a2);
+                upd_store(T, c1r, c1i, b1, b2);
+                pI = -1;
             }
             J += NW;
             while (J > I) { J -= I + 1; ++I; }
         }
+        if (pI >= 0) {
+            double* T0 = tileP(pI, pJ);
+            double c0r[2], c0i[2], a1[2] = {0.0, 0.0}, a2[2] = {0.0, 0.0};
+            upd_load(T0, c0r, c0i);
+            upd_mma(pI, pJ, c0r, c0i, a1, a2);
+            upd_store(T0, c0r, c0i, a1, a2);
+        }
         __syncthreads();
+        MF_SWEEP_MARK(3);
     }
+#undef MF_SWEEP_MARK
 }
 
 __host__ __device__ inline size_t mf_sweep_smem_bytes(int nb) {
@@ -178,15 +218,22 @@ __device__ __forceinline__ cplx mf_tile_get(const double* tiles, int a, int b) {
 // one 8x8 tile (shared memory, [plane][8][8]) -> k-grouped global matrix with ld rows at (row0, col0); executed by one warp:
 // lane = (chunk, row): chunk = (plane, column group of four), 32 contiguous bytes per lane, 256 per eight lanes.
 // TRANSPOSED: the tile holds the transposed block.  sign: +1 / -1.
-template <bool TRANSPOSED>
+// MODE 0: as stored, 1: transposed, 2: diagonal tile (lower triangle mirrored)
+template <int MODE>
 __device__ __forceinline__ void mf_store_tile(const double* __restrict__ T, double* __restrict__ dst, int ld, int row0, int col0,
                                               double sign, int lane) {
     const int pl = lane >> 4, cg = (lane >> 3) & 1, row = lane & 7;
     double2 v01, v23;
-    if (!TRANSPOSED) {
+    if (MODE == 0) {
         const double* src = T + pl * 64 + row * 8 + cg * 4;
         v01 = *reinterpret_cast<const double2*>(src);
         v23 = *reinterpret_cast<const double2*>(src + 2);
+    } else if (MODE == 2) {
+        const double* D = T + pl * 64;
+        const int c0 = cg * 4;
+        auto sym = [&](int r, int c) { return r >= c ? D[r * 8 + c] : D[c * 8 + r]; };
+        v01 = make_double2(sym(row, c0), sym(row, c0 + 1));
+        v23 = make_double2(sym(row, c0 + 2), sym(row, c0 + 3));
     } else {
         const double* src = T + pl * 64 + (cg * 4) * 8 + row;
         v01 = make_double2(src[0], src[8]);
@@ -214,7 +261,17 @@ mf_small_kernel(Tables tb, const int* __restrict__ list) {
     double* mm = raw + 16 * (size_t)fp;
     double* nainv = mm + 16 * (size_t)fp;
     int* fail = reinterpret_cast<int*>(nainv + 128);
+    constexpr int _pc = NW == 2 ? 0 : (NW == 4 ? 1 : (NW == 8 ? 2 : 3));      // profiler class
     long long _t0 = clock64();
+    // loads that do not depend on anything else are issued first: their latency hides behind the zeroing and the extend-add
+    const Chunk ch = tb.chunks[F.chunkPtr];
+    const cplx* vals = tb.vals + (size_t)sys * tb.valStride;
+    OrigEntry oe0{0, 0, -1};
+    cplx ov0 = mk(0.0, 0.0);
+    if (tid < F.nOrig) {
+        oe0 = tb.orig[F.origPtr + tid];
+        ov0 = oe0.src < 0 ? mk(1.0, 0.0) : vals[oe0.src];
+    }
     for (int i = tid; i < nT * 64; i += NT) reinterpret_cast<double2*>(tiles)[i] = make_double2(0.0, 0.0);
     if (tid == 0) *fail = 0;
     __syncthreads();
@@ -222,43 +279,57 @@ mf_small_kernel(Tables tb, const int* __restrict__ list) {
     auto addr = [&](int a, int b) {       // a >= b
         return tiles + (size_t)((a >> 3) * ((a >> 3) + 1) / 2 + (b >> 3)) * 128 + (a & 7) * 8 + (b & 7);
     };
-    // extend-add of the children's update matrices.  Up to two children are added in ONE pass with shared-memory atomics onto the
-    // zeroed tiles: 0 + a + b does not depend on the order, so the result stays deterministic; further children take a pass each.
+    // extend-add of the children's update matrices, one child at a time (entries of one child never collide: plain adds, fixed
+    // order -> deterministic).  The child's row map is staged in shared memory (the operand panel is still unused).
     const double* carena = tb.arena[(F.depth + 1) & 1] + (size_t)sys * tb.arenaStride[(F.depth + 1) & 1];
-    for (int c0 = 0; c0 < F.nChild; c0 += 2) {
-        const int nc = min(2, F.nChild - c0);
-        for (int c = c0; c < c0 + nc; ++c) {
-            const Front& C = tb.fronts[tb.children[F.childPtr + c]];
-            const int cu = C.u, cup = C.up;
-            const int ld = C.isBig ? C.sp + cup : cup, off = C.isBig ? C.sp : 0;
-            const double* U = carena + C.frontOff;
-            const int* rel = tb.rel + C.rowPtr;
-            const int ng = (cu + 3) >> 2;
-            for (int idx = tid; idx < ng * cup; idx += NT) {
-                const int jg = idx / cup, i = idx - jg * cup;
-                if (i >= cu || i < 4 * jg) continue;
-                const double* pr = U + kg_off(ld, off + i, off + 4 * jg, 0);
-                const double* pi = U + kg_off(ld, off + i, off + 4 * jg, 1);
-                const double2 r01 = *reinterpret_cast<const double2*>(pr), r23 = *reinterpret_cast<const double2*>(pr + 2);
-                const double2 i01 = *reinterpret_cast<const double2*>(pi), i23 = *reinterpret_cast<const double2*>(pi + 2);
-                const double re[4] = {r01.x, r01.y, r23.x, r23.y}, im[4] = {i01.x, i01.y, i23.x, i23.y};
-                const int ri = rel[i];
+    int* relS = reinterpret_cast<int*>(raw);
+    for (int c = 0; c < F.nChild; ++c) {
+        const Front& C = tb.fronts[tb.children[F.childPtr + c]];
+        const int cu = C.u, cup = C.up;
+        const int ld = C.isBig ? C.sp + cup : cup, off = C.isBig ? C.sp : 0;
+        const double* U = carena + C.frontOff;
+        const int* rel = tb.rel + C.rowPtr;
+        for (int i = tid; i < cu; i += NT) relS[i] = rel[i];
+        __syncthreads();
+        // work items = (block of eight columns, block of four rows): lane = (row, column), so that the 32 read-modify-writes of
+        // a warp fall into 4 x 8 patches of the tiles — consecutive shared-memory words, no bank conflicts (a 32-row x 1-column
+        // mapping hits 16-way conflicts: the tile rows are 64 bytes apart).  Each warp loads kBatch items before it scatters them.
+        const int nc8 = (cu + 7) >> 3, nr4 = (cu + 3) >> 2;
+        const int lr = lane >> 3, lc = lane & 7;
+        constexpr int kBatch = 4;
+        for (int j8 = 0; j8 < nc8; ++j8) {
+            const int j = 8 * j8 + lc;
+            const int rjc = relS[min(j, cu - 1)];
+            const double* ucol_r = U + kg_off(ld, off, off + j, 0);
+            const double* ucol_i = U + kg_off(ld, off, off + j, 1);
+            for (int r0 = 2 * j8 + warp * kBatch; r0 < nr4; r0 += NW * kBatch) {
+                double vr[kBatch], vi[kBatch];
+                int ii[kBatch];
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                    const int j = 4 * jg + jj;
-                    if (j > i) break;
-                    double* d = addr(ri, rel[j]);
-                    atomicAdd(d, re[jj]);
-                    atomicAdd(d + 64, im[jj]);
+                for (int bq = 0; bq < kBatch; ++bq) {
+                    const int i = 4 * (r0 + bq) + lr;
+                    ii[bq] = (r0 + bq < nr4 && i < cu && j <= i) ? i : -1;
+                    if (ii[bq] >= 0) { vr[bq] = ucol_r[4 * (size_t)i]; vi[bq] = ucol_i[4 * (size_t)i]; }
+                }
+#pragma unroll
+                for (int bq = 0; bq < kBatch; ++bq) {
+                    if (ii[bq] < 0) continue;
+                    double* d = addr(relS[ii[bq]], rjc);
+                    d[0] += vr[bq];
+                    d[64] += vi[bq];
                 }
             }
         }
         __syncthreads();
     }
     MF_PROF_MARK(2);
-    // original matrix entries of the pivot columns (added last: (a + b) + orig for every child order)
-    const cplx* vals = tb.vals + (size_t)sys * tb.valStride;
-    for (int e = tid; e < F.nOrig; e += NT) {
+    // original matrix entries of the pivot columns
+    if (tid < F.nOrig) {
+        double* d = addr(oe0.lrow, oe0.lcol);
+        d[0] += ov0.x;
+        d[64] += ov0.y;
+    }
+    for (int e = tid + NT; e < F.nOrig; e += NT) {
         const OrigEntry oe = tb.orig[F.origPtr + e];
         const cplx v = oe.src < 0 ? mk(1.0, 0.0) : vals[oe.src];
         double* d = addr(oe.lrow, oe.lcol);
@@ -267,22 +338,10 @@ mf_small_kernel(Tables tb, const int* __restrict__ list) {
     }
     __syncthreads();
     MF_PROF_MARK(1);
-    // diagonal tiles: mirror the lower triangle
-    for (int idx = tid; idx < nb * 64; idx += NT) {
-        const int I = idx >> 6, r = (idx >> 3) & 7, c = idx & 7;
-        if (c > r) {
-            double* T = tiles + (size_t)(I * (I + 1) / 2 + I) * 128;
-            T[r * 8 + c] = T[c * 8 + r];
-            T[64 + r * 8 + c] = T[64 + c * 8 + r];
-        }
-    }
-    __syncthreads();
-    MF_PROF_MARK(3);
-    mf_sweep<NW>(tiles, raw, mm, nainv, fail, nb, npb);
+    mf_sweep<NW>(tiles, raw, mm, nainv, fail, nb, npb, tb.prof ? tb.prof + 32 + _pc * 4 : nullptr);
     MF_PROF_MARK(4);
     if (tid == 0 && *fail) tb.status[sys] = kErrSingular;
     // outputs, tile by tile: G = -(pivot x pivot), M = update x pivot (factor arena), U = update x update (update arena, lower tiles)
-    const Chunk ch = tb.chunks[F.chunkPtr];
     double* fac = tb.fac + (size_t)sys * tb.facStride;
     const int sp = F.sp, up = F.up, nub = nb - npb;
     auto tileP = [&](int I, int J) { return tiles + (size_t)(I * (I + 1) / 2 + J) * 128; };
@@ -290,27 +349,28 @@ mf_small_kernel(Tables tb, const int* __restrict__ list) {
         double* G = fac + ch.gOff;
         for (int q = warp; q < npb * npb; q += NW) {
             const int I = q / npb, J = q - I * npb;
-            if (I >= J) mf_store_tile<false>(tileP(I, J), G, sp, I * 8, J * 8, -1.0, lane);
-            else mf_store_tile<true>(tileP(J, I), G, sp, I * 8, J * 8, -1.0, lane);
+            if (I > J) mf_store_tile<0>(tileP(I, J), G, sp, I * 8, J * 8, -1.0, lane);
+            else if (I == J) mf_store_tile<2>(tileP(I, I), G, sp, I * 8, I * 8, -1.0, lane);
+            else mf_store_tile<1>(tileP(J, I), G, sp, I * 8, J * 8, -1.0, lane);
         }
     }
     if (up > 0) {
         double* M = fac + ch.mOff;
         for (int q = warp; q < nub * npb; q += NW) {
             const int I = q / npb, J = q - I * npb;
-            mf_store_tile<false>(tileP(npb + I, J), M, up, I * 8, J * 8, 1.0, lane);
+            mf_store_tile<0>(tileP(npb + I, J), M, up, I * 8, J * 8, 1.0, lane);
         }
         double* U = tb.arena[F.depth & 1] + (size_t)sys * tb.arenaStride[F.depth & 1] + F.frontOff;
         int I = 0, J = warp;
         while (J > I) { J -= I + 1; ++I; }
         for (int L = warp; L < nub * (nub + 1) / 2; L += NW) {
-            mf_store_tile<false>(tileP(npb + I, npb + J), U, up, I * 8, J * 8, 1.0, lane);
+            mf_store_tile<0>(tileP(npb + I, npb + J), U, up, I * 8, J * 8, 1.0, lane);
             J += NW;
             while (J > I) { J -= I + 1; ++I; }
         }
     }
     MF_PROF_MARK(5);
-    if (tb.prof && tid == 0) { atomicAdd(tb.prof + 6, 1ull); atomicAdd(tb.prof + 7, (unsigned long long)npb); }
+    if (tb.prof && tid == 0) { atomicAdd(tb.prof + _pc * 8 + 6, 1ull); atomicAdd(tb.prof + _pc * 8 + 7, (unsigned long long)npb); }
 }
 
 // ------------------------------------------------------------------------------------------------------------------------
@@ -688,7 +748,7 @@ mf_bwd_kernel(Tables tb, SolveArgs sa, const int* __restrict__ list) {
 
 // Small fronts (single chunk, fp <= kSolveSmallMax): one WARP per (front, right-hand side), eight fronts per CTA, warp-level
 // synchronisation only.  list[blockIdx.x * 8 + warp] = front id.
-constexpr int kSolveSmallMax = 144;
+constexpr int kSolveSmallMax = 64;
 constexpr int kSolveWarpsPerCta = 8;
 __global__ void __launch_bounds__(kSolveWarpsPerCta * 32)
 mf_fwd_warp_kernel(Tables tb, SolveArgs sa, const int* __restrict__ list, int n) {
@@ -758,20 +818,25 @@ mf_bwd_warp_kernel(Tables tb, SolveArgs sa, const int* __restrict__ list, int n)
     const Chunk ch = tb.chunks[F.chunkPtr];
     const double* G = tb.fac + (size_t)sys * tb.facStride + ch.gOff;
     const double* M = tb.fac + (size_t)sys * tb.facStride + ch.mOff;
-    // x1[k] = sum_j G[j][k] w1[j] - sum_i M[i][k] x2[i] : one lane per k (no reduction; four lanes share a 32-byte sector)
-    for (int k0 = 0; k0 < sp; k0 += 32) {
-        const int k = k0 + lane;
+    // x1[k] = sum_j G[j][k] w1[j] - sum_i M[i][k] x2[i] : one lane per k (four lanes share a 32-byte sector); when the front has
+    // fewer than 32 pivots the rows are split over 32 / width sub-groups of lanes and combined with shuffles
+    const int width = sp <= 8 ? 8 : (sp <= 16 ? 16 : 32), nparts = 32 / width, part = lane / width, kl = lane - part * width;
+    for (int k0 = 0; k0 < sp; k0 += width) {
+        const int k = k0 + kl;
         cplx acc = mk(0.0, 0.0);
         if (k < sp) {
             const double* gr = G + kg_off(sp, 0, k, 0);
             const double* gi = G + kg_off(sp, 0, k, 1);
-            for (int j = 0; j < sp; ++j) cfma(acc, mk(gr[4 * j], gi[4 * j]), xf[j]);
+            for (int j = part; j < sp; j += nparts) cfma(acc, mk(gr[4 * j], gi[4 * j]), xf[j]);
             const double* mr = M + kg_off(up, 0, k, 0);
             const double* mi = M + kg_off(up, 0, k, 1);
-            for (int i = 0; i < up; ++i) cfma(acc, mk(-mr[4 * i], -mi[4 * i]), xf[sp + i]);
+            for (int i = part; i < up; i += nparts) cfma(acc, mk(-mr[4 * i], -mi[4 * i]), xf[sp + i]);
         }
-        __syncwarp();
-        if (k < sp) {
+        for (int off = width; off < 32; off <<= 1) {
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
+            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+        }
+        if (k < sp && part == 0) {
             v[cbp + k] = acc;
             if (k < fs) x[tb.pos2orig[cbp + k]] = acc;
         }

@@ -22,6 +22,7 @@ struct PerDeviceOnceMf {
     }
 };
 constexpr size_t kMaxSmem = 227 * 1024;
+constexpr int kSolveWarpMaxFp = 64;  // solves: warp-per-front kernels up to this front size
 constexpr int kTinyWarps = 2;       // warps per CTA for fronts with fp <= 48
 
 template <int NW>
@@ -55,13 +56,20 @@ Solver* Solver::create(Symbolic&& S, int nsys, int maxRhs, int64_t valCount, int
 
 Solver::~Solver() {
     if (d_prof) {
-        unsigned long long h[8] = {};
+        unsigned long long h[48] = {};
         cudaDeviceSynchronize();
         cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost);
-        if (h[6])
-            fprintf(stderr, "[hmcmt_b200] mf_small_kernel phases, cycles per front (%llu fronts, %.2f pivot blocks each): zero %.0f  orig %.0f  children %.0f  "
-                    "mirror %.0f  sweep %.0f  output %.0f\n", h[6], (double)h[7] / h[6], (double)h[0] / h[6], (double)h[1] / h[6], (double)h[2] / h[6],
-                    (double)h[3] / h[6], (double)h[4] / h[6], (double)h[5] / h[6]);
+        for (int c = 0; c < 4; ++c) {
+            const unsigned long long* q = h + 8 * c;
+            if (q[6])
+                fprintf(stderr, "[hmcmt_b200] mf_small_kernel<%d> cycles per front (%llu fronts, %.2f pivot blocks each): zero %.0f  orig %.0f  "
+                        "children %.0f  mirror %.0f  sweep %.0f  output %.0f\n", 2 << c, q[6], (double)q[7] / q[6], (double)q[0] / q[6],
+                        (double)q[1] / q[6], (double)q[2] / q[6], (double)q[3] / q[6], (double)q[4] / q[6], (double)q[5] / q[6]);
+            const unsigned long long* w = h + 32 + 4 * c;
+            if (q[7])
+                fprintf(stderr, "[hmcmt_b200]     sweep, cycles per pivot block: panel copy + inversion %.0f  barrier %.0f  M' %.0f  trailing update %.0f\n",
+                        (double)w[0] / q[7], (double)w[1] / q[7], (double)w[2] / q[7], (double)w[3] / q[7]);
+        }
     }
     for (void* p : owned) cudaFree(p);
 }
@@ -91,8 +99,8 @@ int Solver::build(int nsys_, int maxRhs_, int64_t valCount_) {
     MF_TRY(dalloc((void**)&d_v, (size_t)nsys * maxRhs * S.Np * sizeof(cplx)));
     MF_TRY(dalloc((void**)&d_upd, (size_t)nsys * maxRhs * S.updEntries * sizeof(cplx)));
     if (const char* e = std::getenv("HMCMT_MF_PROF"); e && std::atoi(e)) {
-        MF_TRY(dalloc((void**)&d_prof, 8 * sizeof(unsigned long long)));
-        cudaMemset(d_prof, 0, 8 * sizeof(unsigned long long));
+        MF_TRY(dalloc((void**)&d_prof, 48 * sizeof(unsigned long long)));
+        cudaMemset(d_prof, 0, 48 * sizeof(unsigned long long));
     }
 
     // launch schedule
@@ -114,10 +122,13 @@ int Solver::build(int nsys_, int maxRhs_, int64_t valCount_) {
         }
         D.nBig = (int)bg.size();
         D.bigBytes = (size_t)S.bigDoublesAtDepth[d] * sizeof(double);
-        std::vector<int> all(bg);
-        all.insert(all.end(), sm.begin(), sm.end());
-        D.nAll = (int)all.size();
-        if (D.nAll) { MF_TRY(upload(all, &p)); D.allList = p; }
+        // solves: one warp per front up to kSolveWarpMaxFp rows, one CTA per front above
+        std::vector<int> sw, sc(bg);
+        for (int k : sm) (S.fronts[k].fp() <= kSolveWarpMaxFp ? sw : sc).push_back(k);
+        D.nSolveWarp = (int)sw.size();
+        D.nSolveCta = (int)sc.size();
+        if (D.nSolveWarp) { MF_TRY(upload(sw, &p)); D.solveWarpList = p; }
+        if (D.nSolveCta) { MF_TRY(upload(sc, &p)); D.solveCtaList = p; }
         if (!D.nBig) continue;
         MF_TRY(upload(bg, &p));
         D.bigList = p;
@@ -280,25 +291,25 @@ int Solver::solve(cudaStream_t st, int nrhs, const cplx* B, int64_t ldb, cplx* X
     int64_t nl = 0;
     for (int d = S.maxDepth; d >= 0; --d) {
         const DepthSchedule& D = sched[d];
-        if (D.nSmall) {
-            mf_fwd_warp_kernel<<<dim3((D.nSmall + kSolveWarpsPerCta - 1) / kSolveWarpsPerCta, nvec), kSolveWarpsPerCta * 32, 0, st>>>(
-                tb, sa, D.smallList, D.nSmall);
+        if (D.nSolveWarp) {
+            mf_fwd_warp_kernel<<<dim3((D.nSolveWarp + kSolveWarpsPerCta - 1) / kSolveWarpsPerCta, nvec), kSolveWarpsPerCta * 32, 0, st>>>(
+                tb, sa, D.solveWarpList, D.nSolveWarp);
             ++nl;
         }
-        if (D.nBig) {
-            mf_fwd_kernel<<<dim3(D.nBig, nvec), kSolveMfThreads, solveSmem, st>>>(tb, sa, D.bigList);
+        if (D.nSolveCta) {
+            mf_fwd_kernel<<<dim3(D.nSolveCta, nvec), kSolveMfThreads, solveSmem, st>>>(tb, sa, D.solveCtaList);
             ++nl;
         }
     }
     for (int d = 0; d <= S.maxDepth; ++d) {
         const DepthSchedule& D = sched[d];
-        if (D.nSmall) {
-            mf_bwd_warp_kernel<<<dim3((D.nSmall + kSolveWarpsPerCta - 1) / kSolveWarpsPerCta, nvec), kSolveWarpsPerCta * 32, 0, st>>>(
-                tb, sa, D.smallList, D.nSmall);
+        if (D.nSolveWarp) {
+            mf_bwd_warp_kernel<<<dim3((D.nSolveWarp + kSolveWarpsPerCta - 1) / kSolveWarpsPerCta, nvec), kSolveWarpsPerCta * 32, 0, st>>>(
+                tb, sa, D.solveWarpList, D.nSolveWarp);
             ++nl;
         }
-        if (D.nBig) {
-            mf_bwd_kernel<<<dim3(D.nBig, nvec), kSolveMfThreads, solveSmem, st>>>(tb, sa, D.bigList);
+        if (D.nSolveCta) {
+            mf_bwd_kernel<<<dim3(D.nSolveCta, nvec), kSolveMfThreads, solveSmem, st>>>(tb, sa, D.solveCtaList);
             ++nl;
         }
     }

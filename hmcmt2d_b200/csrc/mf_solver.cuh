@@ -40,8 +40,9 @@ struct DepthSchedule {
     };
     std::vector<ChunkStep> chunkSteps;
     size_t bigBytes = 0;                     // leading part of the depth arena holding the large fronts (zeroed before assembly)
-    const int* allList = nullptr;            // solve: every front of the depth
-    int nAll = 0;
+    const int* solveWarpList = nullptr;      // solves: fronts handled one per warp / one per CTA
+    const int* solveCtaList = nullptr;
+    int nSolveWarp = 0, nSolveCta = 0;
 };
 
 class Solver {

@@ -174,6 +174,18 @@ def stage_sweep():
     os.environ.pop("HMCMT_MF_LEAF", None)
 
 
+def stage_fsweep():
+    for fs in (48, 64, 80, 96, 112, 128, 144):
+        os.environ["HMCMT_MF_FSMALL"] = str(fs)
+        try:
+            _, _, i4 = plan_eval(800, 300, 8, None, nrx=40, reps=3)
+            _, _, i2 = plan_eval(200, 100, 30, "mf", nrx=40, reps=5)
+            print(f"[fsweep] fsmall {fs}: cfg4x16 {i4['eval_s'] * 1e3:.2f} ms   cfg2-mf {i2['eval_s'] * 1e3:.2f} ms  launches {i2['launches']}", flush=True)
+        except Exception:
+            traceback.print_exc()
+    os.environ.pop("HMCMT_MF_FSMALL", None)
+
+
 if __name__ == "__main__":
     stages = sys.argv[1:] or ["shim", "plan_small", "cfg2", "cfg4"]
     for s in stages:
