@@ -291,32 +291,41 @@ mf_small_kernel(Tables tb, const int* __restrict__ list) {
         const int* rel = tb.rel + C.rowPtr;
         for (int i = tid; i < cu; i += NT) relS[i] = rel[i];
         __syncthreads();
-        // work items = (block of eight columns, block of four rows): lane = (row, column), so that the 32 read-modify-writes of
-        // a warp fall into 4 x 8 patches of the tiles — consecutive shared-memory words, no bank conflicts (a 32-row x 1-column
-        // mapping hits 16-way conflicts: the tile rows are 64 bytes apart).  Each warp loads kBatch items before it scatters them.
-        const int nc8 = (cu + 7) >> 3, nr4 = (cu + 3) >> 2;
-        const int lr = lane >> 3, lc = lane & 7;
+        // work items = (column group of four, block of 32 rows) of the child's lower triangle, dealt round-robin; a warp issues
+        // the loads of kBatch items (16-byte loads, 64 bytes per lane and item) before it scatters them, so that several
+        // global-memory round trips are in flight.  (A 4-row x 8-column lane mapping avoids the shared-memory bank conflicts of
+        // the scatter but measured slower: the phase is bound by the latency of these loads, not by the scatter.)
+        const int ng = (cu + 3) >> 2, nrb = (cu + 31) >> 5;
         constexpr int kBatch = 4;
-        for (int j8 = 0; j8 < nc8; ++j8) {
-            const int j = 8 * j8 + lc;
-            const int rjc = relS[min(j, cu - 1)];
-            const double* ucol_r = U + kg_off(ld, off, off + j, 0);
-            const double* ucol_i = U + kg_off(ld, off, off + j, 1);
-            for (int r0 = 2 * j8 + warp * kBatch; r0 < nr4; r0 += NW * kBatch) {
-                double vr[kBatch], vi[kBatch];
-                int ii[kBatch];
+        for (int q0 = warp * kBatch; q0 < ng * nrb; q0 += NW * kBatch) {
+            double2 r01[kBatch], r23[kBatch], i01[kBatch], i23[kBatch];
+            int ii[kBatch], jgq[kBatch];
 #pragma unroll
-                for (int bq = 0; bq < kBatch; ++bq) {
-                    const int i = 4 * (r0 + bq) + lr;
-                    ii[bq] = (r0 + bq < nr4 && i < cu && j <= i) ? i : -1;
-                    if (ii[bq] >= 0) { vr[bq] = ucol_r[4 * (size_t)i]; vi[bq] = ucol_i[4 * (size_t)i]; }
+            for (int bq = 0; bq < kBatch; ++bq) {
+                const int q = q0 + bq;
+                const int jg = q / nrb, i = (q - jg * nrb) * 32 + lane;
+                jgq[bq] = jg;
+                ii[bq] = (q < ng * nrb && i < cu && i >= 4 * jg) ? i : -1;
+                if (ii[bq] >= 0) {
+                    const double* pr = U + kg_off(ld, off + i, off + 4 * jg, 0);
+                    const double* pi = U + kg_off(ld, off + i, off + 4 * jg, 1);
+                    r01[bq] = *reinterpret_cast<const double2*>(pr); r23[bq] = *reinterpret_cast<const double2*>(pr + 2);
+                    i01[bq] = *reinterpret_cast<const double2*>(pi); i23[bq] = *reinterpret_cast<const double2*>(pi + 2);
                 }
+            }
 #pragma unroll
-                for (int bq = 0; bq < kBatch; ++bq) {
-                    if (ii[bq] < 0) continue;
-                    double* d = addr(relS[ii[bq]], rjc);
-                    d[0] += vr[bq];
-                    d[64] += vi[bq];
+            for (int bq = 0; bq < kBatch; ++bq) {
+                const int i = ii[bq];
+                if (i < 0) continue;
+                const int jg = jgq[bq];
+                const double re[4] = {r01[bq].x, r01[bq].y, r23[bq].x, r23[bq].y}, im[4] = {i01[bq].x, i01[bq].y, i23[bq].x, i23[bq].y};
+                const int ri = relS[i];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    if (4 * jg + jj > i) break;
+                    double* d = addr(ri, relS[4 * jg + jj]);
+                    d[0] += re[jj];
+                    d[64] += im[jj];
                 }
             }
         }
