@@ -554,8 +554,12 @@ int hmcmt_plan_create(const hmcmt_problem* pr, hmcmt_plan** out) {
     pl->T = round_T(pl->b);
     if (M.nf < 2) { delete pl; return kErrArg; }
     {
-        const char* env = std::getenv("HMCMT_SOLVER");          // "mf": multifrontal solver also for narrow meshes
-        pl->useMf = pl->T == 0 || (env && !std::strcmp(env, "mf"));
+        // "mf" / "band" force a solver (band only where the register window fits); default: see below
+        const char* env = std::getenv("HMCMT_SOLVER");
+        // measured on B200 (tools/dev/t_mf.py crossover): the multifrontal solver wins from ~2 000 unknowns per system upwards
+        // (96x56 cells: 1.16 vs 1.60 ms per evaluation; 200x100: 6.1 vs 6.7 ms; 400x100: 5.1 vs 12.8 ms), the band kernel below
+        const bool wantMf = env ? !std::strcmp(env, "mf") : (M.N >= 2000);
+        pl->useMf = pl->T == 0 || wantMf;
         if (pl->useMf) pl->T = 0;
     }
     {

@@ -1,5 +1,5 @@
-"""Oracle parity at the shapes bench.py times (cfg2: 200x100 cells, register-window band kernel T = 14, two CTAs per system;
-cfg4: 800x300 cells, multifrontal solver) and a teacher-forced chain at 1e-9.  The oracle costs ~0.5 s per (frequency, mode) at
+"""Oracle parity at the shapes bench.py times (cfg2: 200x100 cells — multifrontal solver (the default) and the register-window
+band kernel T = 14 with two CTAs per system; cfg4: 800x300 cells, multifrontal solver) and a teacher-forced chain at 1e-9.  The oracle costs ~0.5 s per (frequency, mode) at
 cfg2 and ~15 s at cfg4, so the number of frequencies is small; the kernels and launch configuration are the benchmarked ones.
 
 Tolerances as in test_gpu_parity.py: 1e-9 wherever the reference's 1-D boundary recursion is well conditioned (few skin
@@ -35,11 +35,11 @@ def _self_sensitivity(octx, m, g0, pred0):
 
 @pytest.mark.parametrize("split", [1, 0])
 def test_cfg2_shape_full_spectrum(split, monkeypatch):
-    """The benchmarked instantiation: band_factor_kernel<14> FM_OWN / FM_SEP + band_solve_kernel<14> SM_BACKZ_OWN (split = 1),
-    and the unsplit kernel, on the stress model, frequencies 100 / 0.32 / 0.001 Hz."""
+    """Round 1's benchmarked instantiation: band_factor_kernel<14> FM_OWN / FM_SEP + band_solve_kernel<14> SM_BACKZ_OWN
+    (split = 1), and the unsplit kernel, on the stress model, frequencies 100 / 0.32 / 0.001 Hz."""
     from hmcmt2d_b200 import api, synthetic
     monkeypatch.setenv("HMCMT_SPLIT", str(split))
-    monkeypatch.delenv("HMCMT_SOLVER", raising=False)
+    monkeypatch.setenv("HMCMT_SOLVER", "band")
     mesh, data, inv, prior = synthetic.make_problem(200, 100, 3)
     m = synthetic.stress_model(inv)
     pl = api.Plan(mesh, data, inv, prior)
@@ -55,14 +55,30 @@ def test_cfg2_shape_full_spectrum(split, monkeypatch):
     assert err.max() < max(TOL, 20 * sens_g), (err.max(), sens_g)
 
 
+def test_cfg2_shape_default_solver_full_spectrum(monkeypatch):
+    """The configuration bench.py times by default: multifrontal solver, stress model, frequencies 100 / 0.32 / 0.001 Hz."""
+    from hmcmt2d_b200 import api, synthetic
+    monkeypatch.delenv("HMCMT_SOLVER", raising=False)
+    mesh, data, inv, prior = synthetic.make_problem(200, 100, 3)
+    m = synthetic.stress_model(inv)
+    pl = api.Plan(mesh, data, inv, prior)
+    assert pl.info(11) == 1 and pl.info(5) == 0
+    pred, phi, g = pl.forward_gradient(m)
+    assert pl.status() == 0
+    pl.close()
+    octx, opred, ophi, og = _oracle(mesh, data, inv, prior, m)
+    sens_g, sens_p = _self_sensitivity(octx, m, og, opred)
+    assert (np.abs(pred[0] - opred) / np.abs(opred)).max() < max(TOL, 20 * sens_p)
+    assert abs(phi[0] - ophi) / abs(ophi) < max(TOL, 20 * sens_p)
+    err = np.abs(g[0] - og) / np.abs(og).max()
+    assert err.max() < max(TOL, 20 * sens_g), (err.max(), sens_g)
+
+
 @pytest.mark.parametrize("solver", ["band", "mf"])
 def test_cfg2_shape_low_frequencies_hit_1e9(solver, monkeypatch):
     """Same mesh, 0.01 and 0.001 Hz: everything at 1e-9, for the band kernel (split) and the multifrontal solver."""
     from hmcmt2d_b200 import api, synthetic
-    if solver == "mf":
-        monkeypatch.setenv("HMCMT_SOLVER", "mf")
-    else:
-        monkeypatch.delenv("HMCMT_SOLVER", raising=False)
+    monkeypatch.setenv("HMCMT_SOLVER", solver)
     mesh, data, inv, prior = synthetic.make_problem(200, 100, 2, fmax_exp=-2.0, fmin_exp=-3.0)
     m = synthetic.stress_model(inv)
     pl = api.Plan(mesh, data, inv, prior)

@@ -113,6 +113,7 @@ def test_multifrontal_equals_band_kernel(monkeypatch):
     from hmcmt2d_b200 import api, synthetic
     mesh, data, inv, prior = synthetic.make_problem(60, 40, 3, nRx=8)
     ms = np.stack([synthetic.stress_model(inv, seed=s) for s in (1, 2)])
+    monkeypatch.setenv("HMCMT_SOLVER", "band")
     pb = api.Plan(mesh, data, inv, prior, nChains=2)
     assert pb.info(11) == 0
     pred0, phi0, g0 = pb.forward_gradient(ms)

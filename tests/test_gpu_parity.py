@@ -49,9 +49,12 @@ def test_tiny_problem_full_parity():
     assert np.abs(g - og).max() / np.abs(og).max() < TOL
 
 
+@pytest.mark.parametrize("solver", ["mf", "band"])
 @pytest.mark.parametrize("name", ["dprism3d", "coprod2"])
-def test_example_parity(name):
-    """cfg1 (examples/dprism3d verbatim) and the cfg5 geometry (examples/coprod2), random log-normal model."""
+def test_example_parity(name, solver, monkeypatch):
+    """cfg1 (examples/dprism3d verbatim) and the cfg5 geometry (examples/coprod2), random log-normal model, on both solvers
+    (multifrontal = the default at these sizes, register-window band kernel)."""
+    monkeypatch.setenv("HMCMT_SOLVER", solver)
     mesh, data, inv, prior = load_example(name)
     rng = np.random.default_rng(1)
     m = np.log(0.01) + 0.7 * rng.standard_normal(len(inv.strModel))

@@ -186,6 +186,16 @@ def stage_fsweep():
     os.environ.pop("HMCMT_MF_FSMALL", None)
 
 
+def stage_crossover():
+    for ny, nz, nf in [(48, 40, 8), (96, 56, 11), (76, 52, 12), (120, 60, 10), (150, 80, 20), (200, 100, 30), (400, 100, 10), (104, 104, 10)]:
+        try:
+            _, _, ib = plan_eval(ny, nz, nf, "band", nrx=10, reps=5)
+            _, _, im = plan_eval(ny, nz, nf, "mf", nrx=10, reps=5)
+            print(f"[crossover] {ny}x{nz} nf {nf}: band {ib['eval_s'] * 1e3:.3f} ms (T={ib['T']})   mf {im['eval_s'] * 1e3:.3f} ms", flush=True)
+        except Exception:
+            traceback.print_exc()
+
+
 if __name__ == "__main__":
     stages = sys.argv[1:] or ["shim", "plan_small", "cfg2", "cfg4"]
     for s in stages:
