@@ -227,6 +227,12 @@ class Plan:
         _lib.check(self.L.hmcmt_jtvec(self.h, v.ctypes.data_as(C.POINTER(C.c_double)), _lib.f64(g)), "hmcmt_jtvec")
         return g
 
+    def jacobian(self):
+        """Explicit Jacobian dZ/dsigma_active of the last forward evaluation: [nChains, nData, nAC] complex."""
+        J = np.zeros((self.nChains, self.nData, self.nAC), dtype=np.complex128)
+        _lib.check(self.L.hmcmt_jacobian(self.h, J.ctypes.data_as(C.POINTER(C.c_double))), "hmcmt_jacobian")
+        return J
+
     def forward_gradient(self, m):
         self.generation = getattr(self, "generation", 0) + 1
         mm = self._m(m)
@@ -472,6 +478,8 @@ def _plan_for(mtMesh, mtData, invParam, hmcprior, nChains=1, device=0) -> Plan:
     key = (id(mtMesh), id(mtData), nChains, device, float(hmcprior.regParam), tuple(hmcprior.sigBounds))
     if key not in cache:
         cache[key] = Plan(mtMesh, mtData, invParam, hmcprior, nChains, device)
+    # hmcprior.massType: "diagonal" (identity) or non-diagonal M = Wm (setMassMatrix HMCSampler.jl:463-489)
+    _lib.check(cache[key].L.hmcmt_set_mass_matrix(cache[key].h, 0 if hmcprior.massType == "diagonal" else 1), "hmcmt_set_mass_matrix")
     return cache[key]
 
 
@@ -554,6 +562,30 @@ def compJacTMatVec(exTE, hxTM, datVec, mt2dMesh, mtData, activeCell=None, AinvTE
     return g
 
 
+def compJacMat(exTE, hxTM, mt2dMesh, mtData, activeCell=None, AinvTE=None, AinvTM=None, linSolver: str = "b200"):
+    """`compJacMat` (compJacMat.jl:7-381): explicit complex Jacobian (nData x nAC) of the predicted impedances with respect
+    to the active-cell conductivities, for the fields / factors of the MT2DFwdData the handles belong to."""
+    h = AinvTE if isinstance(AinvTE, FactorHandle) else AinvTM
+    if not isinstance(h, FactorHandle):
+        raise ValueError("compJacMat needs the factor handle returned by MT2DFwdSolver (AinvTE/AinvTM)")
+    pl = h.plan
+    if h.generation != pl.generation:
+        raise RuntimeError("compJacMat: the factors of this MT2DFwdData were overwritten by a later evaluation")
+    if "Rho_Pha" in mtData.dataType:
+        raise NotImplementedError("explicit Jacobian: Impedance data only")
+    J = pl.jacobian()[0]
+    if activeCell is not None:
+        full = np.zeros((J.shape[0], pl.nCell), dtype=np.complex128)
+        full[:, pl._keep["act"]] = J
+        return np.asarray((activeCell.T @ full.T).T)
+    return J
+
+
+def compJacTMat(exTE, hxTM, mt2dMesh, mtData, activeCell=None, AinvTE=None, AinvTM=None, linSolver: str = "b200"):
+    """`compJacTMat` (compJacTMat.jl:9-406): the transposed Jacobian (nAC x nData)."""
+    return compJacMat(exTE, hxTM, mt2dMesh, mtData, activeCell, AinvTE, AinvTM, linSolver).T.copy()
+
+
 def compDataGradient(mtMesh, mtData, invParam: InvDataModel, hmcprior: HMCPrior):
     """4-argument `compDataGradient` (HMCSampler.jl:277-330) -> (predData, dataMisfit, dataGrad)."""
     pl = _plan_for(mtMesh, mtData, invParam, hmcprior)
@@ -569,7 +601,11 @@ def getHamiltonian(mtData, mtMesh, invParam, hmcprior, hmcParam: HMCParameter):
     pred, _, _ = pl.forward(m=invParam.strModel, fields=False)
     res = invParam.dataW * (pred[0] - invParam.obsData)
     dm = float(np.real(0.5 * np.vdot(res, res)))
-    kp = 0.5 * float(hmcParam.momentum @ hmcParam.momentum)
+    if hmcprior.massType == "diagonal":
+        kp = 0.5 * float(hmcParam.momentum @ hmcParam.momentum)
+    else:                                                    # invM = Wm^{-1} (setMassMatrix(invParam) HMCSampler.jl:478-489)
+        import scipy.sparse.linalg as spla
+        kp = 0.5 * float(hmcParam.momentum @ spla.spsolve(invParam.Wm.tocsc(), hmcParam.momentum))
     d = invParam.strModel - invParam.refModel
     mnorm = 0.5 * float(d @ (invParam.Wm @ d)) * hmcprior.regParam
     return dm, kp, dm + kp + mnorm, mnorm, pred[0]

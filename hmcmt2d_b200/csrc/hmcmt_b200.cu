@@ -68,13 +68,21 @@ struct hmcmt_plan {
     // device buffers
     DevBuf<double> yLen, zLen, zNode, freqs, fdy1, fdy2, wL, wR, bg, wmVal, wd, m, p, mref, sigma, meanSig, planes;
     DevBuf<double> xbuf, Gpart, phiPart, phi, gsig, gdata, gtotal, energies, panels, curM, curP, chainScal, zmom;
-    DevBuf<int> fid, iL, iR, cell2act, act2cell, wmPtr, wmIdx, status, driftFlag, packed2full, Lsteps;
+    DevBuf<int> fid, iL, iR, cell2act, act2cell, wmPtr, wmIdx, status, driftFlag, packed2full, full2packed, Lsteps;
     DevBuf<cplx> obs, bc, bcs, rhs, x, F, lam, Lam, srows, qrow, scratch, predFull, ainvz, zadj, vin, predPacked, wexp, conCols, respFull;
     DevBuf<BandSys> sysDesc;
     DevBuf<SolveJob> jobs, fwdJobs;                 // fwdJobs: back-substitution sweeps of the fused forward systems (split systems)
     // wide meshes (half-bandwidth > 104): nested-dissection multifrontal solver (mf_solver.cuh) instead of the band kernels
     mf::Solver* mfs = nullptr;
     DevBuf<mf::MtValSys> mfSys;
+    // non-diagonal mass matrix M = Wm (setMassMatrix(invParam) HMCSampler.jl:478-489): invM p through a multifrontal
+    // factorisation of Wm, sqrtM z through the banded Cholesky factor of Wm (natural ordering, as the reference's dense one)
+    bool massOn = false;
+    mf::Solver* massSolver = nullptr;
+    DevBuf<double> gradK, Lband;
+    DevBuf<cplx> massBuf;
+    DevBuf<int> massStatus;
+    int massBw = 0;
     // frequency-sharded steps: NCCL communicator over the ranks that share this chain (hmcmt_nccl_init)
     ncclComm_t comm = nullptr;
     int commWorld = 1;
@@ -316,6 +324,25 @@ __global__ void k_unpack_exchange(int nAC, const double* __restrict__ xbuf, cons
     gtotal[(size_t)ch * nAC + a] = gd + beta * pr;
 }
 
+// Explicit Jacobian (compJacMat.jl:7-381 / compJacTMat.jl:9-406): one pass of the adjoint machinery per (receiver, real /
+// imaginary part) yields, in every (frequency, mode) system, the row of that system's datum at this receiver.
+//   v = e_d   -> real(J^T conj(v)) = Re J[d,:]  ;   v = i e_d -> Im J[d,:]
+__global__ void k_jac_vin(int nFull, int nRx, int nModes, int r, cplx val, cplx* __restrict__ vin) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, ch = blockIdx.y;
+    if (i >= nFull) return;
+    const int rx = (i / nModes) % nRx;
+    vin[(size_t)ch * nFull + i] = rx == r ? val : mk(0.0, 0.0);
+}
+__global__ void k_jac_rows(int nAC, int nCell, int nFreq, int nRx, int nModes, int nData, int r, int part, const int* __restrict__ act2cell,
+                           const int* __restrict__ full2packed, const double* __restrict__ Gpart, double* __restrict__ J) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x, sys = blockIdx.y;
+    if (a >= nAC) return;
+    const int f = sys % nFreq, t = sys / nFreq, mi = t % nModes, ch = t / nModes;
+    const int d = full2packed[(f * nRx + r) * nModes + mi];
+    if (d < 0) return;
+    J[(((size_t)ch * nData + d) * nAC + a) * 2 + part] = Gpart[(size_t)sys * nCell + act2cell[a]];
+}
+
 int ensure_pin(hmcmt_plan* pl, size_t bytes) {
     if (pl->pinBytes >= bytes) return kOk;
     if (pl->pin) cudaFreeHost(pl->pin);
@@ -421,7 +448,7 @@ int rx_phase(hmcmt_plan* pl, bool wantAdjoint, const cplx* vin) {
 
 // adjoint part: one solve per system with the factors of the forward phase (A symmetric: no transposition,
 // compJacTMatVec.jl:220-224), contraction into the gradient, prior gradient
-int adjoint_phase(hmcmt_plan* pl) {
+int adjoint_phase(hmcmt_plan* pl, bool reduce = true) {
     const MeshDev& M = pl->M;
     cudaStream_t st = pl->stream;
     const int nSys = pl->nSys, nCh = pl->nChains;
@@ -441,6 +468,7 @@ int adjoint_phase(hmcmt_plan* pl) {
     k_contract_cells<<<dim3((M.nCell + 255) / 256, nSys), 256, 0, st>>>(M, pl->sm, pl->freqs.p, pl->sigma.p, pl->F.p, pl->Lam.p, pl->qrow.p,
                                                                         pl->bcs.p, pl->conCols.p, pl->Gpart.p);
     LAUNCH_CHECK(pl);
+    if (!reduce) return kOk;
     k_reduce_grad<<<dim3((pl->nAC + 255) / 256, nCh), 256, 0, st>>>(pl->nAC, M.nCell, pl->nSysPerChain, pl->act2cell.p, pl->Gpart.p,
                                                                    pl->m.p, pl->mref.p, pl->wmPtr.p, pl->wmIdx.p, pl->wmVal.p, pl->beta,
                                                                    pl->sigma.p, pl->gsig.p, pl->gdata.p, pl->gtotal.p);
@@ -476,8 +504,59 @@ int check_status(hmcmt_plan* pl) {
     return rc;
 }
 
+__global__ void k_real_to_cplx(size_t n, const double* __restrict__ x, cplx* __restrict__ y) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = mk(x[i], 0.0);
+}
+__global__ void k_cplx_to_real(size_t n, const cplx* __restrict__ x, double* __restrict__ y) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = x[i].x;
+}
+// p = L z with the banded lower Cholesky factor, Lband[i*(bw+1) + d] = L[i][i-d]   (getMomentumVector: mp = sqrtM * mp, :450)
+__global__ void k_bandL_matvec(int n, int bw, const double* __restrict__ Lband, const double* __restrict__ z, double* __restrict__ p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, ch = blockIdx.y;
+    if (i >= n) return;
+    const double* zz = z + (size_t)ch * n;
+    const double* row = Lband + (size_t)i * (bw + 1);
+    double acc = 0.0;
+    for (int d = min(bw, i); d >= 0; --d) acc += row[d] * zz[i - d];
+    p[(size_t)ch * n + i] = acc;
+}
+
+// gradK = invM p = Wm^{-1} p for every chain (one multifrontal solve with nChains right-hand sides)
+int mass_apply(hmcmt_plan* pl) {
+    if (!pl->massOn) return kOk;
+    const size_t n = (size_t)pl->nChains * pl->nAC;
+    k_real_to_cplx<<<(unsigned)((n + 255) / 256), 256, 0, pl->stream>>>(n, pl->p.p, pl->massBuf.p);
+    LAUNCH_CHECK(pl);
+    int rc = pl->massSolver->solve(pl->stream, pl->nChains, pl->massBuf.p, pl->nAC, pl->massBuf.p, pl->nAC, &pl->launches);
+    if (rc) return rc;
+    k_cplx_to_real<<<(unsigned)((n + 255) / 256), 256, 0, pl->stream>>>(n, pl->massBuf.p, pl->gradK.p);
+    LAUNCH_CHECK(pl);
+    return kOk;
+}
+// p <- sqrtM p in place (p holds the clipped normal draws)
+int mass_sqrt_apply(hmcmt_plan* pl) {
+    if (!pl->massOn) return kOk;
+    k_bandL_matvec<<<dim3((pl->nAC + 255) / 256, pl->nChains), 256, 0, pl->stream>>>(pl->nAC, pl->massBw, pl->Lband.p, pl->p.p, pl->gradK.p);
+    LAUNCH_CHECK(pl);
+    HMCMT_CUDA_TRY(cudaMemcpyAsync(pl->p.p, pl->gradK.p, sizeof(double) * (size_t)pl->nChains * pl->nAC, cudaMemcpyDeviceToDevice, pl->stream));
+    return kOk;
+}
+
+int energies(hmcmt_plan* pl) {
+    int mrc = mass_apply(pl);
+    if (mrc) return mrc;
+    k_energies<<<pl->nChains, kHmcThreads, 0, pl->stream>>>(pl->nAC, pl->m.p, pl->mref.p, pl->p.p, pl->wmPtr.p, pl->wmIdx.p, pl->wmVal.p,
+                                                            pl->beta, pl->energies.p, pl->massOn ? pl->gradK.p : nullptr);
+    LAUNCH_CHECK(pl);
+    return kOk;
+}
+
 int drift(hmcmt_plan* pl, double dt) {
-    k_drift<<<pl->nChains, kHmcThreads, 0, pl->stream>>>(pl->nAC, dt, pl->lo, pl->hi, pl->m.p, pl->p.p, pl->driftFlag.p);
+    int mrc = mass_apply(pl);
+    if (mrc) return mrc;
+    k_drift<<<pl->nChains, kHmcThreads, 0, pl->stream>>>(pl->nAC, dt, pl->lo, pl->hi, pl->m.p, pl->p.p, pl->driftFlag.p, pl->massOn ? pl->gradK.p : nullptr);
     LAUNCH_CHECK(pl);
     return kOk;
 }
@@ -641,6 +720,11 @@ int hmcmt_plan_create(const hmcmt_problem* pr, hmcmt_plan** out) {
     ok(pl->wmIdx.upload(pr->wmColIdx, nnzWm)); ok(pl->wmVal.upload(pr->wmVal, nnzWm));
     ok(pl->wd.upload(wdFull.data(), pl->nFull)); ok(pl->obs.upload(obsFull.data(), pl->nFull));
     ok(pl->packed2full.upload(pl->h_packed2full.data(), pr->nData));
+    {
+        std::vector<int> f2p(pl->nFull, -1);
+        for (int i = 0; i < pr->nData; ++i) f2p[pl->h_packed2full[i]] = i;
+        ok(pl->full2packed.upload(f2p.data(), f2p.size()));
+    }
     const size_t nCh = pl->nChains, nSys = pl->nSys, N = M.N;
     ok(pl->m.alloc(nCh * pr->nAC)); ok(pl->p.alloc(nCh * pr->nAC)); ok(pl->mref.alloc(nCh * pr->nAC));
     ok(pl->curM.alloc(nCh * pr->nAC)); ok(pl->curP.alloc(nCh * pr->nAC)); ok(pl->zmom.alloc(nCh * pr->nAC));
@@ -778,10 +862,10 @@ void hmcmt_destroy(hmcmt_plan* pl) {
     pl->phi.release(); pl->gsig.release(); pl->gdata.release(); pl->gtotal.release(); pl->energies.release(); pl->panels.release(); pl->curM.release();
     pl->curP.release(); pl->chainScal.release(); pl->zmom.release(); pl->fid.release(); pl->iL.release(); pl->iR.release();
     pl->cell2act.release(); pl->act2cell.release(); pl->wmPtr.release(); pl->wmIdx.release(); pl->status.release();
-    pl->driftFlag.release(); pl->packed2full.release(); pl->Lsteps.release(); pl->obs.release(); pl->bc.release(); pl->bcs.release();
+    pl->driftFlag.release(); pl->packed2full.release(); pl->full2packed.release(); pl->Lsteps.release(); pl->obs.release(); pl->bc.release(); pl->bcs.release();
     pl->rhs.release(); pl->x.release(); pl->F.release(); pl->lam.release(); pl->Lam.release(); pl->srows.release(); pl->qrow.release();
     pl->scratch.release(); pl->predFull.release(); pl->ainvz.release(); pl->zadj.release(); pl->vin.release();
-    pl->predPacked.release(); pl->conCols.release(); pl->xbuf.release(); pl->wexp.release(); pl->respFull.release(); pl->mfSys.release(); delete pl->mfs; pl->mfs = nullptr; pl->fwdJobs.release(); pl->sysDesc.release(); pl->jobs.release();
+    pl->predPacked.release(); pl->conCols.release(); pl->xbuf.release(); pl->wexp.release(); pl->respFull.release(); pl->gradK.release(); pl->Lband.release(); pl->massBuf.release(); pl->massStatus.release(); delete pl->massSolver; pl->massSolver = nullptr; pl->mfSys.release(); delete pl->mfs; pl->mfs = nullptr; pl->fwdJobs.release(); pl->sysDesc.release(); pl->jobs.release();
     if (pl->pin) cudaFreeHost(pl->pin);
     delete pl;
 }
@@ -812,6 +896,82 @@ int hmcmt_sync(hmcmt_plan* pl) {
     HMCMT_CUDA_TRY(cudaStreamSynchronize(pl->stream));
     return kOk;
 }
+int hmcmt_set_mass_matrix(hmcmt_plan* pl, int32_t kind) {
+    if (!pl || kind < 0 || kind > 1) return kErrArg;
+    HMCMT_CUDA_TRY(cudaSetDevice(pl->device));
+    if (kind == 0) { pl->massOn = false; return kOk; }
+    if (pl->massSolver) { pl->massOn = true; return kOk; }
+    const int n = pl->nAC;
+    std::vector<int> ptr(n + 1), idx;
+    std::vector<double> val;
+    HMCMT_CUDA_TRY(cudaMemcpy(ptr.data(), pl->wmPtr.p, sizeof(int) * (n + 1), cudaMemcpyDeviceToHost));
+    idx.resize(ptr[n]); val.resize(ptr[n]);
+    HMCMT_CUDA_TRY(cudaMemcpy(idx.data(), pl->wmIdx.p, sizeof(int) * ptr[n], cudaMemcpyDeviceToHost));
+    HMCMT_CUDA_TRY(cudaMemcpy(val.data(), pl->wmVal.p, sizeof(double) * ptr[n], cudaMemcpyDeviceToHost));
+    // (1) invM p = Wm^{-1} p : multifrontal factorisation of the sparse SPD matrix, nested dissection of its graph
+    std::vector<mf::Entry> ent;
+    std::vector<int> aptr(n + 1, 0);
+    int bw = 0;
+    for (int a = 0; a < n; ++a)
+        for (int q = ptr[a]; q < ptr[a + 1]; ++q) {
+            const int j = idx[q];
+            if (j > a) continue;
+            ent.push_back(mf::Entry{a, j, q});
+            bw = std::max(bw, a - j);
+            if (j != a) { ++aptr[a + 1]; ++aptr[j + 1]; }
+        }
+    for (int a = 0; a < n; ++a) aptr[a + 1] += aptr[a];
+    std::vector<int> adj(aptr[n]), at(aptr.begin(), aptr.end() - 1);
+    for (const mf::Entry& e : ent)
+        if (e.row != e.col) { adj[at[e.row]++] = e.col; adj[at[e.col]++] = e.row; }
+    std::vector<std::vector<int>> sn;
+    mf::mf_order_graph(n, aptr, adj, mf_leaf_size(), sn);
+    mf::Symbolic S;
+    if (!mf::mf_symbolic(n, sn, ent, mf_small_front(), S)) return kErrArg;
+    int rc = kOk;
+    pl->massSolver = mf::Solver::create(std::move(S), 1, pl->nChains, (int64_t)ptr[n], &rc);
+    if (!pl->massSolver) return rc;
+    {
+        std::vector<cplx> cv(ptr[n]);
+        for (int q = 0; q < ptr[n]; ++q) cv[q] = mk(val[q], 0.0);
+        HMCMT_CUDA_TRY(cudaMemcpy(pl->massSolver->vals(), cv.data(), sizeof(cplx) * cv.size(), cudaMemcpyHostToDevice));
+    }
+    if ((rc = pl->massStatus.alloc(1)) != kOk) return rc;
+    HMCMT_CUDA_TRY(cudaMemset(pl->massStatus.p, 0, sizeof(int)));
+    rc = pl->massSolver->factor(pl->stream, pl->massStatus.p, &pl->launches);
+    if (rc) return rc;
+    int hst = 0;
+    HMCMT_CUDA_TRY(cudaMemcpyAsync(&hst, pl->massStatus.p, sizeof(int), cudaMemcpyDeviceToHost, pl->stream));
+    HMCMT_CUDA_TRY(cudaStreamSynchronize(pl->stream));
+    if (hst) return hst;
+    // (2) sqrtM = the lower Cholesky factor of Wm in the NATURAL ordering (decomp.L of the reference's dense cholesky): Wm is
+    //     banded there (half-bandwidth = cells per mesh row), so is L, and the band never fills outside itself
+    std::vector<double> Lb((size_t)n * (bw + 1), 0.0);
+    for (int a = 0; a < n; ++a)
+        for (int q = ptr[a]; q < ptr[a + 1]; ++q)
+            if (idx[q] <= a) Lb[(size_t)a * (bw + 1) + (a - idx[q])] = val[q];
+    for (int j = 0; j < n; ++j) {
+        double* rj = Lb.data() + (size_t)j * (bw + 1);
+        double d = rj[0];
+        for (int k = std::max(0, j - bw); k < j; ++k) d -= rj[j - k] * rj[j - k];
+        if (!(d > 0.0)) return kErrNotPosDef;
+        d = std::sqrt(d);
+        rj[0] = d;
+        for (int i = j + 1; i <= std::min(n - 1, j + bw); ++i) {
+            double* ri = Lb.data() + (size_t)i * (bw + 1);
+            double v = ri[i - j];
+            for (int k = std::max(0, i - bw); k < j; ++k) v -= ri[i - k] * rj[j - k];
+            ri[i - j] = v / d;
+        }
+    }
+    if ((rc = pl->Lband.upload(Lb.data(), Lb.size())) != kOk) return rc;
+    if ((rc = pl->gradK.alloc((size_t)pl->nChains * n)) != kOk) return rc;
+    if ((rc = pl->massBuf.alloc((size_t)pl->nChains * n)) != kOk) return rc;
+    pl->massBw = bw;
+    pl->massOn = true;
+    return kOk;
+}
+
 int hmcmt_status(hmcmt_plan* pl) {
     if (!pl) return kErrArg;
     HMCMT_CUDA_TRY(cudaSetDevice(pl->device));
@@ -935,6 +1095,40 @@ int hmcmt_jtvec(hmcmt_plan* pl, const double* v, double* gsig) {
     return check_status(pl);
 }
 
+int hmcmt_jacobian(hmcmt_plan* pl, double* J) {
+    if (!pl || !J || !pl->haveForward) return kErrArg;
+    HMCMT_CUDA_TRY(cudaSetDevice(pl->device));
+    const MeshDev& M = pl->M;
+    cudaStream_t st = pl->stream;
+    const size_t nJ = (size_t)pl->nChains * pl->nData * pl->nAC * 2;
+    DevBuf<double> dJ;
+    int rc = dJ.alloc(nJ);
+    if (rc) return rc;
+    HMCMT_CUDA_TRY(cudaMemsetAsync(dJ.p, 0, nJ * sizeof(double), st));
+    if (!pl->haveSens) rc = launch_sens_side(pl);
+    for (int r = 0; r < pl->nRx && rc == kOk; ++r)
+        for (int part = 0; part < 2 && rc == kOk; ++part) {
+            k_jac_vin<<<dim3((pl->nFull + 255) / 256, pl->nChains), 256, 0, st>>>(pl->nFull, pl->nRx, pl->nModes, r,
+                                                                                 part == 0 ? mk(1.0, 0.0) : mk(0.0, 1.0), pl->vin.p);
+            ++pl->launches;
+            rc = rx_phase(pl, true, pl->vin.p);
+            if (rc == kOk) rc = adjoint_phase(pl, false);
+            if (rc != kOk) break;
+            k_jac_rows<<<dim3((pl->nAC + 255) / 256, pl->nSys), 256, 0, st>>>(pl->nAC, M.nCell, pl->nFreq, pl->nRx, pl->nModes, pl->nData, r, part,
+                                                                             pl->act2cell.p, pl->full2packed.p, pl->Gpart.p, dJ.p);
+            ++pl->launches;
+        }
+    if (rc == kOk && cudaGetLastError() != cudaSuccess) rc = kErrCuda;
+    if (rc == kOk && cudaMemcpyAsync(J, dJ.p, nJ * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = kErrCuda;
+    if (cudaStreamSynchronize(st) != cudaSuccess && rc == kOk) rc = kErrCuda;
+    dJ.release();
+    if (rc) return rc;
+    // the adjoint passes overwrote the responses / misfit of the data residual: restore them for later calls
+    rc = rx_phase(pl, false, nullptr);
+    if (rc) return rc;
+    return check_status(pl);
+}
+
 int hmcmt_forward_gradient(hmcmt_plan* pl, const double* m, double* pred, double* phid, double* grad) {
     if (!pl || !m) return kErrArg;
     HMCMT_CUDA_TRY(cudaSetDevice(pl->device));
@@ -980,8 +1174,8 @@ static int trajectory_device(hmcmt_plan* pl, double dt, int Lmax, const int* dL)
     LAUNCH_CHECK(pl);
     for (int k = 1; k <= Lmax; ++k) {
         // chains that already finished (k > L) are frozen by a zero drift: handled through dt masking below
-        k_drift<<<pl->nChains, kHmcThreads, 0, pl->stream>>>(pl->nAC, dt, pl->lo, pl->hi, pl->m.p, pl->p.p, pl->driftFlag.p);
-        LAUNCH_CHECK(pl);
+        rc = drift(pl, dt);
+        if (rc) return rc;
         rc = compute_step(pl, true, nullptr);
         if (rc) return rc;
         k_kick_masked<<<g, 256, 0, pl->stream>>>(pl->nAC, dt, k, dL, pl->gtotal.p, pl->p.p);
@@ -1006,9 +1200,8 @@ int hmcmt_leapfrog_trajectory(hmcmt_plan* pl, double dt, const int32_t* intstep,
     HMCMT_CUDA_TRY(cudaStreamSynchronize(pl->stream));
     int rc = trajectory_device(pl, dt, Lmax, pl->Lsteps.p);
     if (rc) return rc;
-    k_energies<<<pl->nChains, kHmcThreads, 0, pl->stream>>>(pl->nAC, pl->m.p, pl->mref.p, pl->p.p, pl->wmPtr.p, pl->wmIdx.p, pl->wmVal.p,
-                                                            pl->beta, pl->energies.p);
-    LAUNCH_CHECK(pl);
+    rc = energies(pl);
+    if (rc) return rc;
     std::vector<double> e(2 * pl->nChains), ph(pl->nChains);
     HMCMT_CUDA_TRY(cudaMemcpyAsync(e.data(), pl->energies.p, sizeof(double) * e.size(), cudaMemcpyDeviceToHost, pl->stream));
     HMCMT_CUDA_TRY(cudaMemcpyAsync(ph.data(), pl->phi.p, sizeof(double) * ph.size(), cudaMemcpyDeviceToHost, pl->stream));
@@ -1170,11 +1363,12 @@ int hmcmt_run_chain(hmcmt_plan* pl, double dt, int32_t nsamples, double rhoref, 
     RC_CUDA(cudaMemcpyAsync(pl->zmom.p, z_init, sizeof(double) * nState, cudaMemcpyHostToDevice, st));
     k_clip_momentum<<<g, 256, 0, st>>>(nAC, pl->zmom.p, pl->p.p);
     pl->launches += 3;
+    RC_TRY(mass_sqrt_apply(pl));
     // Hamiltonian at the start (getHamiltonian HMCSampler.jl:113-115): forward for the homogeneous model, mnorm = 0
     RC_TRY(compute_step(pl, false, nullptr));
-    k_energies<<<nCh, kHmcThreads, 0, st>>>(nAC, pl->m.p, pl->mref.p, pl->p.p, pl->wmPtr.p, pl->wmIdx.p, pl->wmVal.p, pl->beta, pl->energies.p);
+    RC_TRY(energies(pl));
     k_pack_pred<<<dim3((nData + 255) / 256, nCh), 256, 0, st>>>(nData, pl->nFull, pl->packed2full.p, pl->predFull.p, pl->predPacked.p);
-    pl->launches += 2;
+    pl->launches += 1;
     {
         std::vector<double> e(2 * nCh), ph(nCh), sc(4 * nCh);
         RC_CUDA(cudaMemcpyAsync(e.data(), pl->energies.p, sizeof(double) * e.size(), cudaMemcpyDeviceToHost, st));
@@ -1213,13 +1407,14 @@ int hmcmt_run_chain(hmcmt_plan* pl, double dt, int32_t nsamples, double rhoref, 
         const int L = intsteps[it - 1];
         RC_TRY(trajectory_device(pl, dt, L, dL.p + (size_t)(it - 1) * nCh));
         if (!reuse_last_forward) RC_TRY(compute_step(pl, false, nullptr));       // the reference's redundant forward sweep
-        k_energies<<<nCh, kHmcThreads, 0, st>>>(nAC, pl->m.p, pl->mref.p, pl->p.p, pl->wmPtr.p, pl->wmIdx.p, pl->wmVal.p, pl->beta, pl->energies.p);
+        RC_TRY(energies(pl));
         k_pack_pred<<<dim3((nData + 255) / 256, nCh), 256, 0, st>>>(nData, pl->nFull, pl->packed2full.p, pl->predFull.p, pl->predPacked.p);
         const double* zsrc = dZ.p + ((size_t)slot * chunk + inChunk) * nState;
         k_accept<<<nCh, kHmcThreads, 0, st>>>(nAC, nData, it, nsamples, dUacc.p, pl->phi.p, pl->energies.p, zsrc, pl->m.p, pl->p.p,
                                               pl->curM.p, pl->chainScal.p, pl->predPacked.p, dModel.p, dStats.p, dAcc.p, dData.p);
-        pl->launches += 3;
+        pl->launches += 2;
         if (cudaGetLastError() != cudaSuccess) { cleanup(); return kErrCuda; }
+        RC_TRY(mass_sqrt_apply(pl));             // p = sqrtM clip(z); k_accept's kinetic energy 1/2 z^T z equals 1/2 p^T invM p
         if (inChunk == chunk - 1 || it == nsamples) RC_CUDA(cudaEventRecord(evFree[slot], st));
     }
     RC_CUDA(cudaMemcpyAsync(hmcmodel, dModel.p, sizeof(double) * dModel.n, cudaMemcpyDeviceToHost, st));

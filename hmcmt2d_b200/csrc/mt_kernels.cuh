@@ -933,16 +933,19 @@ __global__ void k_kick(int nAC, double dtScaled, const double* __restrict__ grad
 }
 // drift with max-step clip 3.0 and reflection at the log-conductivity bounds
 __global__ void __launch_bounds__(kHmcThreads)
-k_drift(int nAC, double dt, double lo, double hi, double* __restrict__ m, double* __restrict__ p, int* __restrict__ flag) {
+k_drift(int nAC, double dt, double lo, double hi, double* __restrict__ m, double* __restrict__ p, int* __restrict__ flag,
+        const double* __restrict__ gradK) {
+    // gradK = invM p (getKineticGradient HMCSampler.jl:424-431); null: identity mass matrix, gradK = p
     __shared__ double sh[32];
     const int ch = blockIdx.x;
     double* mm = m + (size_t)ch * nAC;
     double* pp = p + (size_t)ch * nAC;
+    const double* gk = gradK ? gradK + (size_t)ch * nAC : pp;
     double mx = 0.0;
-    for (int a = threadIdx.x; a < nAC; a += blockDim.x) mx = fmax(mx, fabs(dt * pp[a]));
+    for (int a = threadIdx.x; a < nAC; a += blockDim.x) mx = fmax(mx, fabs(dt * gk[a]));
     mx = block_reduce(mx, true, sh);
     for (int a = threadIdx.x; a < nAC; a += blockDim.x) {
-        double dm = dt * pp[a];
+        double dm = dt * gk[a];
         if (mx > 3.0) dm = dm / mx * 3.0;
         double v = mm[a] + dm, mom = pp[a];
         if (!(v <= hi && v >= lo)) {
@@ -963,15 +966,17 @@ k_drift(int nAC, double dt, double lo, double hi, double* __restrict__ m, double
 __global__ void __launch_bounds__(kHmcThreads)
 k_energies(int nAC, const double* __restrict__ m, const double* __restrict__ mref, const double* __restrict__ p,
            const int* __restrict__ wmPtr, const int* __restrict__ wmIdx, const double* __restrict__ wmVal, double beta,
-           double* __restrict__ out /* [ch][2] = K, phi_m */) {
+           double* __restrict__ out /* [ch][2] = K, phi_m */, const double* __restrict__ gradK) {
+    // K = 1/2 p^T invM p (getKineticEnergy HMCSampler.jl:407-415): gradK = invM p, null for the identity mass matrix
     __shared__ double sh[32];
     const int ch = blockIdx.x;
     const double* mm = m + (size_t)ch * nAC;
     const double* mr = mref + (size_t)ch * nAC;
     const double* pp = p + (size_t)ch * nAC;
+    const double* gk = gradK ? gradK + (size_t)ch * nAC : pp;
     double k = 0.0, pm = 0.0;
     for (int a = threadIdx.x; a < nAC; a += blockDim.x) {
-        k += pp[a] * pp[a];
+        k += pp[a] * gk[a];
         double row = 0.0;
         for (int q = wmPtr[a]; q < wmPtr[a + 1]; ++q) { int j = wmIdx[q]; row += wmVal[q] * (mm[j] - mr[j]); }
         pm += (mm[a] - mr[a]) * row;

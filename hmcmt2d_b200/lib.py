@@ -61,7 +61,9 @@ def load() -> C.CDLL:
     lib.hmcmt_forward.argtypes = [vp, _f64p, _f64p, _f64p, _f64p]
     lib.hmcmt_forward_sigma.argtypes = [vp, _f64p, _f64p, _f64p, _f64p]
     lib.hmcmt_jtvec.argtypes = [vp, _f64p, _f64p]
+    lib.hmcmt_jacobian.argtypes = [vp, _f64p]
     lib.hmcmt_status.argtypes = [vp]
+    lib.hmcmt_set_mass_matrix.argtypes = [vp, C.c_int32]
     lib.hmcmt_set_response_kind.argtypes = [vp, C.c_int32]
     lib.hmcmt_get_responses.argtypes = [vp, _f64p]
     lib.hmcmt_forward_gradient.argtypes = [vp, _f64p, _f64p, _f64p, _f64p]
@@ -106,7 +108,7 @@ EXPORTED_SYMBOLS = [
     "factor_mumps_cmplx_", "factor_mumps_", "solve_mumps_cmplx_", "solve_mumps_", "solve_mumps_sparse_rhs_",
     "solve_mumps_cmplx_sparse_rhs_", "destroy_mumps_", "destroy_mumps_cmplx_",
     "hmcmt_plan_create", "hmcmt_destroy", "hmcmt_plan_info", "hmcmt_forward", "hmcmt_forward_sigma", "hmcmt_jtvec",
-    "hmcmt_forward_gradient", "hmcmt_status", "hmcmt_set_response_kind", "hmcmt_get_responses",
+    "hmcmt_forward_gradient", "hmcmt_jacobian", "hmcmt_status", "hmcmt_set_mass_matrix", "hmcmt_set_response_kind", "hmcmt_get_responses",
     "hmcmt_set_state", "hmcmt_get_state", "hmcmt_leapfrog_trajectory", "hmcmt_leapfrog_steps_device", "hmcmt_sync",
     "hmcmt_step_partial", "hmcmt_exchange_buffer", "hmcmt_step_finish", "hmcmt_nccl_unique_id", "hmcmt_nccl_init",
     "hmcmt_leapfrog_steps_sharded",

@@ -126,6 +126,13 @@ int hmcmt_forward_sigma(hmcmt_plan* plan, const double* sigma, double* pred, dou
  * AinvTM, compJacTMatVec.jl:220-224, 291-295): only the adjoint sources, one solve per system and the contraction run. */
 int hmcmt_jtvec(hmcmt_plan* plan, const double* v, double* gsig);
 
+/* Explicit Jacobian of the predicted impedances with respect to the active-cell conductivities for the state left by the
+ * last forward evaluation — compJacMat.jl:7-381 (equivalently the transpose compJacTMat.jl:9-406 builds) with the same boundary-
+ * condition approximations as compJacTMatVec: J [nChains][nData][nAC] complex, rows in the packed data order.  One adjoint
+ * pass (adjoint sources, one solve per system with the resident factors, contraction) per receiver and per real / imaginary
+ * part fills that receiver's row in every (frequency, mode) system at once: 2 nRx passes instead of nData. */
+int hmcmt_jacobian(hmcmt_plan* plan, double* J);
+
 /* compDataGradient(mtMesh,mtData,invParam,hmcprior)  HMCSampler.jl:277-330:
  * m -> pred [nChains][nData] complex, phi_d [nChains], grad [nChains][nAC] (w.r.t. log conductivity,
  * data part only, as the reference returns it). Host buffers; H2D/D2H inside. */
@@ -174,6 +181,12 @@ int hmcmt_sync(hmcmt_plan* plan);
  * reference prints a message and loops forever).  Reading clears the flags.  The asynchronous entry points
  * (hmcmt_leapfrog_steps_device, hmcmt_step_partial / _finish) do not check: call this after them. */
 int hmcmt_status(hmcmt_plan* plan);
+/* Mass matrix of the sampler (hmcprior.massType, HMCSampler.jl:81-86): kind 0 = "diagonal" (identity, the default), 1 =
+ * non-diagonal M = Wm (setMassMatrix(invParam) HMCSampler.jl:478-489: dense Cholesky of Wm in the reference).  Here invM p is one
+ * multifrontal solve with the sparse factor of Wm and sqrtM z the product with Wm's banded Cholesky factor (natural ordering,
+ * identical to the reference's dense L).  Affects drift (getKineticGradient), kinetic energy and the momentum draws of
+ * hmcmt_run_chain.  -40 if Wm is not positive definite. */
+int hmcmt_set_mass_matrix(hmcmt_plan* plan, int32_t kind);
 /* Response type of the forward evaluation (compMTRespTE mt2DTE.jl:240-259, compMTRespTM mt2DTM.jl:224-242):
  * kind 0 = impedance, 1 = apparent resistivity rho_a = |Z|^2/(omega mu0) and phase atan2(Im Z, Re Z) in degrees
  * ("Rho_Pha" data).  Forward only: the reference's own sensitivity code never reaches that data type

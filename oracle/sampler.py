@@ -94,17 +94,27 @@ def compDataGradient(mesh, data, inv: InvDataModel, prior: HMCPrior, factor_fn=d
     return pred, misfit, sig_act * g
 
 
-def getKineticEnergy(p):
-    """`getKineticEnergy` HMCSampler.jl:407-415 with the identity mass matrix (:81-83)."""
-    return 0.5 * float(np.dot(p, p))
+def setMassMatrix(inv, prior):
+    """`setMassMatrix` HMCSampler.jl:463-489 -> (invM, sqrtM): None, None for massType "diagonal" (identity, scaling = 1.0,
+    :81-83); else the dense Cholesky of Wm: sqrtM = L, invM = inv(L)' * inv(L)."""
+    if prior.massType == "diagonal":
+        return None, None
+    L = np.linalg.cholesky(np.asarray(inv.Wm.todense(), dtype=np.float64))
+    Linv = np.linalg.inv(L)
+    return Linv.T @ Linv, L
 
 
-def getHamiltonian(data, mesh, inv, prior, momentum, factor_fn=default_factor):
+def getKineticEnergy(p, invM=None):
+    """`getKineticEnergy` HMCSampler.jl:407-415."""
+    return 0.5 * float(np.dot(p, p if invM is None else invM @ p))
+
+
+def getHamiltonian(data, mesh, inv, prior, momentum, factor_fn=default_factor, invM=None):
     """`getHamiltonian` HMCSampler.jl:358-397 -> (dataMisfit, kp, hmp, mnorm, predData).
     Uses mesh.sigma as left by the last compDataGradient / updateStartModel."""
     pred, _ = MT2DFwdSolver(mesh, data, factor_fn)
     dm = getDataMisfit(inv.dataW * (pred - inv.obsData))
-    kp = getKineticEnergy(momentum)
+    kp = getKineticEnergy(momentum, invM)
     mprior = inv.strModel - inv.refModel
     mnorm = 0.5 * float(mprior @ (inv.Wm @ mprior)) * prior.regParam
     return dm, kp, dm + kp + mnorm, mnorm, pred
@@ -138,8 +148,8 @@ def clip_momentum(z):
     return np.clip(z, -2.5, 2.5)
 
 
-def proposeLeapfrog(model, momentum, mesh, data, inv, prior, intstep, factor_fn=default_factor, trace=None):
-    """`proposeLeapfrog` HMCSampler.jl:206-269 with `intstep` injected (rand(t1:t2), :233)."""
+def proposeLeapfrog(model, momentum, mesh, data, inv, prior, intstep, factor_fn=default_factor, trace=None, invM=None):
+    """`proposeLeapfrog` HMCSampler.jl:206-269 with `intstep` injected (rand(t1:t2), :233); invM: getKineticGradient (:424-431)."""
     inv.strModel = model.copy()
     _, _, g = compDataGradient(mesh, data, inv, prior, factor_fn)
     g = g + (inv.Wm @ (model - inv.refModel)) * prior.regParam
@@ -147,7 +157,7 @@ def proposeLeapfrog(model, momentum, mesh, data, inv, prior, intstep, factor_fn=
     p = momentum - 0.5 * dt * g
     m = model.copy()
     for k in range(1, intstep + 1):
-        dm = dt * p
+        dm = dt * (p if invM is None else invM @ p)
         dmMax = np.max(np.abs(dm))
         if dmMax > 3.0:
             dm = dm / dmMax * 3.0
@@ -186,9 +196,11 @@ def runHMCSampler(mesh, data, inv: InvDataModel, prior: HMCPrior, streams: Rando
     """`runHMCSampler` HMCSampler.jl:72-196 -> (hmcmodel[nparam,nsamples], stats dict, hmcdata)."""
     nparam, ndata = len(inv.strModel), len(inv.obsData)
     nsamples = prior.totalsamples if nsamples is None else nsamples
+    invM, sqrtM = setMassMatrix(inv, prior)                 # :81-86
+    draw = (lambda z: clip_momentum(z)) if sqrtM is None else (lambda z: sqrtM @ clip_momentum(z))      # getMomentumVector :441-453
     cur_m = np.array(inv.strModel, dtype=float).copy()      # hmcParamCurrent.rhomodel = copy(invParam.strModel) (:87): the
     #                                                         model-file model, taken BEFORE strModel is replaced below (:100-109)
-    cur_p = clip_momentum(streams.z_init)
+    cur_p = draw(streams.z_init)
     sigma0 = inv.strModel[0]          # unique(strModel)[1]: Julia's unique keeps first-appearance order (:100-101)
     rho0 = 1.0 / np.exp(sigma0)
     rhoref = np.round(rho0 * 0.5 + (rho0 * 1.5 - rho0 * 0.5) * streams.u_start)
@@ -196,7 +208,7 @@ def runHMCSampler(mesh, data, inv: InvDataModel, prior: HMCPrior, streams: Rando
     inv.strModel = strModel.copy()
     inv.refModel = strModel.copy()
     mesh.sigma = inv.activeCell @ np.exp(inv.strModel) + inv.bgModel       # updateStartModel :834-849
-    startD, startK, startH, startM, pred = getHamiltonian(data, mesh, inv, prior, cur_p, factor_fn)
+    startD, startK, startH, startM, pred = getHamiltonian(data, mesh, inv, prior, cur_p, factor_fn, invM)
     hmcmodel = np.zeros((nparam, nsamples))
     hmcdata = np.zeros((ndata, nsamples + 1), dtype=np.complex128)
     hmstats = np.zeros((4, nsamples + 1))
@@ -205,8 +217,8 @@ def runHMCSampler(mesh, data, inv: InvDataModel, prior: HMCPrior, streams: Rando
     hmcdata[:, 0] = pred
     nAccept = nReject = 0
     for it in range(1, nsamples + 1):
-        pm, pp = proposeLeapfrog(cur_m, cur_p, mesh, data, inv, prior, int(streams.intsteps[it - 1]), factor_fn)
-        finD, finK, finH, finM, pred = getHamiltonian(data, mesh, inv, prior, pp, factor_fn)
+        pm, pp = proposeLeapfrog(cur_m, cur_p, mesh, data, inv, prior, int(streams.intsteps[it - 1]), factor_fn, invM=invM)
+        finD, finK, finH, finM, pred = getHamiltonian(data, mesh, inv, prior, pp, factor_fn, invM)
         hdif = startH - finH
         if hdif > 0 or streams.u_accept[it - 1] < np.exp(hdif):
             cur_m, cur_p = pm.copy(), pp.copy()
@@ -217,8 +229,8 @@ def runHMCSampler(mesh, data, inv: InvDataModel, prior: HMCPrior, streams: Rando
         else:
             nReject += 1
             hmcdata[:, it] = hmcdata[:, it - 1]
-        cur_p = clip_momentum(streams.z_momentum[it - 1])
-        startK = getKineticEnergy(cur_p)
+        cur_p = draw(streams.z_momentum[it - 1])
+        startK = getKineticEnergy(cur_p, invM)
         startH = startD + startM + startK
         hmstats[:, it] = [startD, startM, startK, startH]
         hmcmodel[:, it - 1] = cur_m

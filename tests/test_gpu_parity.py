@@ -291,3 +291,28 @@ def test_stale_factor_handle_is_refused():
     P2 = sp.csr_matrix(pi.activeCell.tocsc()[:, perm])
     g_p = api.compJacTMatVec(fwd_b.exTE, fwd_b.hxTM, v, pm, pd, P2, fwd_b.AinvTE, fwd_b.AinvTM)
     assert np.array_equal(g_p, g_b[perm])
+
+
+def test_explicit_jacobian_matches_reference_derivation():
+    """compJacMat (compJacMat.jl:7-381): the explicit complex Jacobian against the oracle's restatement, and its consistency with
+    J^T v (compJacTMatVec) on the device."""
+    from hmcmt2d_b200 import api
+    from oracle import forward as ofwd
+    from oracle import jacobian as ojac
+    mesh, data, inv, prior = tiny_problem(seed=19)
+    pm, pd, pi, pp = to_product(mesh, data, inv, prior)
+    pred, fwd = api.MT2DFwdSolver(pm, pd)
+    J = api.compJacMat(fwd.exTE, fwd.hxTM, pm, pd, pi.activeCell, fwd.AinvTE, fwd.AinvTM)
+    opred, ofw = ofwd.MT2DFwdSolver(mesh, data)
+    oJ = ojac.compJacMat(ofw.exTE, ofw.hxTM, mesh, data, inv.activeCell, ofw.AinvTE, ofw.AinvTM)
+    assert J.shape == oJ.shape == (len(pred), inv.activeCell.shape[1])
+    assert np.abs(J - oJ).max() / np.abs(oJ).max() < TOL
+    rng = np.random.default_rng(2)
+    v = rng.standard_normal(len(pred)) + 1j * rng.standard_normal(len(pred))
+    g = api.compJacTMatVec(fwd.exTE, fwd.hxTM, v, pm, pd, pi.activeCell, fwd.AinvTE, fwd.AinvTM)
+    assert np.abs(g - np.real(J.T @ np.conj(v))).max() / np.abs(g).max() < 1e-11
+    JT = api.compJacTMat(fwd.exTE, fwd.hxTM, pm, pd, pi.activeCell, fwd.AinvTE, fwd.AinvTM)
+    assert JT.shape == J.shape[::-1] and np.array_equal(JT, J.T)
+    # the responses of the plan are intact after the adjoint passes
+    pred2, _ = api.MT2DFwdSolver(pm, pd)
+    assert np.array_equal(pred2, pred)
