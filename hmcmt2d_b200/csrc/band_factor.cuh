@@ -222,8 +222,10 @@ struct EntryProvider {
 // UNROLL: the fully unrolled form has the shorter dependency chain (2 000 vs ~3 000 cycles alone) and suits kernels whose other
 // warps wait for it (mf_kernels.cuh); inside band_factor_kernel, where ~800 more instructions per macro-step compete for the
 // instruction cache with the tile warps' code, the rolled loop measured 5 % faster end to end.
+// nsteps < 8: rows / columns nsteps..7 are identity padding (multifrontal fronts pad their pivot counts to the tile size): their
+// pivot steps would change nothing and are skipped.
 template <bool UNROLL>
-__device__ __forceinline__ void gj_invert8(cplx& a0, cplx& a1, bool& bad, const int i, const int t) {
+__device__ __forceinline__ void gj_invert8(cplx& a0, cplx& a1, bool& bad, const int i, const int t, const int nsteps = 8) {
     const int j0 = 2 * t;
     cplx q = mk(1.0, 0.0);
     auto pivot_step = [&](const int k) {
@@ -254,7 +256,8 @@ __device__ __forceinline__ void gj_invert8(cplx& a0, cplx& a1, bool& bad, const 
     };
     if constexpr (UNROLL) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) pivot_step(k);
+        for (int k = 0; k < 8; ++k)
+            if (k < nsteps) pivot_step(k);
     } else {
 #pragma unroll 1
         for (int k = 0; k < 8; ++k) pivot_step(k);

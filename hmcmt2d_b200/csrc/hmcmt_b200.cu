@@ -56,7 +56,9 @@ struct hmcmt_plan {
     RxDev rx{};
     cudaStream_t stream = nullptr, side = nullptr;      // side: 1-D sensitivity scalars overlap the factorisation
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
-    cudaEvent_t evA = nullptr, evB = nullptr;
+    cudaEvent_t evA = nullptr, evB = nullptr, evPre = nullptr;
+    std::vector<cudaStream_t> groupStreams;             // >= 2: the systems of a step run as groups on these streams (compute_step_grouped)
+    std::vector<cudaEvent_t> groupDone;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> factorEvents;
     size_t factorEventsUsed = 0;
     int64_t launches = 0, factorLaunches = 0;
@@ -93,6 +95,7 @@ struct hmcmt_plan {
 
 namespace {
 
+constexpr int kDefaultGroups = 2;              // groups of systems per evaluation on the multifrontal path (HMCMT_GROUPS)
 constexpr size_t kMaxFactorEvents = 4096;      // CUDA-event pairs kept for hmcmt_kernel_time (opt-in, bounded)
 
 #define LAUNCH_CHECK(pl)                                          \
@@ -201,6 +204,11 @@ int mf_leaf_size() {
     const char* e = std::getenv("HMCMT_MF_LEAF");
     const int v = e ? std::atoi(e) : 16;
     return v < 1 ? 1 : v;
+}
+int mf_cross_size() {
+    const char* e = std::getenv("HMCMT_MF_CROSS");
+    const int v = e ? std::atoi(e) : 0;
+    return v < 0 ? 0 : v;
 }
 int mf_small_front() {
     const char* e = std::getenv("HMCMT_MF_FSMALL");
@@ -368,8 +376,18 @@ int launch_sens_side(hmcmt_plan* pl) {
     return kOk;
 }
 
-// forward part: sigma, stencil, boundary values, right-hand sides, factorisation + forward solve, node-ordered fields
-int forward_phase(hmcmt_plan* pl, bool wantAdjoint) {
+// A contiguous range of systems [s0, s0 + n) and the stream its work is queued on.  One evaluation either runs the whole batch
+// on the plan's stream, or (multifrontal solver, HMCMT_GROUPS >= 2) splits it into groups that run on their own streams: while
+// one group is in the few-CTA top levels of its elimination tree, in the receiver functional or in the contraction, the
+// thousands of small fronts of another group fill the SMs.  The systems of a step are independent (one per frequency x mode,
+// MT2DFwdSolver.jl:163-191), so the groups never exchange anything before the final sums over systems.
+struct SysRange {
+    int s0, n;
+    cudaStream_t st;
+};
+
+// sigma, stencil planes, boundary values and right-hand sides of ALL systems (cheap, plan stream)
+int forward_pre(hmcmt_plan* pl, bool wantAdjoint) {
     const MeshDev& M = pl->M;
     cudaStream_t st = pl->stream;
     const int nSys = pl->nSys, nCh = pl->nChains;
@@ -395,90 +413,149 @@ int forward_phase(hmcmt_plan* pl, bool wantAdjoint) {
         int rc = launch_sens_side(pl);
         if (rc) return rc;
     }
-    // factorisation + forward solve (timed with CUDA events only when the caller asked for it: hmcmt_kernel_time(reset=1))
-    {
-        std::pair<cudaEvent_t, cudaEvent_t>* ev = nullptr;
-        if (pl->timeFactor && pl->factorEventsUsed < kMaxFactorEvents) {
-            if (pl->factorEventsUsed == pl->factorEvents.size()) {
-                cudaEvent_t a, b;
-                HMCMT_CUDA_TRY(cudaEventCreate(&a));
-                HMCMT_CUDA_TRY(cudaEventCreate(&b));
-                pl->factorEvents.emplace_back(a, b);
-            }
-            ev = &pl->factorEvents[pl->factorEventsUsed++];
-            HMCMT_CUDA_TRY(cudaEventRecord(ev->first, st));
-        }
-        int rc;
-        if (pl->useMf) {
-            rc = pl->mfs->set_mt_values(st, M.N, pl->mfSys.p);
-            if (rc) return rc;
-            ++pl->launches;
-            rc = pl->mfs->factor(st, pl->status.p, &pl->launches);
-            if (rc) return rc;
-            rc = pl->mfs->solve(st, 1, pl->rhs.p, M.N, pl->x.p, M.N, &pl->launches);
-        } else {
-            int nl = 0;
-            rc = launch_factor(st, pl->T, pl->sysDesc.p, nSys, pl->dom, pl->fwdJobs.p, &nl);
-            pl->launches += nl;
-        }
+    return kOk;
+}
+
+// factorisation + forward solve + node-ordered fields of one range (the band kernels only take the whole batch)
+int forward_solve(hmcmt_plan* pl, const SysRange& r) {
+    const MeshDev& M = pl->M;
+    int rc;
+    if (pl->useMf) {
+        rc = pl->mfs->set_mt_values(r.st, M.N, pl->mfSys.p, r.s0, r.n);
         if (rc) return rc;
-        ++pl->factorLaunches;
-        if (ev) HMCMT_CUDA_TRY(cudaEventRecord(ev->second, st));
+        ++pl->launches;
+        rc = pl->mfs->factor(r.st, pl->status.p, &pl->launches, r.s0, r.n);
+        if (rc) return rc;
+        rc = pl->mfs->solve(r.st, 1, pl->rhs.p, M.N, pl->x.p, M.N, &pl->launches, r.s0, r.n);
+    } else {
+        if (r.s0 != 0 || r.n != pl->nSys) return kErrArg;
+        int nl = 0;
+        rc = launch_factor(r.st, pl->T, pl->sysDesc.p, pl->nSys, pl->dom, pl->fwdJobs.p, &nl);
+        pl->launches += nl;
     }
-    k_node_field<<<dim3((M.nNode + 255) / 256, nSys), 256, 0, st>>>(M, pl->x.p, pl->bc.p, pl->F.p);
+    return rc;
+}
+int forward_fields(hmcmt_plan* pl, const SysRange& r) {
+    const MeshDev& M = pl->M;
+    k_node_field<<<dim3((M.nNode + 255) / 256, r.n), 256, 0, r.st>>>(M, pl->x.p, pl->bc.p, pl->F.p, r.s0);
     LAUNCH_CHECK(pl);
+    return kOk;
+}
+
+// forward part of the whole batch on the plan's stream, the factorisation + forward solve timed with CUDA events when the caller
+// asked for it (hmcmt_kernel_time(reset=1))
+int forward_phase(hmcmt_plan* pl, bool wantAdjoint) {
+    cudaStream_t st = pl->stream;
+    int rc = forward_pre(pl, wantAdjoint);
+    if (rc) return rc;
+    std::pair<cudaEvent_t, cudaEvent_t>* ev = nullptr;
+    if (pl->timeFactor && pl->factorEventsUsed < kMaxFactorEvents) {
+        if (pl->factorEventsUsed == pl->factorEvents.size()) {
+            cudaEvent_t a, b;
+            HMCMT_CUDA_TRY(cudaEventCreate(&a));
+            HMCMT_CUDA_TRY(cudaEventCreate(&b));
+            pl->factorEvents.emplace_back(a, b);
+        }
+        ev = &pl->factorEvents[pl->factorEventsUsed++];
+        HMCMT_CUDA_TRY(cudaEventRecord(ev->first, st));
+    }
+    const SysRange all{0, pl->nSys, st};
+    rc = forward_solve(pl, all);
+    if (rc) return rc;
+    ++pl->factorLaunches;
+    if (ev) HMCMT_CUDA_TRY(cudaEventRecord(ev->second, st));
+    rc = forward_fields(pl, all);
+    if (rc) return rc;
     pl->haveForward = true;
     return kOk;
 }
 
 // receiver functional: responses, residual, misfit partial and (wantAdjoint) the adjoint sources for the data vector vin
 // (null: v = Wd^2 (pred - obs))
-int rx_phase(hmcmt_plan* pl, bool wantAdjoint, const cplx* vin) {
+int rx_range(hmcmt_plan* pl, const SysRange& r, bool wantAdjoint, const cplx* vin) {
     const MeshDev& M = pl->M;
-    cudaStream_t st = pl->stream;
     size_t rxSmem = (size_t)(6 * (M.ny + 1) + 3 * M.ny) * sizeof(cplx);
-    k_rx_adjoint<<<pl->nSys, kRxThreads, rxSmem, st>>>(M, pl->rx, pl->sm, pl->freqs.p, pl->sigma.p, pl->F.p, pl->obs.p, pl->wd.p, vin,
-                                                       pl->predFull.p, pl->phiPart.p, pl->srows.p, pl->qrow.p, pl->lam.p, wantAdjoint ? 1 : 0,
-                                                       pl->respKind, pl->respFull.p);
-    LAUNCH_CHECK(pl);
-    k_reduce_phi<<<pl->nChains, 32, 0, st>>>(pl->nSysPerChain, pl->phiPart.p, pl->phi.p);
+    k_rx_adjoint<<<r.n, kRxThreads, rxSmem, r.st>>>(M, pl->rx, pl->sm, pl->freqs.p, pl->sigma.p, pl->F.p, pl->obs.p, pl->wd.p, vin,
+                                                    pl->predFull.p, pl->phiPart.p, pl->srows.p, pl->qrow.p, pl->lam.p, wantAdjoint ? 1 : 0,
+                                                    pl->respKind, pl->respFull.p, r.s0);
     LAUNCH_CHECK(pl);
     return kOk;
 }
+int reduce_phi(hmcmt_plan* pl) {
+    k_reduce_phi<<<pl->nChains, 32, 0, pl->stream>>>(pl->nSysPerChain, pl->phiPart.p, pl->phi.p);
+    LAUNCH_CHECK(pl);
+    return kOk;
+}
+int rx_phase(hmcmt_plan* pl, bool wantAdjoint, const cplx* vin) {
+    int rc = rx_range(pl, SysRange{0, pl->nSys, pl->stream}, wantAdjoint, vin);
+    return rc ? rc : reduce_phi(pl);
+}
 
 // adjoint part: one solve per system with the factors of the forward phase (A symmetric: no transposition,
-// compJacTMatVec.jl:220-224), contraction into the gradient, prior gradient
-int adjoint_phase(hmcmt_plan* pl, bool reduce = true) {
+// compJacTMatVec.jl:220-224), contraction into the per-system gradient partials
+int adjoint_range(hmcmt_plan* pl, const SysRange& r) {
     const MeshDev& M = pl->M;
-    cudaStream_t st = pl->stream;
-    const int nSys = pl->nSys, nCh = pl->nChains;
+    cudaStream_t st = r.st;
     int rc;                                                            // lam <- A^{-1} s[ii]  (in place)
-    if (pl->useMf) rc = pl->mfs->solve(st, 1, pl->lam.p, M.N, pl->lam.p, M.N, &pl->launches);
+    if (pl->useMf) rc = pl->mfs->solve(st, 1, pl->lam.p, M.N, pl->lam.p, M.N, &pl->launches, r.s0, r.n);
     else {
-        rc = launch_solve(st, pl->T, pl->jobs.p, nSys, pl->dom);
+        if (r.s0 != 0 || r.n != pl->nSys) return kErrArg;
+        rc = launch_solve(st, pl->T, pl->jobs.p, pl->nSys, pl->dom);
         pl->launches += pl->dom.split ? 3 : 1;
     }
     if (rc) return rc;
-    k_node_field<<<dim3((M.nNode + 255) / 256, nSys), 256, 0, st>>>(M, pl->lam.p, nullptr, pl->Lam.p);
+    k_node_field<<<dim3((M.nNode + 255) / 256, r.n), 256, 0, st>>>(M, pl->lam.p, nullptr, pl->Lam.p, r.s0);
     LAUNCH_CHECK(pl);
     HMCMT_CUDA_TRY(cudaStreamWaitEvent(st, pl->evJoin, 0));
-    k_contract_cols<<<nSys, kConThreads, contract_cols_smem(M.ny, M.nz, pl->conStaged), st>>>(M, pl->sm, pl->freqs.p, pl->sigma.p, pl->Lam.p,
-                                                                                               pl->srows.p, pl->scratch.p, pl->conCols.p, pl->conStaged);
+    k_contract_cols<<<r.n, kConThreads, contract_cols_smem(M.ny, M.nz, pl->conStaged), st>>>(M, pl->sm, pl->freqs.p, pl->sigma.p, pl->Lam.p,
+                                                                                              pl->srows.p, pl->scratch.p, pl->conCols.p, pl->conStaged, r.s0);
     LAUNCH_CHECK(pl);
-    k_contract_cells<<<dim3((M.nCell + 255) / 256, nSys), 256, 0, st>>>(M, pl->sm, pl->freqs.p, pl->sigma.p, pl->F.p, pl->Lam.p, pl->qrow.p,
-                                                                        pl->bcs.p, pl->conCols.p, pl->Gpart.p);
-    LAUNCH_CHECK(pl);
-    if (!reduce) return kOk;
-    k_reduce_grad<<<dim3((pl->nAC + 255) / 256, nCh), 256, 0, st>>>(pl->nAC, M.nCell, pl->nSysPerChain, pl->act2cell.p, pl->Gpart.p,
-                                                                   pl->m.p, pl->mref.p, pl->wmPtr.p, pl->wmIdx.p, pl->wmVal.p, pl->beta,
-                                                                   pl->sigma.p, pl->gsig.p, pl->gdata.p, pl->gtotal.p);
+    k_contract_cells<<<dim3((M.nCell + 255) / 256, r.n), 256, 0, st>>>(M, pl->sm, pl->freqs.p, pl->sigma.p, pl->F.p, pl->Lam.p, pl->qrow.p,
+                                                                       pl->bcs.p, pl->conCols.p, pl->Gpart.p, r.s0);
     LAUNCH_CHECK(pl);
     return kOk;
+}
+// sum over the systems of a chain, chain rule to ln(sigma), prior gradient
+int reduce_grad(hmcmt_plan* pl) {
+    const MeshDev& M = pl->M;
+    k_reduce_grad<<<dim3((pl->nAC + 255) / 256, pl->nChains), 256, 0, pl->stream>>>(pl->nAC, M.nCell, pl->nSysPerChain, pl->act2cell.p, pl->Gpart.p,
+                                                                                    pl->m.p, pl->mref.p, pl->wmPtr.p, pl->wmIdx.p, pl->wmVal.p, pl->beta,
+                                                                                    pl->sigma.p, pl->gsig.p, pl->gdata.p, pl->gtotal.p);
+    LAUNCH_CHECK(pl);
+    return kOk;
+}
+int adjoint_phase(hmcmt_plan* pl, bool reduce = true) {
+    int rc = adjoint_range(pl, SysRange{0, pl->nSys, pl->stream});
+    if (rc || !reduce) return rc;
+    return reduce_grad(pl);
+}
+
+// forward + adjoint gradient of the whole batch with the systems split into groups on their own streams
+int compute_step_grouped(hmcmt_plan* pl) {
+    const int G = (int)pl->groupStreams.size();
+    int rc = forward_pre(pl, true);
+    if (rc) return rc;
+    HMCMT_CUDA_TRY(cudaEventRecord(pl->evPre, pl->stream));
+    for (int g = 0; g < G; ++g) {
+        const int s0 = (int)((int64_t)pl->nSys * g / G), s1 = (int)((int64_t)pl->nSys * (g + 1) / G);
+        if (s1 <= s0) continue;
+        const SysRange r{s0, s1 - s0, pl->groupStreams[g]};
+        HMCMT_CUDA_TRY(cudaStreamWaitEvent(r.st, pl->evPre, 0));
+        if ((rc = forward_solve(pl, r)) || (rc = forward_fields(pl, r)) || (rc = rx_range(pl, r, true, nullptr)) || (rc = adjoint_range(pl, r)))
+            return rc;
+        HMCMT_CUDA_TRY(cudaEventRecord(pl->groupDone[g], r.st));
+        HMCMT_CUDA_TRY(cudaStreamWaitEvent(pl->stream, pl->groupDone[g], 0));
+    }
+    ++pl->factorLaunches;
+    pl->haveForward = true;
+    if ((rc = reduce_phi(pl))) return rc;
+    return reduce_grad(pl);
 }
 
 // One evaluation of the hot path for the device-resident model pl->m:
 //   forward (all chains x modes x freqs) [+ adjoint gradient + prior gradient].
 int compute_step(hmcmt_plan* pl, bool wantAdjoint, const cplx* vin) {
+    if (wantAdjoint && !vin && pl->useMf && pl->groupStreams.size() >= 2 && !pl->timeFactor) return compute_step_grouped(pl);
     int rc = forward_phase(pl, wantAdjoint);
     if (rc) return rc;
     rc = rx_phase(pl, wantAdjoint, vin);
@@ -818,7 +895,7 @@ int hmcmt_plan_create(const hmcmt_problem* pr, hmcmt_plan** out) {
         // nested-dissection multifrontal solver for all systems of the plan (one symbolic analysis, shared by every system)
         std::vector<std::vector<int>> sn;
         std::vector<mf::Entry> ent;
-        mf::mf_order_grid(M.nl, M.nf, mf_leaf_size(), sn);
+        mf::mf_order_grid(M.nl, M.nf, mf_leaf_size(), sn, mf_cross_size());
         mf::mf_grid_entries(M.nl, M.nf, ent);
         mf::Symbolic S;
         if (!mf::mf_symbolic(M.N, sn, ent, mf_small_front(), S)) { hmcmt_destroy(pl); return kErrArg; }
@@ -833,9 +910,24 @@ int hmcmt_plan_create(const hmcmt_problem* pr, hmcmt_plan** out) {
         cudaStreamCreateWithFlags(&pl->side, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&pl->evFork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&pl->evJoin, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&pl->evPre, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&pl->evA) != cudaSuccess || cudaEventCreate(&pl->evB) != cudaSuccess) {
         hmcmt_destroy(pl);
         return kErrCuda;
+    }
+    if (pl->useMf) {
+        // groups of systems on their own streams (compute_step_grouped); HMCMT_GROUPS=1 keeps everything on the plan's stream
+        const char* env = std::getenv("HMCMT_GROUPS");
+        int G = env ? std::atoi(env) : kDefaultGroups;
+        G = std::max(1, std::min(G, std::min(pl->nSys, 8)));
+        for (int g = 0; G >= 2 && g < G; ++g) {
+            cudaStream_t s = nullptr;
+            cudaEvent_t e = nullptr;
+            if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) { hmcmt_destroy(pl); return kErrCuda; }
+            pl->groupStreams.push_back(s);
+            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { hmcmt_destroy(pl); return kErrCuda; }
+            pl->groupDone.push_back(e);
+        }
     }
     *out = pl;
     return kOk;
@@ -851,6 +943,9 @@ void hmcmt_destroy(hmcmt_plan* pl) {
     }
     if (pl->stream) { cudaStreamSynchronize(pl->stream); cudaStreamDestroy(pl->stream); }
     if (pl->side) { cudaStreamSynchronize(pl->side); cudaStreamDestroy(pl->side); }
+    for (cudaStream_t s : pl->groupStreams) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+    for (cudaEvent_t e : pl->groupDone) cudaEventDestroy(e);
+    if (pl->evPre) cudaEventDestroy(pl->evPre);
     if (pl->evFork) cudaEventDestroy(pl->evFork);
     if (pl->evJoin) cudaEventDestroy(pl->evJoin);
     if (pl->evA) cudaEventDestroy(pl->evA);
@@ -1013,7 +1108,9 @@ int hmcmt_kernel_time(hmcmt_plan* pl, int reset, float* factor_ms, int64_t* fact
     }
     if (factor_ms) *factor_ms = tot;
     if (factor_launches) *factor_launches = (int64_t)pl->factorEventsUsed;
-    if (reset) { pl->factorEventsUsed = 0; pl->timeFactor = true; }      // timing is opt-in: the first reset switches it on
+    // timing is opt-in: reset = 1 switches it on (the evaluations then run un-grouped on the plan's stream so that the events
+    // bracket the factorisation alone), reset = -1 switches it off again
+    if (reset) { pl->factorEventsUsed = 0; pl->timeFactor = reset > 0; }
     return kOk;
 }
 

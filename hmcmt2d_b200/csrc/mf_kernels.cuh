@@ -48,200 +48,222 @@ struct Tables {
 #define MF_PROF_MARK(slot) do { if (tb.prof && threadIdx.x == 0) { const long long _t = clock64(); atomicAdd(tb.prof + _pc * 8 + (slot), (unsigned long long)(_t - _t0)); _t0 = _t; } } while (0)
 
 // ------------------------------------------------------------------------------------------------------------------------
-// block sweep of the first npb pivot blocks of an nb x nb tile matrix held in shared memory (lower-triangle tiles, 128 doubles
-// each: [plane][8][8]; of a diagonal tile only the lower triangle is meaningful: it is always read mirrored).  On return: pivot x pivot tiles hold -G, rest x pivot tiles hold M, rest x rest U.
+// Fronts in shared memory: lower-triangle 8x8 tiles, tile (I,J), I >= J, at tiles + (I(I+1)/2 + J) * 128 doubles.  Inside a tile the
+// layout is the k-grouped one of the global matrices, element (r,c) of plane pl at pl*64 + (c/4)*32 + r*4 + c%4:
+//   * the DMMA A / B operand of a k-half (lane (g,t) reads [row g][k 4kk+t]) is 32 consecutive doubles: conflict-free, so the tiles
+//     themselves serve as operands and no operand panels are copied;
+//   * the C fragment (lane holds [g][2t], [g][2t+1]) is two runs of 32 consecutive doubles read / written as 16-byte pairs;
+//   * a (plane, column group) chunk of a tile is 32 consecutive doubles in shared AND in global memory (kg_off): outputs are
+//     straight vector copies.
+// Of a diagonal tile the assembly maintains the lower triangle only; the pivot-block sweep replaces the pivot diagonal tiles by
+// full symmetric ones.
+__device__ __forceinline__ int tl_off(int r, int c) { return ((c >> 2) << 5) | (r << 2) | (c & 3); }
+__device__ __forceinline__ double* mf_tile(double* tiles, int I, int J) { return tiles + (size_t)(I * (I + 1) / 2 + J) * 128; }
+
+struct TileFrag {      // A or B operand of one 8x8 complex tile (both k-halves), or its C fragment
+    double re[2], im[2];
+};
+// operand [row g][k 4kk+t] of the tile as stored / of its transpose
+__device__ __forceinline__ void frag_load(TileFrag& f, const double* T, int lane) {
+    f.re[0] = T[lane]; f.re[1] = T[32 + lane]; f.im[0] = T[64 + lane]; f.im[1] = T[96 + lane];
+}
+__device__ __forceinline__ void frag_load_t(TileFrag& f, const double* T, int g, int t) {
+    const int o0 = tl_off(t, g), o1 = tl_off(4 + t, g);
+    f.re[0] = T[o0]; f.re[1] = T[o1]; f.im[0] = T[64 + o0]; f.im[1] = T[64 + o1];
+}
+__device__ __forceinline__ void frag_store(const TileFrag& f, double* T, int lane) {
+    T[lane] = f.re[0]; T[32 + lane] = f.re[1]; T[64 + lane] = f.im[0]; T[96 + lane] = f.im[1];
+}
+// C fragment: elements (g, 2t), (g, 2t+1)
+__device__ __forceinline__ void cfrag_load(TileFrag& c, const double* T, int g, int t) {
+    const int o = tl_off(g, 2 * t);
+    const double2 r = *reinterpret_cast<const double2*>(T + o), i = *reinterpret_cast<const double2*>(T + 64 + o);
+    c.re[0] = r.x; c.re[1] = r.y; c.im[0] = i.x; c.im[1] = i.y;
+}
+__device__ __forceinline__ void cfrag_store(const TileFrag& c, double* T, int g, int t, double sign = 1.0) {
+    const int o = tl_off(g, 2 * t);
+    *reinterpret_cast<double2*>(T + o) = make_double2(sign * c.re[0], sign * c.re[1]);
+    *reinterpret_cast<double2*>(T + 64 + o) = make_double2(sign * c.im[0], sign * c.im[1]);
+}
+// c += a b^T (complex, no conjugation), x accumulates the -Im Im / Im Re parts separately: two independent DMMA chains per plane
+__device__ __forceinline__ void frag_mma(TileFrag& c, TileFrag& x, const TileFrag& a, const TileFrag& b) {
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+        dmma884(c.re, a.re[kk], b.re[kk]);
+        dmma884(c.im, a.re[kk], b.im[kk]);
+        dmma884(x.re, -a.im[kk], b.im[kk]);
+        dmma884(x.im, a.im[kk], b.re[kk]);
+    }
+}
+__device__ __forceinline__ void frag_zero(TileFrag& c) { c.re[0] = c.re[1] = c.im[0] = c.im[1] = 0.0; }
+__device__ __forceinline__ void frag_add(TileFrag& c, const TileFrag& x) {
+    c.re[0] += x.re[0]; c.re[1] += x.re[1]; c.im[0] += x.im[0]; c.im[1] += x.im[1];
+}
+
+// Partial factorisation of an nb x nb tile matrix whose first npb tile rows / columns are the pivots (sReal of the 8 npb pivot
+// unknowns are real, the rest identity padding):
+//   B  block sweep of the pivot x pivot tiles alone (8x8 pivot blocks inverted in registers)         -> pivot tiles = -G (full)
+//   C  M' = F21 (-G)      into mbuf (tile (I - npb, kb) at mbuf + ((I - npb) npb + kb) 128)          -> mbuf = -M
+//   D  U  = F22 + M' F21^T  accumulated over all pivots in registers                                  -> update tiles = U
+// The update rows never enter the latency-bound sweep: they see two perfectly parallel products with K = all pivots.
+// scratch: 2 npb tiles (column operands of the sweep; may alias mbuf).  All NW warps call; ends with a CTA barrier.
 template <int NW>
-__device__ __forceinline__ void mf_sweep(double* __restrict__ tiles, double* __restrict__ raw, double* __restrict__ mm,
-                                         double* __restrict__ nainv, int* __restrict__ fail, const int nb, const int npb,
-                                         unsigned long long* __restrict__ prof = nullptr) {
+__device__ __forceinline__ void mf_front_factor(double* __restrict__ tiles, double* __restrict__ scratch, double* __restrict__ mbuf,
+                                                double* __restrict__ nainv, int* __restrict__ fail, const int nb, const int npb,
+                                                const int sReal, unsigned long long* __restrict__ prof = nullptr) {
     const int tid = threadIdx.x, lane = tid & 31;
     long long _s0 = prof ? clock64() : 0;
 #define MF_SWEEP_MARK(slot) do { if (prof && tid == 0) { const long long _t = clock64(); atomicAdd(prof + (slot), (unsigned long long)(_t - _s0)); _s0 = _t; } } while (0)
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int g = lane >> 2, t = lane & 3;
-    const int R = nb * 8;
-    const int nT = nb * (nb + 1) / 2;
-    auto tileP = [&](int I, int J) { return tiles + (size_t)(I * (I + 1) / 2 + J) * 128; };
-    auto opnd = [&](double* base, int pl, int kk, int row) { return base + ((size_t)(pl * 2 + kk) * R + row) * 4; };
-    // lane roles of the tile <-> operand-panel copies: plane, row, k-half
-    const int cpl = lane >> 4, crow = (lane >> 1) & 7, ckk = lane & 1;
+    double* const rawb = scratch;                         // raw_I = A[I][kb] of the current sweep step, I in the pivot range
+    double* const mmb = scratch + (size_t)npb * 128;      // m_I = raw_I (-P)
+    // ---- B: sweep of the pivot block ----
     for (int kb = 0; kb < npb; ++kb) {
-        // (a) column block kb of the symmetric matrix as an operand panel: raw_I = A[I][kb]  (one tile per warp and trip)
-        for (int I = warp; I < nb; I += NW) {
-            double2 v01, v23;
-            if (I > kb) {
-                const double* src = tileP(I, kb) + cpl * 64 + crow * 8 + ckk * 4;
-                v01 = *reinterpret_cast<const double2*>(src);
-                v23 = *reinterpret_cast<const double2*>(src + 2);
-            } else if (I == kb) {          // diagonal tile: only its lower triangle is maintained -> mirrored read
-                const double* D = tileP(kb, kb) + cpl * 64;
-                const int c0 = ckk * 4;
-                auto sym = [&](int r, int c) { return r >= c ? D[r * 8 + c] : D[c * 8 + r]; };
-                v01 = make_double2(sym(crow, c0), sym(crow, c0 + 1));
-                v23 = make_double2(sym(crow, c0 + 2), sym(crow, c0 + 3));
-            } else {
-                const double* src = tileP(kb, I) + cpl * 64 + (ckk * 4) * 8 + crow;
-                v01 = make_double2(src[0], src[8]);
-                v23 = make_double2(src[16], src[24]);
-            }
-            double* dst = opnd(raw, cpl, ckk, I * 8 + crow);
-            *reinterpret_cast<double2*>(dst) = v01;
-            *reinterpret_cast<double2*>(dst + 2) = v23;
-        }
-        // (b) P = A[kb][kb]^{-1} in registers (warp 0 reads the diagonal tile itself: no barrier needed before);
-        //     publish -P as the B operand and as the new diagonal tile
         if (warp == 0) {
-            __syncwarp();
-            double* D = tileP(kb, kb);
-            auto symre = [&](int r, int c) { return r >= c ? D[r * 8 + c] : D[c * 8 + r]; };
-            auto symim = [&](int r, int c) { return r >= c ? D[64 + r * 8 + c] : D[64 + c * 8 + r]; };
-            cplx a0 = mk(symre(g, 2 * t), symim(g, 2 * t)), a1 = mk(symre(g, 2 * t + 1), symim(g, 2 * t + 1));
+            // P = A[kb][kb]^{-1} in registers (mirrored read of the lower triangle), -P published as an operand tile
+            const double* D = mf_tile(tiles, kb, kb);
+            auto sym = [&](int r, int c, int pl) { return r >= c ? D[pl * 64 + tl_off(r, c)] : D[pl * 64 + tl_off(c, r)]; };
+            cplx a0 = mk(sym(g, 2 * t, 0), sym(g, 2 * t, 1)), a1 = mk(sym(g, 2 * t + 1, 0), sym(g, 2 * t + 1, 1));
             bool bad = false;
-            gj_invert8<true>(a0, a1, bad, g, t);
+            const int left = sReal - 8 * kb;
+            gj_invert8<true>(a0, a1, bad, g, t, left < 8 ? (left < 0 ? 0 : left) : 8);
             if (__any_sync(0xffffffffu, bad) && lane == 0) *fail = 1;
-            const int j0 = 2 * t;
-            *reinterpret_cast<double2*>(nainv + ((0 * 2 + (j0 >> 2)) * 8 + g) * 4 + (j0 & 3)) = make_double2(-a0.x, -a1.x);
-            *reinterpret_cast<double2*>(nainv + ((1 * 2 + (j0 >> 2)) * 8 + g) * 4 + (j0 & 3)) = make_double2(-a0.y, -a1.y);
+            TileFrag p;
+            p.re[0] = -a0.x; p.re[1] = -a1.x; p.im[0] = -a0.y; p.im[1] = -a1.y;
+            cfrag_store(p, nainv, g, t);
+            __syncwarp();
+            // the diagonal tile itself takes -P (nobody else reads it during this step)
+            double* Dw = mf_tile(tiles, kb, kb);
+            cfrag_store(p, Dw, g, t);
         }
+        if (npb == 1) break;
+        __syncthreads();
         MF_SWEEP_MARK(0);
+        // m_I = raw_I (-P) for the other pivot block rows; raw_I kept as an operand tile for the update below
+        for (int I = warp; I < npb; I += NW) {
+            if (I == kb) continue;
+            TileFrag a, b, c, x;
+            if (I > kb) frag_load(a, mf_tile(tiles, I, kb), lane);
+            else frag_load_t(a, mf_tile(tiles, kb, I), g, t);
+            frag_load(b, nainv, lane);
+            frag_zero(c); frag_zero(x);
+            frag_mma(c, x, a, b);
+            frag_add(c, x);
+            frag_store(a, rawb + (size_t)I * 128, lane);
+            cfrag_store(c, mmb + (size_t)I * 128, g, t);
+        }
         __syncthreads();
         MF_SWEEP_MARK(1);
-        if (warp == 0) {       // the raw copy of the diagonal tile is complete: the tile itself may now take -P
-            double* D = tileP(kb, kb);
-            const int j0 = 2 * t;
-            const double2 pre = *reinterpret_cast<const double2*>(nainv + ((0 * 2 + (j0 >> 2)) * 8 + g) * 4 + (j0 & 3));
-            const double2 pim = *reinterpret_cast<const double2*>(nainv + ((1 * 2 + (j0 >> 2)) * 8 + g) * 4 + (j0 & 3));
-            *reinterpret_cast<double2*>(D + g * 8 + 2 * t) = pre;
-            *reinterpret_cast<double2*>(D + 64 + g * 8 + 2 * t) = pim;
-        }
-        // (c) m_I = raw_I (-P) for every block row I != kb
-        for (int I = warp; I < nb; I += NW) {
-            if (I == kb) continue;
-            double mre[2] = {0.0, 0.0}, mim[2] = {0.0, 0.0}, mr2[2] = {0.0, 0.0}, mi2[2] = {0.0, 0.0};
-            const int r = I * 8 + g;
-#pragma unroll
-            for (int kk = 0; kk < 2; ++kk) {
-                const double are = opnd(raw, 0, kk, r)[t], aim = opnd(raw, 1, kk, r)[t];
-                const double bre = nainv[((0 * 2 + kk) * 8 + g) * 4 + t], bim = nainv[((1 * 2 + kk) * 8 + g) * 4 + t];
-                dmma884(mre, are, bre);
-                dmma884(mim, are, bim);
-                dmma884(mr2, -aim, bim);
-                dmma884(mi2, aim, bre);
+        // A[I][J] += m_I raw_J^T (I, J != kb), column / row kb <- -m
+        {
+            int I = 0, J = warp;
+            while (J > I) { J -= I + 1; ++I; }
+            for (int L = warp; L < npb * (npb + 1) / 2; L += NW) {
+                double* T = mf_tile(tiles, I, J);
+                if (I == kb && J == kb) {
+                } else if (J == kb) {
+                    TileFrag c;
+                    cfrag_load(c, mmb + (size_t)I * 128, g, t);
+                    cfrag_store(c, T, g, t, -1.0);
+                } else if (I == kb) {              // J < kb: tile (kb, J) = -(m_J)^T
+                    const double* Ms = mmb + (size_t)J * 128;
+                    TileFrag c;
+                    c.re[0] = Ms[tl_off(2 * t, g)]; c.re[1] = Ms[tl_off(2 * t + 1, g)];
+                    c.im[0] = Ms[64 + tl_off(2 * t, g)]; c.im[1] = Ms[64 + tl_off(2 * t + 1, g)];
+                    cfrag_store(c, T, g, t, -1.0);
+                } else {
+                    TileFrag a, b, c, x;
+                    frag_load(a, mmb + (size_t)I * 128, lane);
+                    frag_load(b, rawb + (size_t)J * 128, lane);
+                    cfrag_load(c, T, g, t);
+                    frag_zero(x);
+                    frag_mma(c, x, a, b);
+                    frag_add(c, x);
+                    cfrag_store(c, T, g, t);
+                }
+                J += NW;
+                while (J > I) { J -= I + 1; ++I; }
             }
-            mre[0] += mr2[0]; mre[1] += mr2[1]; mim[0] += mi2[0]; mim[1] += mi2[1];
-            *reinterpret_cast<double2*>(opnd(mm, 0, t >> 1, r) + (t & 1) * 2) = make_double2(mre[0], mre[1]);
-            *reinterpret_cast<double2*>(opnd(mm, 1, t >> 1, r) + (t & 1) * 2) = make_double2(mim[0], mim[1]);
         }
         __syncthreads();
         MF_SWEEP_MARK(2);
-        // (d) A[I][J] += m_I raw_J^T for I,J != kb ;  (e) column kb <- raw P = -m.   Lower tiles dealt round-robin to the warps;
-        // trailing updates are issued two tiles at a time (16 independent DMMAs in flight: their latency is ~138 cycles).
-        auto upd_load = [&](double* T, double (&cre)[2], double (&cim)[2]) {
-            const double2 cr = *reinterpret_cast<const double2*>(T + g * 8 + 2 * t);
-            const double2 ci = *reinterpret_cast<const double2*>(T + 64 + g * 8 + 2 * t);
-            cre[0] = cr.x; cre[1] = cr.y; cim[0] = ci.x; cim[1] = ci.y;
-        };
-        auto upd_mma = [&](int I_, int J_, double (&cre)[2], double (&cim)[2], double (&t1)[2], double (&t2)[2]) {
-            const int ra = I_ * 8 + g, rb = J_ * 8 + g;
-#pragma unroll
-            for (int kk = 0; kk < 2; ++kk) {
-                const double are = opnd(mm, 0, kk, ra)[t], aim = opnd(mm, 1, kk, ra)[t];
-                const double bre = opnd(raw, 0, kk, rb)[t], bim = opnd(raw, 1, kk, rb)[t];
-                dmma884(cre, are, bre);
-                dmma884(cim, are, bim);
-                dmma884(t1, -aim, bim);
-                dmma884(t2, aim, bre);
-            }
-        };
-        auto upd_store = [&](double* T, const double (&cre)[2], const double (&cim)[2], const double (&t1)[2], const double (&t2)[2]) {
-            *reinterpret_cast<double2*>(T + g * 8 + 2 * t) = make_double2(cre[0] + t1[0], cre[1] + t1[1]);
-            *reinterpret_cast<double2*>(T + 64 + g * 8 + 2 * t) = make_double2(cim[0] + t2[0], cim[1] + t2[1]);
-        };
+    }
+    const int nub = nb - npb;
+    if (nub == 0) { __syncthreads(); return; }
+    __syncthreads();
+    // ---- C: M'(I, kb) = sum_j F21(I, j) (-G)(j, kb) ----
+    for (int q = warp; q < nub * npb; q += NW) {
+        const int Iu = q / npb, kb = q - Iu * npb, I = npb + Iu;
+        TileFrag c, x;
+        frag_zero(c); frag_zero(x);
+        for (int j = 0; j < npb; ++j) {
+            TileFrag a, b;
+            frag_load(a, mf_tile(tiles, I, j), lane);
+            if (kb >= j) frag_load(b, mf_tile(tiles, kb, j), lane);       // B[n][k] = (-G)(kb n, j k)
+            else frag_load_t(b, mf_tile(tiles, j, kb), g, t);
+            frag_mma(c, x, a, b);
+        }
+        frag_add(c, x);
+        cfrag_store(c, mbuf + (size_t)q * 128, g, t);
+    }
+    __syncthreads();
+    MF_SWEEP_MARK(3);
+    // ---- D: U(I, J) += sum_kb M'(I, kb) F21(J, kb)^T, lower tiles, two tiles per trip (independent DMMA chains) ----
+    {
+        const int nU = nub * (nub + 1) / 2;
         int I = 0, J = warp;
         while (J > I) { J -= I + 1; ++I; }
-        int pI = -1, pJ = -1;          // pending trailing-update tile (waiting for a partner)
-        for (int L = warp; L < nT; L += NW) {
-            double* T = tileP(I, J);
-            if (I == kb && J == kb) {
-            } else if (J == kb) {              // I > kb
-                const double2 a = *reinterpret_cast<const double2*>(opnd(mm, 0, t >> 1, I * 8 + g) + (t & 1) * 2);
-                const double2 b = *reinterpret_cast<const double2*>(opnd(mm, 1, t >> 1, I * 8 + g) + (t & 1) * 2);
-                *reinterpret_cast<double2*>(T + g * 8 + 2 * t) = make_double2(-a.x, -a.y);
-                *reinterpret_cast<double2*>(T + 64 + g * 8 + 2 * t) = make_double2(-b.x, -b.y);
-            } else if (I == kb) {              // J < kb: transposed
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    T[g * 8 + 2 * t + e] = -opnd(mm, 0, g >> 2, J * 8 + 2 * t + e)[g & 3];
-                    T[64 + g * 8 + 2 * t + e] = -opnd(mm, 1, g >> 2, J * 8 + 2 * t + e)[g & 3];
-                }
-            } else if (pI < 0) {
-                pI = I; pJ = J;
-            } else {
-                double* T0 = tileP(pI, pJ);
-                double c0r[2], c0i[2], c1r[2], c1i[2], a1[2] = {0.0, 0.0}, a2[2] = {0.0, 0.0}, b1[2] = {0.0, 0.0}, b2[2] = {0.0, 0.0};
-                upd_load(T0, c0r, c0i);
-                upd_load(T, c1r, c1i);
-                upd_mma(pI, pJ, c0r, c0i, a1, a2);
-                upd_mma(I, J, c1r, c1i, b1, b2);
-                upd_store(T0, c0r, c0i, a1, a2);
-                upd_store(T, c1r, c1i, b1, b2);
-                pI = -1;
-            }
+        for (int L = warp; L < nU; L += 2 * NW) {
+            const int I0 = I, J0 = J;
             J += NW;
             while (J > I) { J -= I + 1; ++I; }
+            const bool two = L + NW < nU;
+            const int I1 = I, J1 = J;
+            J += NW;
+            while (J > I) { J -= I + 1; ++I; }
+            double* T0 = mf_tile(tiles, npb + I0, npb + J0);
+            double* T1 = mf_tile(tiles, npb + I1, npb + J1);
+            TileFrag c0, x0, c1, x1;
+            cfrag_load(c0, T0, g, t);
+            frag_zero(x0);
+            if (two) { cfrag_load(c1, T1, g, t); frag_zero(x1); }
+            for (int kb = 0; kb < npb; ++kb) {
+                TileFrag a, b;
+                frag_load(a, mbuf + (size_t)(I0 * npb + kb) * 128, lane);
+                frag_load(b, mf_tile(tiles, npb + J0, kb), lane);
+                frag_mma(c0, x0, a, b);
+                if (two) {
+                    frag_load(a, mbuf + (size_t)(I1 * npb + kb) * 128, lane);
+                    frag_load(b, mf_tile(tiles, npb + J1, kb), lane);
+                    frag_mma(c1, x1, a, b);
+                }
+            }
+            frag_add(c0, x0);
+            cfrag_store(c0, T0, g, t);
+            if (two) { frag_add(c1, x1); cfrag_store(c1, T1, g, t); }
         }
-        if (pI >= 0) {
-            double* T0 = tileP(pI, pJ);
-            double c0r[2], c0i[2], a1[2] = {0.0, 0.0}, a2[2] = {0.0, 0.0};
-            upd_load(T0, c0r, c0i);
-            upd_mma(pI, pJ, c0r, c0i, a1, a2);
-            upd_store(T0, c0r, c0i, a1, a2);
-        }
-        __syncthreads();
-        MF_SWEEP_MARK(3);
     }
+    __syncthreads();
+    MF_SWEEP_MARK(3);
 #undef MF_SWEEP_MARK
 }
 
-__host__ __device__ inline size_t mf_sweep_smem_bytes(int nb) {
-    return ((size_t)nb * (nb + 1) / 2 * 128 + 2 * 16 * (size_t)nb * 8 + 128) * sizeof(double) + 16;
-}
-
-// element (a,b) of the symmetric tile matrix, a,b local indices
-__device__ __forceinline__ cplx mf_tile_get(const double* tiles, int a, int b) {
-    if (a < b) { const int x = a; a = b; b = x; }
-    const int I = a >> 3, J = b >> 3;
-    const double* T = tiles + (size_t)(I * (I + 1) / 2 + J) * 128 + (a & 7) * 8 + (b & 7);
-    return mk(T[0], T[64]);
-}
-
-// one 8x8 tile (shared memory, [plane][8][8]) -> k-grouped global matrix with ld rows at (row0, col0); executed by one warp:
-// lane = (chunk, row): chunk = (plane, column group of four), 32 contiguous bytes per lane, 256 per eight lanes.
-// TRANSPOSED: the tile holds the transposed block.  sign: +1 / -1.
-// MODE 0: as stored, 1: transposed, 2: diagonal tile (lower triangle mirrored)
-template <int MODE>
+// one 8x8 tile (shared memory) -> k-grouped global matrix with ld rows at (row0, col0), executed by one warp: the four (plane,
+// column group) chunks are 32 consecutive doubles on both sides.  TRANSPOSED: the tile holds the transposed block (gather).
+template <bool TRANSPOSED>
 __device__ __forceinline__ void mf_store_tile(const double* __restrict__ T, double* __restrict__ dst, int ld, int row0, int col0,
                                               double sign, int lane) {
-    const int pl = lane >> 4, cg = (lane >> 3) & 1, row = lane & 7;
-    double2 v01, v23;
-    if (MODE == 0) {
-        const double* src = T + pl * 64 + row * 8 + cg * 4;
-        v01 = *reinterpret_cast<const double2*>(src);
-        v23 = *reinterpret_cast<const double2*>(src + 2);
-    } else if (MODE == 2) {
-        const double* D = T + pl * 64;
-        const int c0 = cg * 4;
-        auto sym = [&](int r, int c) { return r >= c ? D[r * 8 + c] : D[c * 8 + r]; };
-        v01 = make_double2(sym(row, c0), sym(row, c0 + 1));
-        v23 = make_double2(sym(row, c0 + 2), sym(row, c0 + 3));
-    } else {
-        const double* src = T + pl * 64 + (cg * 4) * 8 + row;
-        v01 = make_double2(src[0], src[8]);
-        v23 = make_double2(src[16], src[24]);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int idx = lane + 32 * h;               // 16-byte pair index: chunk = idx / 16, (row, column pair) inside
+        const int chunk = idx >> 4, w = idx & 15, pl = chunk >> 1, cg = chunk & 1, r = w >> 1, c2 = (w & 1) * 2;
+        double2 v;
+        if (!TRANSPOSED) v = *reinterpret_cast<const double2*>(T + chunk * 32 + w * 2);
+        else v = make_double2(T[pl * 64 + tl_off(cg * 4 + c2, r)], T[pl * 64 + tl_off(cg * 4 + c2 + 1, r)]);
+        double* out = dst + kg_off(ld, row0 + r, col0 + cg * 4, pl) + c2;
+        *reinterpret_cast<double2*>(out) = make_double2(sign * v.x, sign * v.y);
     }
-    double* out = dst + kg_off(ld, row0 + row, col0 + cg * 4, pl);
-    *reinterpret_cast<double2*>(out) = make_double2(sign * v01.x, sign * v01.y);
-    *reinterpret_cast<double2*>(out + 2) = make_double2(sign * v23.x, sign * v23.y);
 }
 
 // ------------------------------------------------------------------------------------------------------------------------
@@ -254,12 +276,11 @@ mf_small_kernel(Tables tb, const int* __restrict__ list) {
     const Front F = tb.fronts[list[blockIdx.x]];
     const int sys = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-    const int fp = F.sp + F.up, nb = fp >> 3, npb = F.sp >> 3;
+    const int fp = F.sp + F.up, nb = fp >> 3, npb = F.sp >> 3, nub = nb - npb;
     const int nT = nb * (nb + 1) / 2;
     double* tiles = reinterpret_cast<double*>(mf_smem);
-    double* raw = tiles + (size_t)nT * 128;
-    double* mm = raw + 16 * (size_t)fp;
-    double* nainv = mm + 16 * (size_t)fp;
+    double* mbuf = tiles + (size_t)nT * 128;                                   // sweep scratch, then M'
+    double* nainv = mbuf + (size_t)(2 * npb > nub * npb ? 2 * npb : nub * npb) * 128;
     int* fail = reinterpret_cast<int*>(nainv + 128);
     constexpr int _pc = NW == 2 ? 0 : (NW == 4 ? 1 : (NW == 8 ? 2 : 3));      // profiler class
     long long _t0 = clock64();
@@ -277,12 +298,12 @@ mf_small_kernel(Tables tb, const int* __restrict__ list) {
     __syncthreads();
     MF_PROF_MARK(0);
     auto addr = [&](int a, int b) {       // a >= b
-        return tiles + (size_t)((a >> 3) * ((a >> 3) + 1) / 2 + (b >> 3)) * 128 + (a & 7) * 8 + (b & 7);
+        return tiles + (size_t)((a >> 3) * ((a >> 3) + 1) / 2 + (b >> 3)) * 128 + tl_off(a & 7, b & 7);
     };
     // extend-add of the children's update matrices, one child at a time (entries of one child never collide: plain adds, fixed
-    // order -> deterministic).  The child's row map is staged in shared memory (the operand panel is still unused).
+    // order -> deterministic).  The child's row map is staged in shared memory (the M' buffer is still unused).
     const double* carena = tb.arena[(F.depth + 1) & 1] + (size_t)sys * tb.arenaStride[(F.depth + 1) & 1];
-    int* relS = reinterpret_cast<int*>(raw);
+    int* relS = reinterpret_cast<int*>(mbuf);
     for (int c = 0; c < F.nChild; ++c) {
         const Front& C = tb.fronts[tb.children[F.childPtr + c]];
         const int cu = C.u, cup = C.up;
@@ -293,8 +314,7 @@ mf_small_kernel(Tables tb, const int* __restrict__ list) {
         __syncthreads();
         // work items = (column group of four, block of 32 rows) of the child's lower triangle, dealt round-robin; a warp issues
         // the loads of kBatch items (16-byte loads, 64 bytes per lane and item) before it scatters them, so that several
-        // global-memory round trips are in flight.  (A 4-row x 8-column lane mapping avoids the shared-memory bank conflicts of
-        // the scatter but measured slower: the phase is bound by the latency of these loads, not by the scatter.)
+        // global-memory round trips are in flight.
         const int ng = (cu + 3) >> 2, nrb = (cu + 31) >> 5;
         constexpr int kBatch = 4;
         for (int q0 = warp * kBatch; q0 < ng * nrb; q0 += NW * kBatch) {
@@ -347,33 +367,31 @@ mf_small_kernel(Tables tb, const int* __restrict__ list) {
     }
     __syncthreads();
     MF_PROF_MARK(1);
-    mf_sweep<NW>(tiles, raw, mm, nainv, fail, nb, npb, tb.prof ? tb.prof + 32 + _pc * 4 : nullptr);
+    mf_front_factor<NW>(tiles, mbuf, mbuf, nainv, fail, nb, npb, F.s, tb.prof ? tb.prof + 32 + _pc * 4 : nullptr);
     MF_PROF_MARK(4);
     if (tid == 0 && *fail) tb.status[sys] = kErrSingular;
-    // outputs, tile by tile: G = -(pivot x pivot), M = update x pivot (factor arena), U = update x update (update arena, lower tiles)
+    // outputs, tile by tile: G = -(pivot x pivot), M = -M' (factor arena), U = update x update (update arena, lower tiles)
     double* fac = tb.fac + (size_t)sys * tb.facStride;
-    const int sp = F.sp, up = F.up, nub = nb - npb;
-    auto tileP = [&](int I, int J) { return tiles + (size_t)(I * (I + 1) / 2 + J) * 128; };
+    const int sp = F.sp, up = F.up;
     {
         double* G = fac + ch.gOff;
         for (int q = warp; q < npb * npb; q += NW) {
             const int I = q / npb, J = q - I * npb;
-            if (I > J) mf_store_tile<0>(tileP(I, J), G, sp, I * 8, J * 8, -1.0, lane);
-            else if (I == J) mf_store_tile<2>(tileP(I, I), G, sp, I * 8, I * 8, -1.0, lane);
-            else mf_store_tile<1>(tileP(J, I), G, sp, I * 8, J * 8, -1.0, lane);
+            if (I >= J) mf_store_tile<false>(mf_tile(tiles, I, J), G, sp, I * 8, J * 8, -1.0, lane);
+            else mf_store_tile<true>(mf_tile(tiles, J, I), G, sp, I * 8, J * 8, -1.0, lane);
         }
     }
     if (up > 0) {
         double* M = fac + ch.mOff;
         for (int q = warp; q < nub * npb; q += NW) {
             const int I = q / npb, J = q - I * npb;
-            mf_store_tile<0>(tileP(npb + I, J), M, up, I * 8, J * 8, 1.0, lane);
+            mf_store_tile<false>(mbuf + (size_t)q * 128, M, up, I * 8, J * 8, -1.0, lane);
         }
         double* U = tb.arena[F.depth & 1] + (size_t)sys * tb.arenaStride[F.depth & 1] + F.frontOff;
         int I = 0, J = warp;
         while (J > I) { J -= I + 1; ++I; }
         for (int L = warp; L < nub * (nub + 1) / 2; L += NW) {
-            mf_store_tile<0>(tileP(npb + I, npb + J), U, up, I * 8, J * 8, 1.0, lane);
+            mf_store_tile<false>(mf_tile(tiles, npb + I, npb + J), U, up, I * 8, J * 8, 1.0, lane);
             J += NW;
             while (J > I) { J -= I + 1; ++I; }
         }
@@ -438,51 +456,33 @@ mf_inv_kernel(Tables tb, const int* __restrict__ list, int c) {
     extern __shared__ __align__(16) unsigned char mf_smem[];
     const Front F = tb.fronts[list[blockIdx.x]];
     const Chunk ch = tb.chunks[F.chunkPtr + c];
-    const int sys = blockIdx.y, tid = threadIdx.x;
+    const int sys = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int sc = ch.p1 - ch.p0, nb = sc >> 3, fp = F.sp + F.up;
     const int nT = nb * (nb + 1) / 2;
     double* tiles = reinterpret_cast<double*>(mf_smem);
-    double* raw = tiles + (size_t)nT * 128;
-    double* mm = raw + 16 * (size_t)sc;
-    double* nainv = mm + 16 * (size_t)sc;
+    double* scratch = tiles + (size_t)nT * 128;
+    double* nainv = scratch + (size_t)2 * nb * 128;
     int* fail = reinterpret_cast<int*>(nainv + 128);
     const double* A = tb.arena[F.depth & 1] + (size_t)sys * tb.arenaStride[F.depth & 1] + F.frontOff;
     if (tid == 0) *fail = 0;
-    // lower triangle of A[p0:p1][p0:p1] -> tiles (diagonal tiles mirrored)
-    for (int idx = tid; idx < (sc >> 2) * sc; idx += NT) {
-        const int jg = idx / sc, i = idx - jg * sc;
-        if ((i >> 3) < (jg >> 1)) continue;                      // tile strictly above the diagonal
-        const double* pr = A + kg_off(fp, ch.p0 + i, ch.p0 + 4 * jg, 0);
-        const double* pi = A + kg_off(fp, ch.p0 + i, ch.p0 + 4 * jg, 1);
-        const double2 r01 = *reinterpret_cast<const double2*>(pr), r23 = *reinterpret_cast<const double2*>(pr + 2);
-        const double2 i01 = *reinterpret_cast<const double2*>(pi), i23 = *reinterpret_cast<const double2*>(pi + 2);
-        const int I = i >> 3, J = jg >> 1;
-        double* T = tiles + (size_t)(I * (I + 1) / 2 + J) * 128 + (i & 7) * 8 + (jg & 1) * 4;
-        *reinterpret_cast<double2*>(T) = r01; *reinterpret_cast<double2*>(T + 2) = r23;
-        *reinterpret_cast<double2*>(T + 64) = i01; *reinterpret_cast<double2*>(T + 66) = i23;
+    // lower tiles of A[p0:p1][p0:p1]: a (plane, column group) chunk of a tile is 32 consecutive doubles on both sides
+    for (int idx = tid; idx < nT * 64; idx += NT) {
+        const int L = idx >> 6, w = idx & 63, chunk = w >> 4, pl = chunk >> 1, cg = chunk & 1, r = (w & 15) >> 1, c2 = (w & 1) * 2;
+        int I = 0, J = L;
+        while (J > I) { J -= I + 1; ++I; }
+        const double* src = A + kg_off(fp, ch.p0 + I * 8 + r, ch.p0 + J * 8 + cg * 4, pl) + c2;
+        *reinterpret_cast<double2*>(tiles + (size_t)L * 128 + chunk * 32 + (w & 15) * 2) = *reinterpret_cast<const double2*>(src);
     }
     __syncthreads();
-    for (int idx = tid; idx < nb * 64; idx += NT) {
-        const int I = idx >> 6, r = (idx >> 3) & 7, cc = idx & 7;
-        if (cc > r) {
-            double* T = tiles + (size_t)(I * (I + 1) / 2 + I) * 128;
-            T[r * 8 + cc] = T[cc * 8 + r];
-            T[64 + r * 8 + cc] = T[64 + cc * 8 + r];
-        }
-    }
-    __syncthreads();
-    mf_sweep<kInvWarps>(tiles, raw, mm, nainv, fail, nb, nb);
+    // pivots of the chunk that are real unknowns (the identity padding sits at the end of the front's pivot range)
+    const int sReal = F.s - ch.p0 < sc ? (F.s - ch.p0 < 0 ? 0 : F.s - ch.p0) : sc;
+    mf_front_factor<kInvWarps>(tiles, scratch, scratch, nainv, fail, nb, nb, sReal);
     if (tid == 0 && *fail) tb.status[sys] = kErrSingular;
     double* G = tb.fac + (size_t)sys * tb.facStride + ch.gOff;
-    for (int idx = tid; idx < (sc >> 2) * sc; idx += NT) {
-        const int jg = idx / sc, i = idx - jg * sc;
-        double re[4], im[4];
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) { const cplx v = mf_tile_get(tiles, i, 4 * jg + jj); re[jj] = -v.x; im[jj] = -v.y; }
-        double* pr = G + kg_off(sc, i, 4 * jg, 0);
-        double* pi = G + kg_off(sc, i, 4 * jg, 1);
-        *reinterpret_cast<double2*>(pr) = make_double2(re[0], re[1]); *reinterpret_cast<double2*>(pr + 2) = make_double2(re[2], re[3]);
-        *reinterpret_cast<double2*>(pi) = make_double2(im[0], im[1]); *reinterpret_cast<double2*>(pi + 2) = make_double2(im[2], im[3]);
+    for (int q = warp; q < nb * nb; q += kInvWarps) {
+        const int I = q / nb, J = q - I * nb;
+        if (I >= J) mf_store_tile<false>(mf_tile(tiles, I, J), G, sc, I * 8, J * 8, -1.0, lane);
+        else mf_store_tile<true>(mf_tile(tiles, J, I), G, sc, I * 8, J * 8, -1.0, lane);
     }
 }
 

@@ -115,8 +115,11 @@ int Solver::build(int nsys_, int maxRhs_, int64_t valCount_) {
             MF_TRY(upload(sm, &p));
             D.smallList = p;
             int mx = 0;
-            for (int k : sm) mx = std::max(mx, S.fronts[k].fp());
-            D.smallSmem = mf_sweep_smem_bytes(mx / 8);
+            D.smallSmem = 0;
+            for (int k : sm) {
+                mx = std::max(mx, S.fronts[k].fp());
+                D.smallSmem = std::max(D.smallSmem, mf_front_smem_bytes(S.fronts[k].fp() / 8, S.fronts[k].sp / 8));
+            }
             const char* tw = std::getenv("HMCMT_MF_TINYWARPS");
             D.smallWarps = mx <= 48 ? (tw ? std::atoi(tw) : kTinyWarps) : (mx <= 64 ? 4 : (mx <= 104 ? 8 : 16));
         }
@@ -191,7 +194,7 @@ int Solver::build(int nsys_, int maxRhs_, int64_t valCount_) {
             }
             MF_TRY(upload(inv, &p));
             cs.invList = p; cs.nInv = (int)inv.size();
-            cs.invSmem = mf_sweep_smem_bytes(maxSc / 8);
+            cs.invSmem = mf_front_smem_bytes(maxSc / 8, maxSc / 8);
             GemmJob* pj = nullptr;
             GemmTile* ptile = nullptr;
             MF_TRY(upload(jobs, &pj));
@@ -204,24 +207,30 @@ int Solver::build(int nsys_, int maxRhs_, int64_t valCount_) {
         }
     }
     solveSmem = (size_t)(2 * S.maxFp + 16) * sizeof(cplx);
-    if (solveSmem > kMaxSmem || mf_sweep_smem_bytes(std::max(S.maxFpSmall, 8) / 8) > kMaxSmem) return kErrArg;
+    if (solveSmem > kMaxSmem) return kErrArg;
 #undef MF_TRY
     return kOk;
 }
 
-int Solver::set_mt_values(cudaStream_t st, int N, const MtValSys* dSys) {
+int Solver::set_mt_values(cudaStream_t st, int N, const MtValSys* dSys, int sys0, int n) {
     if (valCount < 3 * (int64_t)N) return kErrArg;
-    mf_mt_vals_kernel<<<dim3((3 * N + 255) / 256, nsys), 256, 0, st>>>(N, dSys, d_vals, valCount);
+    if (n < 0) n = nsys - sys0;
+    if (sys0 < 0 || n < 1 || sys0 + n > nsys) return kErrArg;
+    mf_mt_vals_kernel<<<dim3((3 * N + 255) / 256, n), 256, 0, st>>>(N, dSys + sys0, d_vals + (size_t)sys0 * valCount, valCount);
     HMCMT_CUDA_TRY(cudaGetLastError());
     return kOk;
 }
 
-int Solver::factor(cudaStream_t st, int* dStatus, int64_t* nLaunches) {
+int Solver::factor(cudaStream_t st, int* dStatus, int64_t* nLaunches, int sys0, int n) {
+    if (n < 0) n = this->nsys - sys0;
+    if (sys0 < 0 || n < 1 || sys0 + n > this->nsys) return kErrArg;
+    const int nsys = n;      // systems of this call: the kernels index them 0..n-1 from the offset bases below
     Tables tb{};
     tb.fronts = d_fronts; tb.rows = d_rows; tb.rel = d_rel; tb.children = d_children; tb.orig = d_orig; tb.chunks = d_chunks;
-    tb.pos2orig = d_pos2orig; tb.fac = d_fac; tb.arena[0] = d_arena[0]; tb.arena[1] = d_arena[1];
+    tb.pos2orig = d_pos2orig; tb.fac = d_fac + (size_t)sys0 * S.factorDoubles;
+    tb.arena[0] = d_arena[0] + (size_t)sys0 * S.arenaDoubles[0]; tb.arena[1] = d_arena[1] + (size_t)sys0 * S.arenaDoubles[1];
     tb.facStride = S.factorDoubles; tb.arenaStride[0] = S.arenaDoubles[0]; tb.arenaStride[1] = S.arenaDoubles[1];
-    tb.vals = d_vals; tb.valStride = valCount; tb.status = dStatus; tb.prof = d_prof;
+    tb.vals = d_vals + (size_t)sys0 * valCount; tb.valStride = valCount; tb.status = dStatus ? dStatus + sys0 : nullptr; tb.prof = d_prof;
     static PerDeviceOnceMf once;
     if (once.need()) {
         HMCMT_CUDA_TRY(cudaFuncSetAttribute(mf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
@@ -241,7 +250,7 @@ int Solver::factor(cudaStream_t st, int* dStatus, int64_t* nLaunches) {
             ++nl;
         }
         if (!D.nBig) continue;
-        HMCMT_CUDA_TRY(cudaMemset2DAsync(d_arena[par], (size_t)S.arenaDoubles[par] * sizeof(double), 0, D.bigBytes, nsys, st));
+        HMCMT_CUDA_TRY(cudaMemset2DAsync(tb.arena[par], (size_t)S.arenaDoubles[par] * sizeof(double), 0, D.bigBytes, nsys, st));
         if (D.nOrigPairs) {
             mf_asm_orig_kernel<<<dim3((D.nOrigPairs + 255) / 256, nsys), 256, 0, st>>>(tb, D.origPairs, D.nOrigPairs);
             ++nl;
@@ -274,14 +283,21 @@ int Solver::factor(cudaStream_t st, int* dStatus, int64_t* nLaunches) {
     return kOk;
 }
 
-int Solver::solve(cudaStream_t st, int nrhs, const cplx* B, int64_t ldb, cplx* X, int64_t ldx, int64_t* nLaunches) {
+int Solver::solve(cudaStream_t st, int nrhs, const cplx* B, int64_t ldb, cplx* X, int64_t ldx, int64_t* nLaunches, int sys0, int n) {
     if (nrhs < 1 || nrhs > maxRhs) return kErrArg;
+    if (n < 0) n = this->nsys - sys0;
+    if (sys0 < 0 || n < 1 || sys0 + n > this->nsys) return kErrArg;
+    const int nsys = n;
     Tables tb{};
     tb.fronts = d_fronts; tb.rows = d_rows; tb.rel = d_rel; tb.children = d_children; tb.orig = d_orig; tb.chunks = d_chunks;
-    tb.pos2orig = d_pos2orig; tb.fac = d_fac; tb.arena[0] = d_arena[0]; tb.arena[1] = d_arena[1];
+    tb.pos2orig = d_pos2orig; tb.fac = d_fac + (size_t)sys0 * S.factorDoubles;
+    tb.arena[0] = d_arena[0] + (size_t)sys0 * S.arenaDoubles[0]; tb.arena[1] = d_arena[1] + (size_t)sys0 * S.arenaDoubles[1];
     tb.facStride = S.factorDoubles; tb.arenaStride[0] = S.arenaDoubles[0]; tb.arenaStride[1] = S.arenaDoubles[1];
     tb.vals = d_vals; tb.valStride = valCount; tb.status = nullptr; tb.prof = nullptr;
-    SolveArgs sa{B, X, ldb, ldx, d_v, d_upd, (int64_t)S.Np, S.updEntries, nrhs};
+    const size_t vec0 = (size_t)sys0 * nrhs;
+    // the workspaces are laid out for maxRhs vectors per system
+    SolveArgs sa{B + vec0 * ldb, X + vec0 * ldx, ldb, ldx, d_v + (size_t)sys0 * maxRhs * S.Np, d_upd + (size_t)sys0 * maxRhs * S.updEntries,
+                 (int64_t)S.Np, S.updEntries, nrhs};
     static PerDeviceOnceMf once;
     if (once.need()) {
         HMCMT_CUDA_TRY(cudaFuncSetAttribute(mf_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));

@@ -55,11 +55,15 @@ class Solver {
     int64_t val_stride() const { return valCount; }
     const Symbolic& symbolic() const { return S; }
     // fills vals() of every system from its stencil planes (pattern of mf_grid_entries: [diag N | e1 N | e2 N])
-    int set_mt_values(cudaStream_t st, int N, const MtValSys* dSys);
-    // numeric factorisation of all systems from vals(); status: device array [nsys] (set to -10 on a singular pivot block)
-    int factor(cudaStream_t st, int* dStatus, int64_t* nLaunches = nullptr);
+    // Every call below covers the systems [sys0, sys0 + n) (n < 0: all from sys0); disjoint ranges may be in flight on different
+    // streams at the same time (the per-system arenas, factors and workspaces do not overlap).
+    int set_mt_values(cudaStream_t st, int N, const MtValSys* dSys, int sys0 = 0, int n = -1);
+    // numeric factorisation from vals(); status: device array [nsys] (set to -10 on a singular pivot block)
+    int factor(cudaStream_t st, int* dStatus, int64_t* nLaunches = nullptr, int sys0 = 0, int n = -1);
     // nrhs right-hand sides per system: vector (sys, r) at B + (sys*nrhs + r)*ldb, original numbering; X may alias B
-    int solve(cudaStream_t st, int nrhs, const cplx* B, int64_t ldb, cplx* X, int64_t ldx, int64_t* nLaunches = nullptr);
+    // (B and X are the bases of the whole batch; the range is applied inside)
+    int solve(cudaStream_t st, int nrhs, const cplx* B, int64_t ldb, cplx* X, int64_t ldx, int64_t* nLaunches = nullptr, int sys0 = 0,
+              int n = -1);
     size_t device_bytes() const { return bytes; }
     double factor_flops() const { return S.flops; }
     int64_t factor_doubles() const { return S.factorDoubles; }

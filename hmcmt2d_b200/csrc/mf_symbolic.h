@@ -28,6 +28,14 @@ constexpr int kChunkMax = 96;      // pivots eliminated per step on a large fron
 
 inline int pad8(int x) { return (x + 7) & ~7; }
 
+// shared memory of the single-CTA front kernel (mf_kernels.cuh) for a front of nb tile rows of which npb are pivots:
+// lower tiles + max(sweep scratch, M' buffer) + the pivot block inverse + flag
+inline size_t mf_front_smem_bytes(int nb, int npb) {
+    const size_t nT = (size_t)nb * (nb + 1) / 2, nS = 2 * (size_t)npb, nM = (size_t)(nb - npb) * npb;
+    return (nT + (nS > nM ? nS : nM) + 1) * 128 * sizeof(double) + 16;
+}
+constexpr size_t kFrontSmemMax = 227 * 1024;
+
 // lower-triangular entry of the original matrix (row >= col, original numbering) and where its value comes from
 struct Entry {
     int row, col, src;      // src: index into the per-system value array handed to the numeric phase
@@ -82,7 +90,11 @@ struct Symbolic {
 // orderings: each returns the supernodes (lists of original indices) in elimination order
 
 // nl lines of nf unknowns, q = l*nf + f, 5-point coupling (q, q-1) inside a line and (q, q-nf) between lines
-inline void mf_order_grid(int nl, int nf, int leaf, std::vector<std::vector<int>>& out) {
+//   leaf  : boxes of at most `leaf` unknowns are eliminated as one dense supernode
+//   cross : boxes whose longer side is at most `cross` are cut four ways by a cross-shaped separator (one supernode = the
+//           middle line + the two halves of the middle column): half as many tree levels and no 3..6-unknown separators padded
+//           to a whole 8-pivot tile at the bottom of the tree, where the fronts are bound by latency and not by flops
+inline void mf_order_grid(int nl, int nf, int leaf, std::vector<std::vector<int>>& out, int cross = 0) {
     std::function<void(int, int, int, int)> rec = [&](int l0, int l1, int f0, int f1) {
         const int nL = l1 - l0, nF = f1 - f0;
         if (nL <= 0 || nF <= 0) return;
@@ -95,7 +107,16 @@ inline void mf_order_grid(int nl, int nf, int leaf, std::vector<std::vector<int>
             return;
         }
         std::vector<int> sep;
-        if (nL >= nF) {
+        if (std::max(nL, nF) <= cross && std::min(nL, nF) >= 3) {
+            const int ml = (l0 + l1) / 2, mf = (f0 + f1) / 2;
+            rec(l0, ml, f0, mf);
+            rec(l0, ml, mf + 1, f1);
+            rec(ml + 1, l1, f0, mf);
+            rec(ml + 1, l1, mf + 1, f1);
+            for (int f = f0; f < f1; ++f) sep.push_back(ml * nf + f);
+            for (int l = l0; l < l1; ++l)
+                if (l != ml) sep.push_back(l * nf + mf);
+        } else if (nL >= nF) {
             const int mid = (l0 + l1) / 2;
             rec(l0, mid, f0, f1);
             rec(mid + 1, l1, f0, f1);
@@ -370,7 +391,7 @@ inline bool mf_symbolic(int N, const std::vector<std::vector<int>>& snodes, cons
     for (int k = 0; k < K; ++k) {
         Front& F = S.fronts[k];
         const int fp = F.fp();
-        F.isBig = fp > fSmall ? 1 : 0;
+        F.isBig = (fp > fSmall || mf_front_smem_bytes(fp / 8, F.sp / 8) > kFrontSmemMax) ? 1 : 0;
         S.maxFp = std::max(S.maxFp, fp);
         (F.isBig ? S.maxFpBig : S.maxFpSmall) = std::max(F.isBig ? S.maxFpBig : S.maxFpSmall, fp);
         (F.isBig ? S.byDepthBig : S.byDepthSmall)[F.depth].push_back(k);

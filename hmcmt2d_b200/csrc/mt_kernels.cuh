@@ -251,10 +251,11 @@ __global__ void k_rhs(MeshDev M, SysMap sm, const double* __restrict__ sigma, co
 
 // full node-ordered field from the interior solution + boundary values (mt2DTE.jl:57-62).
 // grid: (ceil(nNode/256), nSys).  If bc == nullptr the boundary is zero (adjoint field).
-__global__ void k_node_field(MeshDev M, const cplx* __restrict__ x, const cplx* __restrict__ bc, cplx* __restrict__ F) {
+// (sys0: first system of the group this launch covers; the groups of a step run on different streams, hmcmt_b200.cu)
+__global__ void k_node_field(MeshDev M, const cplx* __restrict__ x, const cplx* __restrict__ bc, cplx* __restrict__ F, int sys0) {
     int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= M.nNode) return;
-    const int sys = blockIdx.y, ny = M.ny, nz = M.nz;
+    const int sys = blockIdx.y + sys0, ny = M.ny, nz = M.nz;
     int kn = n / (ny + 1), jn = n - kn * (ny + 1);
     cplx v = mk(0.0, 0.0);
     if (jn >= 1 && jn <= ny - 1 && kn >= 1 && kn <= nz - 1) {
@@ -292,7 +293,7 @@ k_rx_adjoint(MeshDev M, RxDev rx, SysMap sm, const double* __restrict__ freqs, c
              const cplx* __restrict__ F, const cplx* __restrict__ obs, const double* __restrict__ wd,
              const cplx* __restrict__ vin, cplx* __restrict__ pred, double* __restrict__ phiPart,
              cplx* __restrict__ srows, cplx* __restrict__ qrow, cplx* __restrict__ adjrhs, int wantAdjoint, int respKind,
-             cplx* __restrict__ resp) {
+             cplx* __restrict__ resp, int sys0) {
     extern __shared__ __align__(16) unsigned char smraw[];
     const int ny = M.ny;
     cplx* F0 = reinterpret_cast<cplx*>(smraw);        // ny+1
@@ -304,7 +305,7 @@ k_rx_adjoint(MeshDev M, RxDev rx, SysMap sm, const double* __restrict__ freqs, c
     cplx* Qc = aG0 + (ny + 1);                         // HzQ / EzQ  (ny)
     cplx* aQc = Qc + ny;                               // adjoint of HzQ / EzQ (ny)
     cplx* qv = aQc + ny;                               // q on the receiver cell row (ny)
-    const int sys = blockIdx.x;
+    const int sys = blockIdx.x + sys0;
     int ch, mi, mode, f;
     sys_decode(sm, sys, ch, mi, mode, f);
     const int nFreq = sm.nFreq;
@@ -733,15 +734,15 @@ __host__ __device__ inline size_t contract_cols_smem(int ny, int nz, int staged)
 __global__ void __launch_bounds__(kConThreads)
 k_contract_cols(MeshDev M, SysMap sm, const double* __restrict__ freqs, const double* __restrict__ sigma,
                 const cplx* __restrict__ Lam, const cplx* __restrict__ srows, cplx* __restrict__ scratch,
-                cplx* __restrict__ cols, int staged) {
+                cplx* __restrict__ cols, int staged, int sys0) {
     extern __shared__ __align__(16) unsigned char smraw[];
     const int ny = M.ny, nz = M.nz;
     cplx* tL = reinterpret_cast<cplx*>(smraw);   // nz   (node rows 1..nz)
     cplx* tR = tL + nz;                            // nz
     cplx* tB = tR + nz;                            // ny-1 (nodes jn = 1..ny-1)
     cplx* prof = staged ? tB + (ny - 1)            // 3 * prof_stride(nz): the three profiles' scalars, staged
-                        : scratch + (size_t)blockIdx.x * 3 * prof_stride(nz);       // (too deep a mesh: read them in place)
-    const int sys = blockIdx.x;
+                        : scratch + (size_t)(blockIdx.x + sys0) * 3 * prof_stride(nz);       // (too deep a mesh: read them in place)
+    const int sys = blockIdx.x + sys0;
     int ch, mi, mode, f;
     sys_decode(sm, sys, ch, mi, mode, f);
     const int tid = threadIdx.x;
@@ -803,9 +804,9 @@ k_contract_cols(MeshDev M, SysMap sm, const double* __restrict__ freqs, const do
 __global__ void __launch_bounds__(256)
 k_contract_cells(MeshDev M, SysMap sm, const double* __restrict__ freqs, const double* __restrict__ sigma,
                  const cplx* __restrict__ F, const cplx* __restrict__ Lam, const cplx* __restrict__ qrow,
-                 const cplx* __restrict__ bcs, const cplx* __restrict__ cols, double* __restrict__ Gpart) {
+                 const cplx* __restrict__ bcs, const cplx* __restrict__ cols, double* __restrict__ Gpart, int sys0) {
     const int ny = M.ny, nz = M.nz;
-    const int sys = blockIdx.y;
+    const int sys = blockIdx.y + sys0;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= M.nCell) return;
     int ch, mi, mode, f;

@@ -198,7 +198,10 @@ int hmcmt_get_responses(hmcmt_plan* plan, double* out);
 /* CUDA-event bracket on the plan's stream: start / stop (returns elapsed ms through *ms) */
 int hmcmt_timer_start(hmcmt_plan* plan);
 int hmcmt_timer_stop(hmcmt_plan* plan, float* ms);
-/* accumulated CUDA-event time of the dominant kernel (band_factor) since the last reset, and launch count */
+/* accumulated CUDA-event time of the factorisation + forward solve since the last reset, and how many were timed.
+ * reset = 1: clear and switch the timing on — evaluations then run un-grouped on the plan's stream so that the events bracket
+ * the factorisation alone; reset = -1: clear and switch it off again (the default: groups of systems on their own streams
+ * overlap each other, HMCMT_GROUPS); reset = 0: read only. */
 int hmcmt_kernel_time(hmcmt_plan* plan, int reset, float* factor_ms, int64_t* factor_launches);
 
 /* runHMCSampler(mtMesh,mtData,invParam,hmcprior)  HMCSampler.jl:72-196 for all chains of the plan with injected

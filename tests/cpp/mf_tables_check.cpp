@@ -41,7 +41,8 @@ int main(int argc, char** argv) {
         fSmall = atoi(argv[5]);
         N = nl * nf;
         mf_grid_entries(nl, nf, ent);
-        mf_order_grid(nl, nf, leaf, sn);
+        const int cross = argc > 6 ? atoi(argv[6]) : 0;      // four-way cross separators for boxes up to this size
+        mf_order_grid(nl, nf, leaf, sn, cross);
     } else {
         int nx = atoi(argv[2]), ny = atoi(argv[3]), nz = atoi(argv[4]), leaf = atoi(argv[5]);
         fSmall = atoi(argv[6]);
@@ -76,6 +77,20 @@ int main(int argc, char** argv) {
     for (auto& F : S.fronts) nbig += F.isBig;
     printf("N %d Np %d K %d depth %d maxFp %d big %d factor MB %.1f arena MB %.1f/%.1f flops %.3e\n", S.N, S.Np, S.K, S.maxDepth, S.maxFp, nbig,
            S.factorDoubles * 8 / 1e6, S.arenaDoubles[0] * 8 / 1e6, S.arenaDoubles[1] * 8 / 1e6, S.flops);
+    if (getenv("MF_STATS")) {
+        // per depth: fronts handled by the single-CTA kernel / the large-front path, pivot blocks, largest front, modelled flops
+        for (int d = S.maxDepth; d >= 0; --d) {
+            int ns = 0, nb = 0, pb = 0, mx = 0;
+            double fl = 0.0;
+            for (auto& F : S.fronts) if (F.depth == d) {
+                (F.isBig ? nb : ns)++; pb += F.sp / 8; mx = std::max(mx, F.fp());
+                const double a = F.sp, b = F.up;
+                fl += 8.0 * (0.5 * a * a * a + a * a * b + 0.5 * a * b * b);
+            }
+            printf("  depth %2d: small %5d big %3d pivot blocks %5d max fp %3d flops %.2e\n", d, ns, nb, pb, mx, fl);
+        }
+        if (getenv("MF_STATS")[0] == '2') return 0;
+    }
     // checks of the schedule invariants
     for (int k = 0; k < S.K; ++k) {
         const Front& F = S.fronts[k];

@@ -174,6 +174,21 @@ def stage_sweep():
     os.environ.pop("HMCMT_MF_LEAF", None)
 
 
+def stage_xsweep():
+    """ordering knobs at cfg2: leaf size x cross-separator size (HMCMT_MF_LEAF, HMCMT_MF_CROSS)"""
+    combos = [tuple(int(v) for v in c.split(",")) for c in os.environ.get("XSWEEP", "16,0 16,8 16,13 25,13 36,13 36,0 16,26 36,26 49,13 49,26").split()]
+    for leaf, cross in combos:
+        os.environ["HMCMT_MF_LEAF"], os.environ["HMCMT_MF_CROSS"] = str(leaf), str(cross)
+        try:
+            _, _, i2 = plan_eval(200, 100, 30, "mf", nrx=40, reps=5)
+            print(f"[xsweep] leaf {leaf} cross {cross}: cfg2-mf {i2['eval_s'] * 1e3:.2f} ms (factor {i2['factor_MB']:.1f} MB, {i2['flops']:.3e} flop, "
+                  f"{i2['launches']} launches)", flush=True)
+        except Exception:
+            traceback.print_exc()
+    os.environ.pop("HMCMT_MF_LEAF", None)
+    os.environ.pop("HMCMT_MF_CROSS", None)
+
+
 def stage_fsweep():
     for fs in (48, 64, 80, 96, 112, 128, 144):
         os.environ["HMCMT_MF_FSMALL"] = str(fs)
