@@ -77,6 +77,7 @@ struct hmcmt_plan {
     // wide meshes (half-bandwidth > 104): nested-dissection multifrontal solver (mf_solver.cuh) instead of the band kernels
     mf::Solver* mfs = nullptr;
     DevBuf<mf::MtValSys> mfSys;
+    int patRhs = 0, patAdj = 0;                     // sparsity patterns of the forward / adjoint right-hand sides (Solver::add_rhs_pattern)
     // non-diagonal mass matrix M = Wm (setMassMatrix(invParam) HMCSampler.jl:478-489): invM p through a multifrontal
     // factorisation of Wm, sqrtM z through the banded Cholesky factor of Wm (natural ordering, as the reference's dense one)
     bool massOn = false;
@@ -426,7 +427,7 @@ int forward_solve(hmcmt_plan* pl, const SysRange& r) {
         ++pl->launches;
         rc = pl->mfs->factor(r.st, pl->status.p, &pl->launches, r.s0, r.n);
         if (rc) return rc;
-        rc = pl->mfs->solve(r.st, 1, pl->rhs.p, M.N, pl->x.p, M.N, &pl->launches, r.s0, r.n);
+        rc = pl->mfs->solve(r.st, 1, pl->rhs.p, M.N, pl->x.p, M.N, &pl->launches, r.s0, r.n, pl->patRhs);
     } else {
         if (r.s0 != 0 || r.n != pl->nSys) return kErrArg;
         int nl = 0;
@@ -497,7 +498,7 @@ int adjoint_range(hmcmt_plan* pl, const SysRange& r) {
     const MeshDev& M = pl->M;
     cudaStream_t st = r.st;
     int rc;                                                            // lam <- A^{-1} s[ii]  (in place)
-    if (pl->useMf) rc = pl->mfs->solve(st, 1, pl->lam.p, M.N, pl->lam.p, M.N, &pl->launches, r.s0, r.n);
+    if (pl->useMf) rc = pl->mfs->solve(st, 1, pl->lam.p, M.N, pl->lam.p, M.N, &pl->launches, r.s0, r.n, pl->patAdj);
     else {
         if (r.s0 != 0 || r.n != pl->nSys) return kErrArg;
         rc = launch_solve(st, pl->T, pl->jobs.p, pl->nSys, pl->dom);
@@ -902,6 +903,20 @@ int hmcmt_plan_create(const hmcmt_problem* pr, hmcmt_plan** out) {
         int mrc = kOk;
         pl->mfs = mf::Solver::create(std::move(S), pl->nSys, 1, 3 * (int64_t)M.N, &mrc);
         if (!pl->mfs) { hmcmt_destroy(pl); return mrc; }
+        if (const char* e = std::getenv("HMCMT_MF_PRUNE"); !e || std::atoi(e)) {
+            // rhs = -Aio bc (k_rhs) lives on the nodes next to the Dirichlet boundary, the adjoint sources (k_rx_adjoint) on the
+            // two receiver node rows zid, zid + 1: the forward eliminations skip every subtree without such a node
+            std::vector<unsigned char> nzR(M.N, 0), nzA(M.N, 0);
+            for (int kn = 1; kn <= nz - 1; ++kn)
+                for (int jn = 1; jn <= ny - 1; ++jn) {
+                    const int q = M.fastZ ? (jn - 1) * M.nf + (kn - 1) : (kn - 1) * M.nf + (jn - 1);
+                    if (jn == 1 || jn == ny - 1 || kn == 1 || kn == nz - 1) nzR[q] = 1;
+                    if (kn == M.zid || kn == M.zid + 1) nzA[q] = 1;
+                }
+            pl->patRhs = pl->mfs->add_rhs_pattern(nzR);
+            pl->patAdj = pl->mfs->add_rhs_pattern(nzA);
+            if (pl->patRhs < 0 || pl->patAdj < 0) { hmcmt_destroy(pl); return kErrAlloc; }
+        }
         std::vector<mf::MtValSys> mv(nSys);
         for (size_t s = 0; s < nSys; ++s) { mv[s].planes = sd[s].dr; mv[s].omega = sd[s].omega; }
         if (pl->mfSys.upload(mv.data(), nSys) != kOk) { hmcmt_destroy(pl); return kErrAlloc; }

@@ -214,14 +214,17 @@ __device__ __forceinline__ void mf_front_factor(double* __restrict__ tiles, doub
         const int nU = nub * (nub + 1) / 2;
         int I = 0, J = warp;
         while (J > I) { J -= I + 1; ++I; }
-        for (int L = warp; L < nU; L += 2 * NW) {
+        constexpr bool kPair = NW > 4;      // few warps: the fronts resident on the SM hide the DMMA latency, registers are scarce
+        for (int L = warp; L < nU; L += (kPair ? 2 : 1) * NW) {
             const int I0 = I, J0 = J;
             J += NW;
             while (J > I) { J -= I + 1; ++I; }
-            const bool two = L + NW < nU;
+            const bool two = kPair && L + NW < nU;
             const int I1 = I, J1 = J;
-            J += NW;
-            while (J > I) { J -= I + 1; ++I; }
+            if (kPair) {
+                J += NW;
+                while (J > I) { J -= I + 1; ++I; }
+            }
             double* T0 = mf_tile(tiles, npb + I0, npb + J0);
             double* T1 = mf_tile(tiles, npb + I1, npb + J1);
             TileFrag c0, x0, c1, x1;
@@ -268,8 +271,10 @@ __device__ __forceinline__ void mf_store_tile(const double* __restrict__ T, doub
 
 // ------------------------------------------------------------------------------------------------------------------------
 // small fronts: one CTA per (front, system).  list[blockIdx.x] = front id.
+// (register budget: the two- and four-warp instantiations serve the thousands of tiny fronts at the bottom of the tree, where the
+// number of fronts resident per SM hides the latency of the 8x8 inversions: 64 registers per thread -> 16 / 8 CTAs per SM)
 template <int NW>
-__global__ void __launch_bounds__(NW * 32)
+__global__ void __launch_bounds__(NW * 32, NW <= 4 ? 32 / NW : 1)
 mf_small_kernel(Tables tb, const int* __restrict__ list) {
     constexpr int NT = NW * 32;
     extern __shared__ __align__(16) unsigned char mf_smem[];
@@ -316,7 +321,7 @@ mf_small_kernel(Tables tb, const int* __restrict__ list) {
         // the loads of kBatch items (16-byte loads, 64 bytes per lane and item) before it scatters them, so that several
         // global-memory round trips are in flight.
         const int ng = (cu + 3) >> 2, nrb = (cu + 31) >> 5;
-        constexpr int kBatch = 4;
+        constexpr int kBatch = NW <= 4 ? 2 : 4;      // (the small instantiations live on 64 registers)
         for (int q0 = warp * kBatch; q0 < ng * nrb; q0 += NW * kBatch) {
             double2 r01[kBatch], r23[kBatch], i01[kBatch], i23[kBatch];
             int ii[kBatch], jgq[kBatch];

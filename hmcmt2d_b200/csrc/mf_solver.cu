@@ -283,8 +283,46 @@ int Solver::factor(cudaStream_t st, int* dStatus, int64_t* nLaunches, int sys0, 
     return kOk;
 }
 
-int Solver::solve(cudaStream_t st, int nrhs, const cplx* B, int64_t ldb, cplx* X, int64_t ldx, int64_t* nLaunches, int sys0, int n) {
-    if (nrhs < 1 || nrhs > maxRhs) return kErrArg;
+int Solver::add_rhs_pattern(const std::vector<unsigned char>& nz) {
+    if ((int)nz.size() != S.N) return kErrArg;
+    std::vector<char> active(S.K, 0);
+    for (int k = 0; k < S.K; ++k) {          // elimination order: children before parents
+        const Front& F = S.fronts[k];
+        for (int i = 0; i < F.s && !active[k]; ++i) {
+            const int o = S.pos2orig[F.cbp + i];
+            if (o >= 0 && nz[o]) active[k] = 1;
+        }
+        if (active[k] && F.parent >= 0) active[F.parent] = 1;
+    }
+    FwdLists L;
+    int rc;
+#define MF_TRY(x) do { rc = (x); if (rc) return rc; } while (0)
+    for (int d = 0; d <= S.maxDepth; ++d) {
+        std::vector<int> sw, sc;
+        for (int k : S.byDepthBig[d]) if (active[k]) sc.push_back(k);
+        for (int k : S.byDepthSmall[d]) if (active[k]) (S.fronts[k].fp() <= kSolveWarpMaxFp ? sw : sc).push_back(k);
+        int* p = nullptr;
+        if (!sw.empty()) MF_TRY(upload(sw, &p));
+        L.warpList.push_back(sw.empty() ? nullptr : p);
+        L.nWarp.push_back((int)sw.size());
+        p = nullptr;
+        if (!sc.empty()) MF_TRY(upload(sc, &p));
+        L.ctaList.push_back(sc.empty() ? nullptr : p);
+        L.nCta.push_back((int)sc.size());
+        L.nFronts += (int)(sw.size() + sc.size());
+    }
+#undef MF_TRY
+    patterns.push_back(std::move(L));
+    return (int)patterns.size();
+}
+
+int Solver::fwd_fronts(int pattern) const {
+    return pattern >= 1 && pattern <= (int)patterns.size() ? patterns[pattern - 1].nFronts : S.K;
+}
+
+int Solver::solve(cudaStream_t st, int nrhs, const cplx* B, int64_t ldb, cplx* X, int64_t ldx, int64_t* nLaunches, int sys0, int n,
+                  int pattern) {
+    if (nrhs < 1 || nrhs > maxRhs || pattern < 0 || pattern > (int)patterns.size()) return kErrArg;
     if (n < 0) n = this->nsys - sys0;
     if (sys0 < 0 || n < 1 || sys0 + n > this->nsys) return kErrArg;
     const int nsys = n;
@@ -305,15 +343,23 @@ int Solver::solve(cudaStream_t st, int nrhs, const cplx* B, int64_t ldb, cplx* X
     }
     const int nvec = nsys * nrhs;
     int64_t nl = 0;
+    const FwdLists* P = pattern ? &patterns[pattern - 1] : nullptr;
+    if (P) {
+        // fronts outside the pattern are not visited: their pivot parts and update vectors are zero
+        HMCMT_CUDA_TRY(cudaMemsetAsync(sa.v, 0, (size_t)nvec * S.Np * sizeof(cplx), st));
+        HMCMT_CUDA_TRY(cudaMemsetAsync(sa.upd, 0, (size_t)nvec * S.updEntries * sizeof(cplx), st));
+    }
     for (int d = S.maxDepth; d >= 0; --d) {
         const DepthSchedule& D = sched[d];
-        if (D.nSolveWarp) {
-            mf_fwd_warp_kernel<<<dim3((D.nSolveWarp + kSolveWarpsPerCta - 1) / kSolveWarpsPerCta, nvec), kSolveWarpsPerCta * 32, 0, st>>>(
-                tb, sa, D.solveWarpList, D.nSolveWarp);
+        const int nW = P ? P->nWarp[d] : D.nSolveWarp, nC = P ? P->nCta[d] : D.nSolveCta;
+        const int* wl = P ? P->warpList[d] : D.solveWarpList;
+        const int* cl = P ? P->ctaList[d] : D.solveCtaList;
+        if (nW) {
+            mf_fwd_warp_kernel<<<dim3((nW + kSolveWarpsPerCta - 1) / kSolveWarpsPerCta, nvec), kSolveWarpsPerCta * 32, 0, st>>>(tb, sa, wl, nW);
             ++nl;
         }
-        if (D.nSolveCta) {
-            mf_fwd_kernel<<<dim3(D.nSolveCta, nvec), kSolveMfThreads, solveSmem, st>>>(tb, sa, D.solveCtaList);
+        if (nC) {
+            mf_fwd_kernel<<<dim3(nC, nvec), kSolveMfThreads, solveSmem, st>>>(tb, sa, cl);
             ++nl;
         }
     }

@@ -62,8 +62,17 @@ class Solver {
     int factor(cudaStream_t st, int* dStatus, int64_t* nLaunches = nullptr, int sys0 = 0, int n = -1);
     // nrhs right-hand sides per system: vector (sys, r) at B + (sys*nrhs + r)*ldb, original numbering; X may alias B
     // (B and X are the bases of the whole batch; the range is applied inside)
+    // pattern: 0 = dense right-hand sides, > 0 = an id returned by add_rhs_pattern (the rows outside it MUST be zero)
     int solve(cudaStream_t st, int nrhs, const cplx* B, int64_t ldb, cplx* X, int64_t ldx, int64_t* nLaunches = nullptr, int sys0 = 0,
-              int n = -1);
+              int n = -1, int pattern = 0);
+    // Right-hand sides with a known sparsity pattern (nz[i] != 0: row i, original numbering, may be non-zero).  The forward
+    // elimination then visits only the fronts whose subtree holds such a row — every other front would hand a zero update
+    // vector to its parent — which prunes most of the tree when the sources sit on a few grid lines (MT right-hand sides:
+    // the nodes next to the Dirichlet boundary, the two receiver rows of the adjoint sources).  The backward substitution is
+    // always complete.  Returns the pattern id (> 0), or a negative error code.
+    int add_rhs_pattern(const std::vector<unsigned char>& nz);
+    // fronts visited by the forward elimination of a pattern (0: all), for diagnostics
+    int fwd_fronts(int pattern) const;
     size_t device_bytes() const { return bytes; }
     double factor_flops() const { return S.flops; }
     int64_t factor_doubles() const { return S.factorDoubles; }
@@ -79,6 +88,12 @@ class Solver {
     size_t bytes = 0;
     std::vector<void*> owned;
     std::vector<DepthSchedule> sched;
+    struct FwdLists {                            // forward-elimination launch lists of one right-hand-side pattern, per depth
+        std::vector<const int*> warpList, ctaList;
+        std::vector<int> nWarp, nCta;
+        int nFronts = 0;
+    };
+    std::vector<FwdLists> patterns;
     // device tables
     Front* d_fronts = nullptr;
     int *d_rows = nullptr, *d_rel = nullptr, *d_children = nullptr, *d_pos2orig = nullptr;
