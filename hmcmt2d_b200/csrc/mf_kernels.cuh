@@ -556,6 +556,17 @@ mf_gemm_kernel(Tables tb, const GemmJob* __restrict__ jobs, const GemmTile* __re
     for (int a = 0; a < 2; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) cre[a][b][0] = cre[a][b][1] = cim[a][b][0] = cim[a][b][1] = 0.0;
+    // 8x8 blocks of this warp that hold anything the epilogue stores: inside the m x n job and, for the lower-triangle jobs, not
+    // strictly above the diagonal.  Fronts are padded to multiples of 8, not 64: on the trailing tiles of a front and on its
+    // diagonal tiles up to half of the blocks are skipped, and with them their DMMAs (the warp still helps loading the stages).
+    unsigned act = 0;
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int rb = r0 + wr * 16 + a * 8, cb = c0 + wc * 32 + b * 8;
+            if (rb < jb.m && cb < jb.n && !(jb.lower && jb.cC + cb > jb.rC + rb)) act |= 1u << (a * 4 + b);
+        }
     for (int s = 0; s < kGemmStages - 1; ++s) {
         if (s < nk) load_stage(s, s); else cp_async_commit();
     }
@@ -563,10 +574,13 @@ mf_gemm_kernel(Tables tb, const GemmJob* __restrict__ jobs, const GemmTile* __re
         cp_async_wait<kGemmStages - 2>();
         __syncthreads();
         if (ks + kGemmStages - 1 < nk) load_stage(ks + kGemmStages - 1, (ks + kGemmStages - 1) % kGemmStages); else cp_async_commit();
+        if (!act) continue;
         const double* sA = sm + (size_t)(ks % kGemmStages) * kGemmStageDoubles;
         const double* sB = sA + (kGemmKC / 4) * 2 * 64 * 4;
+        const int ngrp = min(kGemmKC / 4, (jb.K - ks * kGemmKC + 3) >> 2);      // K is a multiple of 8, not of the stage depth
 #pragma unroll
         for (int grp = 0; grp < kGemmKC / 4; ++grp) {
+            if (grp >= ngrp) break;
             double are[2], aim[2], nai[2], bre[4], bim[4];
 #pragma unroll
             for (int a = 0; a < 2; ++a) {
@@ -583,15 +597,17 @@ mf_gemm_kernel(Tables tb, const GemmJob* __restrict__ jobs, const GemmTile* __re
             for (int a = 0; a < 2; ++a)
 #pragma unroll
                 for (int b = 0; b < 4; ++b) {
-                    dmma884(cre[a][b], are[a], bre[b]);
-                    dmma884(cim[a][b], are[a], bim[b]);
+                    const int on = (act >> (a * 4 + b)) & 1;
+                    dmma884_p(cre[a][b], are[a], bre[b], on);
+                    dmma884_p(cim[a][b], are[a], bim[b], on);
                 }
 #pragma unroll
             for (int a = 0; a < 2; ++a)
 #pragma unroll
                 for (int b = 0; b < 4; ++b) {
-                    dmma884(cre[a][b], nai[a], bim[b]);
-                    dmma884(cim[a][b], aim[a], bre[b]);
+                    const int on = (act >> (a * 4 + b)) & 1;
+                    dmma884_p(cre[a][b], nai[a], bim[b], on);
+                    dmma884_p(cim[a][b], aim[a], bre[b], on);
                 }
         }
     }
@@ -602,8 +618,7 @@ mf_gemm_kernel(Tables tb, const GemmJob* __restrict__ jobs, const GemmTile* __re
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             const int rb = r0 + wr * 16 + a * 8, cb = c0 + wc * 32 + b * 8;
-            if (rb >= jb.m || cb >= jb.n) continue;
-            if (jb.lower && jb.cC + cb > jb.rC + rb) continue;
+            if (!((act >> (a * 4 + b)) & 1)) continue;
             double* pr = C + kg_off(jb.ldC, jb.rC + rb + g, jb.cC + cb + 2 * t, 0);
             double* pi = C + kg_off(jb.ldC, jb.rC + rb + g, jb.cC + cb + 2 * t, 1);
             double2 vr = make_double2(jb.alpha * cre[a][b][0], jb.alpha * cre[a][b][1]);
