@@ -275,22 +275,86 @@ __device__ __forceinline__ void mf_store_tile(const double* __restrict__ T, doub
 // number of fronts resident per SM hides the latency of the 8x8 inversions: 64 registers per thread -> 16 / 8 CTAs per SM)
 template <int NW>
 __global__ void __launch_bounds__(NW * 32, NW <= 4 ? 32 / NW : 1)
-mf_small_kernel(Tables tb, const int* __restrict__ list) {
+mf_small_kernel(Tables tb, const SmallDesc* __restrict__ descs) {
     constexpr int NT = NW * 32;
     extern __shared__ __align__(16) unsigned char mf_smem[];
-    const Front F = tb.fronts[list[blockIdx.x]];
+    SmallDesc& F = *reinterpret_cast<SmallDesc*>(mf_smem);      // the first kFrontDescBytes of the dynamic block
     const int sys = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    constexpr int _pc = NW == 2 ? 0 : (NW == 4 ? 1 : (NW == 8 ? 2 : 3));      // profiler class
+    long long _t0 = clock64();
+    // the front's record: one coalesced read
+    static_assert(sizeof(SmallDesc) % 4 == 0 && sizeof(SmallDesc) / 4 <= 64 && sizeof(SmallDesc) <= kFrontDescBytes,
+                  "SmallDesc is copied by the first two warps into the head of the dynamic shared memory");
+    if (tid < (int)(sizeof(SmallDesc) / 4))
+        reinterpret_cast<int*>(&F)[tid] = reinterpret_cast<const int*>(descs + blockIdx.x)[tid];
+    __syncthreads();
     const int fp = F.sp + F.up, nb = fp >> 3, npb = F.sp >> 3, nub = nb - npb;
     const int nT = nb * (nb + 1) / 2;
-    double* tiles = reinterpret_cast<double*>(mf_smem);
+    double* tiles = reinterpret_cast<double*>(mf_smem + kFrontDescBytes);
     double* mbuf = tiles + (size_t)nT * 128;                                   // sweep scratch, then M'
     double* nainv = mbuf + (size_t)(2 * npb > nub * npb ? 2 * npb : nub * npb) * 128;
     int* fail = reinterpret_cast<int*>(nainv + 128);
-    constexpr int _pc = NW == 2 ? 0 : (NW == 4 ? 1 : (NW == 8 ? 2 : 3));      // profiler class
-    long long _t0 = clock64();
-    // loads that do not depend on anything else are issued first: their latency hides behind the zeroing and the extend-add
-    const Chunk ch = tb.chunks[F.chunkPtr];
+    // row maps of all children, back to back, already split into the two address parts of the tile layout: an entry (a, b),
+    // a >= b, of the front sits at tiles + rowPart(a) + colPart(b)
+    int2* relS = reinterpret_cast<int2*>(fail + 4);
+    auto rel_parts = [](int r) { return make_int2(((r >> 3) * ((r >> 3) + 1) / 2) * 128 + (r & 7) * 4, (r >> 3) * 128 + ((r & 4) << 3) + (r & 3)); };
+    // everything that depends on the record alone is requested now: the children's row maps, the first batches of the children's
+    // update matrices, the first original entry of every thread (and its value); the latency hides behind the zeroing
+    const int nChild = F.nChild;
+    {
+        int base = 0;
+        for (int c = 0; c < nChild; ++c) {
+            const int cu = F.cU[c];
+            const int* rel = tb.rel + F.cRel[c];
+            for (int i = tid; i < cu; i += NT) relS[base + i] = rel_parts(rel[i]);
+            base += cu;
+        }
+    }
+    // Extend-add of the children's update matrices.  Work items = (column group of four, block of 32 rows) of a child's lower
+    // triangle (16-byte loads, 64 bytes per lane and item), dealt round-robin to the warps in batches of kBatch.  Every warp
+    // walks ITS batches of all children in order with two batches in flight: the loads of batch k+2 are issued before batch k
+    // is scattered, across the child boundaries too, so that one global-memory round trip is exposed per front instead of one
+    // or two per child.  Children are scattered one after the other (a CTA barrier per child boundary: entries of one child
+    // never collide, plain adds, fixed order -> deterministic).
+    const double* carena = tb.arena[F.par ^ 1] + (size_t)sys * tb.arenaStride[F.par ^ 1];
+    constexpr int kBatch = NW <= 4 ? 1 : 2;      // (the small instantiations live on 64 registers)
+    struct Batch {
+        double2 r01[kBatch], r23[kBatch], i01[kBatch], i23[kBatch];
+        int ii[kBatch], jg[kBatch];
+        int c;                                    // child, -1: nothing left
+    };
+    int curC = 0, curQ = warp * kBatch;
+    auto load_batch = [&](Batch& bt) {
+        while (curC < nChild) {
+            const int cu = F.cU[curC];
+            if (curQ < ((cu + 3) >> 2) * ((cu + 31) >> 5)) break;
+            ++curC;
+            curQ = warp * kBatch;
+        }
+        bt.c = curC < nChild ? curC : -1;
+        if (bt.c < 0) return;
+        const int cu = F.cU[curC], ld = F.cLd[curC], off = F.cFirst[curC];
+        const double* U = carena + F.cOff[curC];
+        const int ng = (cu + 3) >> 2, nrb = (cu + 31) >> 5;
+#pragma unroll
+        for (int bq = 0; bq < kBatch; ++bq) {
+            const int q = curQ + bq;
+            const int jg = q / nrb, i = (q - jg * nrb) * 32 + lane;
+            bt.jg[bq] = jg;
+            bt.ii[bq] = (q < ng * nrb && i < cu && i >= 4 * jg) ? i : -1;
+            if (bt.ii[bq] >= 0) {
+                const double* pr = U + kg_off(ld, off + i, off + 4 * jg, 0);
+                const double* pi = U + kg_off(ld, off + i, off + 4 * jg, 1);
+                bt.r01[bq] = *reinterpret_cast<const double2*>(pr); bt.r23[bq] = *reinterpret_cast<const double2*>(pr + 2);
+                bt.i01[bq] = *reinterpret_cast<const double2*>(pi); bt.i23[bq] = *reinterpret_cast<const double2*>(pi + 2);
+            }
+        }
+        curQ += NW * kBatch;
+    };
+    Batch b0, b1;
+    load_batch(b0);
+    load_batch(b1);
     const cplx* vals = tb.vals + (size_t)sys * tb.valStride;
     OrigEntry oe0{0, 0, -1};
     cplx ov0 = mk(0.0, 0.0);
@@ -305,55 +369,40 @@ mf_small_kernel(Tables tb, const int* __restrict__ list) {
     auto addr = [&](int a, int b) {       // a >= b
         return tiles + (size_t)((a >> 3) * ((a >> 3) + 1) / 2 + (b >> 3)) * 128 + tl_off(a & 7, b & 7);
     };
-    // extend-add of the children's update matrices, one child at a time (entries of one child never collide: plain adds, fixed
-    // order -> deterministic).  The child's row map is staged in shared memory (the M' buffer is still unused).
-    const double* carena = tb.arena[(F.depth + 1) & 1] + (size_t)sys * tb.arenaStride[(F.depth + 1) & 1];
-    int* relS = reinterpret_cast<int*>(mbuf);
-    for (int c = 0; c < F.nChild; ++c) {
-        const Front& C = tb.fronts[tb.children[F.childPtr + c]];
-        const int cu = C.u, cup = C.up;
-        const int ld = C.isBig ? C.sp + cup : cup, off = C.isBig ? C.sp : 0;
-        const double* U = carena + C.frontOff;
-        const int* rel = tb.rel + C.rowPtr;
-        for (int i = tid; i < cu; i += NT) relS[i] = rel[i];
-        __syncthreads();
-        // work items = (column group of four, block of 32 rows) of the child's lower triangle, dealt round-robin; a warp issues
-        // the loads of kBatch items (16-byte loads, 64 bytes per lane and item) before it scatters them, so that several
-        // global-memory round trips are in flight.
-        const int ng = (cu + 3) >> 2, nrb = (cu + 31) >> 5;
-        constexpr int kBatch = NW <= 4 ? 2 : 4;      // (the small instantiations live on 64 registers)
-        for (int q0 = warp * kBatch; q0 < ng * nrb; q0 += NW * kBatch) {
-            double2 r01[kBatch], r23[kBatch], i01[kBatch], i23[kBatch];
-            int ii[kBatch], jgq[kBatch];
+    {
+        int passed = 0;                           // child boundaries (CTA barriers) this warp went through: nChild - 1 in the end
+        auto scatter = [&](const Batch& bt) {
+            while (passed < bt.c) { __syncthreads(); ++passed; }
+            const int2* relC = relS + ((bt.c > 0 ? F.cU[0] : 0) + (bt.c > 1 ? F.cU[1] : 0) + (bt.c > 2 ? F.cU[2] : 0));
 #pragma unroll
             for (int bq = 0; bq < kBatch; ++bq) {
-                const int q = q0 + bq;
-                const int jg = q / nrb, i = (q - jg * nrb) * 32 + lane;
-                jgq[bq] = jg;
-                ii[bq] = (q < ng * nrb && i < cu && i >= 4 * jg) ? i : -1;
-                if (ii[bq] >= 0) {
-                    const double* pr = U + kg_off(ld, off + i, off + 4 * jg, 0);
-                    const double* pi = U + kg_off(ld, off + i, off + 4 * jg, 1);
-                    r01[bq] = *reinterpret_cast<const double2*>(pr); r23[bq] = *reinterpret_cast<const double2*>(pr + 2);
-                    i01[bq] = *reinterpret_cast<const double2*>(pi); i23[bq] = *reinterpret_cast<const double2*>(pi + 2);
-                }
-            }
-#pragma unroll
-            for (int bq = 0; bq < kBatch; ++bq) {
-                const int i = ii[bq];
+                const int i = bt.ii[bq];
                 if (i < 0) continue;
-                const int jg = jgq[bq];
-                const double re[4] = {r01[bq].x, r01[bq].y, r23[bq].x, r23[bq].y}, im[4] = {i01[bq].x, i01[bq].y, i23[bq].x, i23[bq].y};
-                const int ri = relS[i];
+                const int jg = bt.jg[bq];
+                const double re[4] = {bt.r01[bq].x, bt.r01[bq].y, bt.r23[bq].x, bt.r23[bq].y};
+                const double im[4] = {bt.i01[bq].x, bt.i01[bq].y, bt.i23[bq].x, bt.i23[bq].y};
+                double* rowp = tiles + relC[i].x;
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
                     if (4 * jg + jj > i) break;
-                    double* d = addr(ri, relS[4 * jg + jj]);
+                    double* d = rowp + relC[4 * jg + jj].y;
                     d[0] += re[jj];
                     d[64] += im[jj];
                 }
             }
+        };
+        while (b0.c >= 0) {
+            scatter(b0);
+            load_batch(b0);
+            if (b1.c < 0) break;
+            scatter(b1);
+            load_batch(b1);
         }
+        // (b0 may still hold a batch when b1 ran dry first)
+        if (b0.c >= 0 && b1.c < 0) {
+            while (b0.c >= 0) { scatter(b0); load_batch(b0); }
+        }
+        while (passed < nChild - 1) { __syncthreads(); ++passed; }
         __syncthreads();
     }
     MF_PROF_MARK(2);
@@ -379,7 +428,7 @@ mf_small_kernel(Tables tb, const int* __restrict__ list) {
     double* fac = tb.fac + (size_t)sys * tb.facStride;
     const int sp = F.sp, up = F.up;
     {
-        double* G = fac + ch.gOff;
+        double* G = fac + F.gOff;
         for (int q = warp; q < npb * npb; q += NW) {
             const int I = q / npb, J = q - I * npb;
             if (I >= J) mf_store_tile<false>(mf_tile(tiles, I, J), G, sp, I * 8, J * 8, -1.0, lane);
@@ -387,12 +436,12 @@ mf_small_kernel(Tables tb, const int* __restrict__ list) {
         }
     }
     if (up > 0) {
-        double* M = fac + ch.mOff;
+        double* M = fac + F.mOff;
         for (int q = warp; q < nub * npb; q += NW) {
             const int I = q / npb, J = q - I * npb;
             mf_store_tile<false>(mbuf + (size_t)q * 128, M, up, I * 8, J * 8, -1.0, lane);
         }
-        double* U = tb.arena[F.depth & 1] + (size_t)sys * tb.arenaStride[F.depth & 1] + F.frontOff;
+        double* U = tb.arena[F.par] + (size_t)sys * tb.arenaStride[F.par] + F.uOff;
         int I = 0, J = warp;
         while (J > I) { J -= I + 1; ++I; }
         for (int L = warp; L < nub * (nub + 1) / 2; L += NW) {
@@ -805,9 +854,10 @@ mf_fwd_warp_kernel(Tables tb, SolveArgs sa, const int* __restrict__ list, int n)
     }
     if (up > 0) {
         const double* M = tb.fac + (size_t)sys * tb.facStride + tb.chunks[F.chunkPtr].mOff;
-        for (int i = lane; i < up; i += 32) {
+        const int fu = F.u, ngr = (fs + 3) >> 2;      // real update rows / column groups holding a real pivot (the rest is padding)
+        for (int i = lane; i < fu; i += 32) {
             cplx acc = mk(0.0, 0.0);
-            for (int kg = 0; kg < (sp >> 2); ++kg) {
+            for (int kg = 0; kg < ngr; ++kg) {
                 const double* pr = M + kg_off(up, i, 4 * kg, 0);
                 const double* pi = M + kg_off(up, i, 4 * kg, 1);
                 const double2 r01 = *reinterpret_cast<const double2*>(pr), r23 = *reinterpret_cast<const double2*>(pr + 2);
@@ -848,26 +898,27 @@ mf_bwd_warp_kernel(Tables tb, SolveArgs sa, const int* __restrict__ list, int n)
     const double* G = tb.fac + (size_t)sys * tb.facStride + ch.gOff;
     const double* M = tb.fac + (size_t)sys * tb.facStride + ch.mOff;
     // x1[k] = sum_j G[j][k] w1[j] - sum_i M[i][k] x2[i] : one lane per k (four lanes share a 32-byte sector); when the front has
-    // fewer than 32 pivots the rows are split over 32 / width sub-groups of lanes and combined with shuffles
-    const int width = sp <= 8 ? 8 : (sp <= 16 ? 16 : 32), nparts = 32 / width, part = lane / width, kl = lane - part * width;
-    for (int k0 = 0; k0 < sp; k0 += width) {
+    // fewer than 32 pivots the rows are split over 32 / width sub-groups of lanes and combined with shuffles.  Only the real
+    // pivots / update rows are visited: the identity padding (up to 7 of 16 pivots on a leaf) is never read back by anybody.
+    const int width = fs <= 8 ? 8 : (fs <= 16 ? 16 : 32), nparts = 32 / width, part = lane / width, kl = lane - part * width;
+    for (int k0 = 0; k0 < fs; k0 += width) {
         const int k = k0 + kl;
         cplx acc = mk(0.0, 0.0);
-        if (k < sp) {
+        if (k < fs) {
             const double* gr = G + kg_off(sp, 0, k, 0);
             const double* gi = G + kg_off(sp, 0, k, 1);
-            for (int j = part; j < sp; j += nparts) cfma(acc, mk(gr[4 * j], gi[4 * j]), xf[j]);
+            for (int j = part; j < fs; j += nparts) cfma(acc, mk(gr[4 * j], gi[4 * j]), xf[j]);
             const double* mr = M + kg_off(up, 0, k, 0);
             const double* mi = M + kg_off(up, 0, k, 1);
-            for (int i = part; i < up; i += nparts) cfma(acc, mk(-mr[4 * i], -mi[4 * i]), xf[sp + i]);
+            for (int i = part; i < fu; i += nparts) cfma(acc, mk(-mr[4 * i], -mi[4 * i]), xf[sp + i]);
         }
         for (int off = width; off < 32; off <<= 1) {
             acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
             acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
         }
-        if (k < sp && part == 0) {
+        if (k < fs && part == 0) {
             v[cbp + k] = acc;
-            if (k < fs) x[tb.pos2orig[cbp + k]] = acc;
+            x[tb.pos2orig[cbp + k]] = acc;
         }
     }
 }

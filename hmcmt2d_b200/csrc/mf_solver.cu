@@ -26,7 +26,7 @@ constexpr int kSolveWarpMaxFp = 64;  // solves: warp-per-front kernels up to thi
 constexpr int kTinyWarps = 2;       // warps per CTA for fronts with fp <= 48
 
 template <int NW>
-int launch_small(cudaStream_t st, const Tables& tb, const int* list, int n, int nsys, size_t smem) {
+int launch_small(cudaStream_t st, const Tables& tb, const SmallDesc* list, int n, int nsys, size_t smem) {
     static PerDeviceOnceMf once;
     if (once.need()) HMCMT_CUDA_TRY(cudaFuncSetAttribute(mf_small_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
     mf_small_kernel<NW><<<dim3(n, nsys), NW * 32, smem, st>>>(tb, list);
@@ -112,14 +112,26 @@ int Solver::build(int nsys_, int maxRhs_, int64_t valCount_) {
         int* p = nullptr;
         D.nSmall = (int)sm.size();
         if (D.nSmall) {
-            MF_TRY(upload(sm, &p));
-            D.smallList = p;
             int mx = 0;
             D.smallSmem = 0;
+            std::vector<SmallDesc> descs;
             for (int k : sm) {
-                mx = std::max(mx, S.fronts[k].fp());
-                D.smallSmem = std::max(D.smallSmem, mf_front_smem_bytes(S.fronts[k].fp() / 8, S.fronts[k].sp / 8));
+                const Front& F = S.fronts[k];
+                mx = std::max(mx, F.fp());
+                D.smallSmem = std::max(D.smallSmem, mf_front_smem_bytes(F.fp() / 8, F.sp / 8, mf_rel_total(S, k)));
+                SmallDesc sd{};
+                sd.sp = F.sp; sd.up = F.up; sd.s = F.s; sd.nChild = F.nChild; sd.nOrig = F.nOrig; sd.origPtr = F.origPtr;
+                sd.par = F.depth & 1; sd.front = k;
+                sd.gOff = S.chunks[F.chunkPtr].gOff; sd.mOff = S.chunks[F.chunkPtr].mOff; sd.uOff = F.frontOff;
+                for (int c = 0; c < std::min(F.nChild, kDescChildren); ++c) {
+                    const Front& C = S.fronts[S.children[F.childPtr + c]];
+                    sd.cOff[c] = C.frontOff; sd.cLd[c] = C.ldU(); sd.cFirst[c] = C.offU(); sd.cU[c] = C.u; sd.cRel[c] = C.rowPtr;
+                }
+                descs.push_back(sd);
             }
+            SmallDesc* pd = nullptr;
+            MF_TRY(upload(descs, &pd));
+            D.smallDescs = pd;
             const char* tw = std::getenv("HMCMT_MF_TINYWARPS");
             D.smallWarps = mx <= 48 ? (tw ? std::atoi(tw) : kTinyWarps) : (mx <= 64 ? 4 : (mx <= 104 ? 8 : 16));
         }
@@ -242,10 +254,10 @@ int Solver::factor(cudaStream_t st, int* dStatus, int64_t* nLaunches, int sys0, 
         const int par = d & 1;
         if (D.nSmall) {
             int rc = kOk;
-            if (D.smallWarps == 2) rc = launch_small<2>(st, tb, D.smallList, D.nSmall, nsys, D.smallSmem);
-            else if (D.smallWarps == 4) rc = launch_small<4>(st, tb, D.smallList, D.nSmall, nsys, D.smallSmem);
-            else if (D.smallWarps == 8) rc = launch_small<8>(st, tb, D.smallList, D.nSmall, nsys, D.smallSmem);
-            else rc = launch_small<16>(st, tb, D.smallList, D.nSmall, nsys, D.smallSmem);
+            if (D.smallWarps == 2) rc = launch_small<2>(st, tb, D.smallDescs, D.nSmall, nsys, D.smallSmem);
+            else if (D.smallWarps == 4) rc = launch_small<4>(st, tb, D.smallDescs, D.nSmall, nsys, D.smallSmem);
+            else if (D.smallWarps == 8) rc = launch_small<8>(st, tb, D.smallDescs, D.nSmall, nsys, D.smallSmem);
+            else rc = launch_small<16>(st, tb, D.smallDescs, D.nSmall, nsys, D.smallSmem);
             if (rc) return rc;
             ++nl;
         }

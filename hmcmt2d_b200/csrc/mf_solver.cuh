@@ -18,10 +18,21 @@ struct MtValSys {
     double omega;
 };
 
+// Everything the single-CTA front kernel needs to know about a front, in one record (one global-memory round trip instead of
+// the chain list -> front -> child ids -> child fronts): offsets in doubles into the per-system factor / depth-parity arenas.
+constexpr int kDescChildren = kSmallChildren;      // fronts with more children take the global-memory path (mf_symbolic)
+struct SmallDesc {
+    int sp, up, s, nChild;
+    int nOrig, origPtr, par, front;       // par: depth parity (arena that takes its update matrix); front: id in Symbolic::fronts
+    int64_t gOff, mOff, uOff;
+    int64_t cOff[kDescChildren];          // child update matrices (arena of the other parity)
+    int cLd[kDescChildren], cFirst[kDescChildren], cU[kDescChildren], cRel[kDescChildren];   // ld, first row / column, real rows, rel offset
+};
+
 struct DepthSchedule {
     int nSmall = 0, smallWarps = 4;
     size_t smallSmem = 0;
-    const int* smallList = nullptr;
+    const SmallDesc* smallDescs = nullptr;
     int nBig = 0;
     const int* bigList = nullptr;
     int nOrigPairs = 0;

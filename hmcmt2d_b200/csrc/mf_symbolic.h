@@ -30,9 +30,12 @@ inline int pad8(int x) { return (x + 7) & ~7; }
 
 // shared memory of the single-CTA front kernel (mf_kernels.cuh) for a front of nb tile rows of which npb are pivots:
 // lower tiles + max(sweep scratch, M' buffer) + the pivot block inverse + flag
-inline size_t mf_front_smem_bytes(int nb, int npb) {
+// (+ the front's record at the head, + relTotal ints: the row maps of all children, staged together ahead of the extend-add)
+constexpr size_t kFrontDescBytes = 160;
+constexpr int kSmallChildren = 4;
+inline size_t mf_front_smem_bytes(int nb, int npb, int relTotal = 0) {
     const size_t nT = (size_t)nb * (nb + 1) / 2, nS = 2 * (size_t)npb, nM = (size_t)(nb - npb) * npb;
-    return (nT + (nS > nM ? nS : nM) + 1) * 128 * sizeof(double) + 16;
+    return kFrontDescBytes + (nT + (nS > nM ? nS : nM) + 1) * 128 * sizeof(double) + 16 + (((size_t)relTotal + 1) & ~(size_t)1) * 2 * sizeof(int);
 }
 constexpr size_t kFrontSmemMax = 227 * 1024;
 
@@ -391,7 +394,10 @@ inline bool mf_symbolic(int N, const std::vector<std::vector<int>>& snodes, cons
     for (int k = 0; k < K; ++k) {
         Front& F = S.fronts[k];
         const int fp = F.fp();
-        F.isBig = (fp > fSmall || mf_front_smem_bytes(fp / 8, F.sp / 8) > kFrontSmemMax) ? 1 : 0;
+        int relTotal = 0;
+        for (int c = 0; c < F.nChild; ++c) relTotal += S.fronts[S.children[F.childPtr + c]].u;
+        // (the single-CTA kernel's front record describes up to kSmallChildren children)
+        F.isBig = (fp > fSmall || F.nChild > kSmallChildren || mf_front_smem_bytes(fp / 8, F.sp / 8, relTotal) > kFrontSmemMax) ? 1 : 0;
         S.maxFp = std::max(S.maxFp, fp);
         (F.isBig ? S.maxFpBig : S.maxFpSmall) = std::max(F.isBig ? S.maxFpBig : S.maxFpSmall, fp);
         (F.isBig ? S.byDepthBig : S.byDepthSmall)[F.depth].push_back(k);
@@ -431,6 +437,14 @@ inline bool mf_symbolic(int N, const std::vector<std::vector<int>>& snodes, cons
     S.arenaDoubles[1] = arena[1];
     S.updEntries = upd;
     return true;
+}
+
+// real update rows of all children of front k (entries of the staged row maps)
+inline int mf_rel_total(const Symbolic& S, int k) {
+    const Front& F = S.fronts[k];
+    int n = 0;
+    for (int c = 0; c < F.nChild; ++c) n += S.fronts[S.children[F.childPtr + c]].u;
+    return n;
 }
 
 // pattern of the MT stencil systems in the internal ordering (mt_kernels.cuh): value array = [diag N | e1 N | e2 N]
