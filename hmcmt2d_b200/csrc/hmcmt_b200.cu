@@ -211,6 +211,11 @@ int mf_cross_size() {
     const int v = e ? std::atoi(e) : 0;
     return v < 0 ? 0 : v;
 }
+int mf_push_size() {
+    const char* e = std::getenv("HMCMT_MF_PUSH");
+    const int v = e ? std::atoi(e) : 2;      // measured at cfg2: 0 -> 4.85, 1 -> 4.82, 2 -> 4.73, 7 -> 4.78 ms per step
+    return v < 0 ? 0 : (v > 7 ? 7 : v);
+}
 int mf_small_front() {
     const char* e = std::getenv("HMCMT_MF_FSMALL");
     int v = e ? std::atoi(e) : 144;
@@ -896,7 +901,7 @@ int hmcmt_plan_create(const hmcmt_problem* pr, hmcmt_plan** out) {
         // nested-dissection multifrontal solver for all systems of the plan (one symbolic analysis, shared by every system)
         std::vector<std::vector<int>> sn;
         std::vector<mf::Entry> ent;
-        mf::mf_order_grid(M.nl, M.nf, mf_leaf_size(), sn, mf_cross_size());
+        mf::mf_order_grid(M.nl, M.nf, mf_leaf_size(), sn, mf_cross_size(), mf_push_size());
         mf::mf_grid_entries(M.nl, M.nf, ent);
         mf::Symbolic S;
         if (!mf::mf_symbolic(M.N, sn, ent, mf_small_front(), S)) { hmcmt_destroy(pl); return kErrArg; }

@@ -139,7 +139,7 @@ __device__ __forceinline__ void mf_front_factor(double* __restrict__ tiles, doub
         }
         if (npb == 1) break;
         __syncthreads();
-        MF_SWEEP_MARK(0);
+        MF_SWEEP_MARK(0);      // slot 0: 8x8 inversions
         // m_I = raw_I (-P) for the other pivot block rows; raw_I kept as an operand tile for the update below
         for (int I = warp; I < npb; I += NW) {
             if (I == kb) continue;
@@ -154,7 +154,7 @@ __device__ __forceinline__ void mf_front_factor(double* __restrict__ tiles, doub
             cfrag_store(c, mmb + (size_t)I * 128, g, t);
         }
         __syncthreads();
-        MF_SWEEP_MARK(1);
+        MF_SWEEP_MARK(1);      // slot 1: rest of the pivot-block sweep
         // A[I][J] += m_I raw_J^T (I, J != kb), column / row kb <- -m
         {
             int I = 0, J = warp;
@@ -187,11 +187,12 @@ __device__ __forceinline__ void mf_front_factor(double* __restrict__ tiles, doub
             }
         }
         __syncthreads();
-        MF_SWEEP_MARK(2);
+        MF_SWEEP_MARK(1);
     }
     const int nub = nb - npb;
     if (nub == 0) { __syncthreads(); return; }
     __syncthreads();
+    if (npb == 1) MF_SWEEP_MARK(0);
     // ---- C: M'(I, kb) = sum_j F21(I, j) (-G)(j, kb) ----
     for (int q = warp; q < nub * npb; q += NW) {
         const int Iu = q / npb, kb = q - Iu * npb, I = npb + Iu;
@@ -208,7 +209,7 @@ __device__ __forceinline__ void mf_front_factor(double* __restrict__ tiles, doub
         cfrag_store(c, mbuf + (size_t)q * 128, g, t);
     }
     __syncthreads();
-    MF_SWEEP_MARK(3);
+    MF_SWEEP_MARK(2);      // slot 2: M' = F21 (-G)
     // ---- D: U(I, J) += sum_kb M'(I, kb) F21(J, kb)^T, lower tiles, two tiles per trip (independent DMMA chains) ----
     {
         const int nU = nub * (nub + 1) / 2;

@@ -67,7 +67,7 @@ Solver::~Solver() {
                         (double)q[1] / q[6], (double)q[2] / q[6], (double)q[3] / q[6], (double)q[4] / q[6], (double)q[5] / q[6]);
             const unsigned long long* w = h + 32 + 4 * c;
             if (q[7])
-                fprintf(stderr, "[hmcmt_b200]     sweep, cycles per pivot block: panel copy + inversion %.0f  barrier %.0f  M' %.0f  trailing update %.0f\n",
+                fprintf(stderr, "[hmcmt_b200]     factorisation of the front, cycles per pivot block: 8x8 inversions %.0f  rest of the pivot-block sweep %.0f  M' = F21 (-G) %.0f  U += M' F21^T %.0f\n",
                         (double)w[0] / q[7], (double)w[1] / q[7], (double)w[2] / q[7], (double)w[3] / q[7]);
         }
     }

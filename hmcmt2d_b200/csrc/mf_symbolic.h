@@ -97,42 +97,65 @@ struct Symbolic {
 //   cross : boxes whose longer side is at most `cross` are cut four ways by a cross-shaped separator (one supernode = the
 //           middle line + the two halves of the middle column): half as many tree levels and no 3..6-unknown separators padded
 //           to a whole 8-pivot tile at the bottom of the tree, where the fronts are bound by latency and not by flops
-inline void mf_order_grid(int nl, int nf, int leaf, std::vector<std::vector<int>>& out, int cross = 0) {
-    std::function<void(int, int, int, int)> rec = [&](int l0, int l1, int f0, int f1) {
+//   push  : a leaf box whose unknown count exceeds a multiple of 8 by at most `push` hands that excess (nodes next to the
+//           separator above it) to the separator's supernode when that one has padding to spare: a 3 x 3 leaf then eliminates
+//           8 unknowns in ONE 8-pivot tile instead of 9 in two (the second tile would be 1 pivot + 7 identity rows: a whole
+//           inversion / barrier round, and a 16 x 16 instead of an 8 x 8 block in the factor), the 3-unknown separator takes the
+//           ninth into its own padding.  Any partition is a valid elimination order; only the fill changes (marginally).
+inline void mf_order_grid(int nl, int nf, int leaf, std::vector<std::vector<int>>& out, int cross = 0, int push = 0) {
+    // returns the index in `out` of the supernode emitted last for the box (-1: none) and whether the box was a leaf
+    std::function<int(int, int, int, int, bool&)> rec = [&](int l0, int l1, int f0, int f1, bool& isLeaf) -> int {
         const int nL = l1 - l0, nF = f1 - f0;
-        if (nL <= 0 || nF <= 0) return;
+        isLeaf = false;
+        if (nL <= 0 || nF <= 0) return -1;
         if (nL * nF <= leaf) {
             std::vector<int> v;
             v.reserve((size_t)nL * nF);
             for (int l = l0; l < l1; ++l)
                 for (int f = f0; f < f1; ++f) v.push_back(l * nf + f);
             out.push_back(std::move(v));
-            return;
+            isLeaf = true;
+            return (int)out.size() - 1;
         }
         std::vector<int> sep;
+        bool la = false, lb = false, lc = false, ld = false;
         if (std::max(nL, nF) <= cross && std::min(nL, nF) >= 3) {
             const int ml = (l0 + l1) / 2, mf = (f0 + f1) / 2;
-            rec(l0, ml, f0, mf);
-            rec(l0, ml, mf + 1, f1);
-            rec(ml + 1, l1, f0, mf);
-            rec(ml + 1, l1, mf + 1, f1);
+            rec(l0, ml, f0, mf, la);
+            rec(l0, ml, mf + 1, f1, lb);
+            rec(ml + 1, l1, f0, mf, lc);
+            rec(ml + 1, l1, mf + 1, f1, ld);
             for (int f = f0; f < f1; ++f) sep.push_back(ml * nf + f);
             for (int l = l0; l < l1; ++l)
                 if (l != ml) sep.push_back(l * nf + mf);
-        } else if (nL >= nF) {
-            const int mid = (l0 + l1) / 2;
-            rec(l0, mid, f0, f1);
-            rec(mid + 1, l1, f0, f1);
-            for (int f = f0; f < f1; ++f) sep.push_back(mid * nf + f);
         } else {
-            const int mid = (f0 + f1) / 2;
-            rec(l0, l1, f0, mid);
-            rec(l0, l1, mid + 1, f1);
-            for (int l = l0; l < l1; ++l) sep.push_back(l * nf + mid);
+            const bool byLine = nL >= nF;
+            const int mid = byLine ? (l0 + l1) / 2 : (f0 + f1) / 2;
+            const int a = byLine ? rec(l0, mid, f0, f1, la) : rec(l0, l1, f0, mid, la);
+            const int b = byLine ? rec(mid + 1, l1, f0, f1, lb) : rec(l0, l1, mid + 1, f1, lb);
+            if (byLine) for (int f = f0; f < f1; ++f) sep.push_back(mid * nf + f);
+            else for (int l = l0; l < l1; ++l) sep.push_back(l * nf + mid);
+            const int cap = pad8((int)sep.size());
+            auto absorb = [&](int ci, bool childIsLeaf, int adj) {      // adj: line / column of the child next to the separator
+                if (ci < 0 || !childIsLeaf || push <= 0) return;
+                std::vector<int>& v = out[ci];
+                const int s = (int)v.size(), e = s % 8;
+                if (s <= 8 || e == 0 || e > push || (int)sep.size() + e > cap) return;
+                int moved = 0;
+                for (size_t i = 0; i < v.size() && moved < e;) {
+                    const int q = v[i], l = q / nf, f = q - l * nf;
+                    if ((byLine ? l : f) == adj) { sep.push_back(q); v.erase(v.begin() + i); ++moved; }
+                    else ++i;
+                }
+            };
+            absorb(a, la, mid - 1);
+            absorb(b, lb, mid + 1);
         }
         out.push_back(std::move(sep));
+        return (int)out.size() - 1;
     };
-    rec(0, nl, 0, nf);
+    bool dummy = false;
+    rec(0, nl, 0, nf, dummy);
 }
 
 // general symmetric pattern (adjacency in CSR form without the diagonal): recursive bisection, the separator is the smallest

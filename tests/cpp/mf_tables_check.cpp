@@ -42,7 +42,8 @@ int main(int argc, char** argv) {
         N = nl * nf;
         mf_grid_entries(nl, nf, ent);
         const int cross = argc > 6 ? atoi(argv[6]) : 0;      // four-way cross separators for boxes up to this size
-        mf_order_grid(nl, nf, leaf, sn, cross);
+        const int push = argc > 7 ? atoi(argv[7]) : 0;        // leaf excess over a multiple of 8 handed to the separator above
+        mf_order_grid(nl, nf, leaf, sn, cross, push);
     } else {
         int nx = atoi(argv[2]), ny = atoi(argv[3]), nz = atoi(argv[4]), leaf = atoi(argv[5]);
         fSmall = atoi(argv[6]);
