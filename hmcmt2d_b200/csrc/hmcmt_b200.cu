@@ -56,7 +56,7 @@ struct hmcmt_plan {
     RxDev rx{};
     cudaStream_t stream = nullptr, side = nullptr;      // side: 1-D sensitivity scalars overlap the factorisation
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
-    cudaEvent_t evA = nullptr, evB = nullptr, evPre = nullptr;
+    cudaEvent_t evA = nullptr, evB = nullptr, evPre = nullptr, evRhs = nullptr;
     std::vector<cudaStream_t> groupStreams;             // >= 2: the systems of a step run as groups on these streams (compute_step_grouped)
     std::vector<cudaEvent_t> groupDone;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> factorEvents;
@@ -96,7 +96,7 @@ struct hmcmt_plan {
 
 namespace {
 
-constexpr int kDefaultGroups = 2;              // groups of systems per evaluation on the multifrontal path (HMCMT_GROUPS)
+constexpr int kDefaultGroups = 3;              // groups of systems per evaluation on the multifrontal path (HMCMT_GROUPS)
 constexpr size_t kMaxFactorEvents = 4096;      // CUDA-event pairs kept for hmcmt_kernel_time (opt-in, bounded)
 
 #define LAUNCH_CHECK(pl)                                          \
@@ -392,11 +392,11 @@ struct SysRange {
     cudaStream_t st;
 };
 
-// sigma, stencil planes, boundary values and right-hand sides of ALL systems (cheap, plan stream)
-int forward_pre(hmcmt_plan* pl, bool wantAdjoint) {
+// sigma and stencil planes of all chains / modes: everything the factorisations need (plan stream)
+int forward_model(hmcmt_plan* pl) {
     const MeshDev& M = pl->M;
     cudaStream_t st = pl->stream;
-    const int nSys = pl->nSys, nCh = pl->nChains;
+    const int nCh = pl->nChains;
     pl->haveForward = false;
     pl->haveSens = false;
     if (!pl->sigmaDirect) {
@@ -405,6 +405,14 @@ int forward_pre(hmcmt_plan* pl, bool wantAdjoint) {
     }
     k_stencil_planes<<<dim3((M.N + 255) / 256, nCh * pl->nModes), 256, 0, st>>>(M, pl->sm, pl->sigma.p, pl->planes.p);
     LAUNCH_CHECK(pl);
+    return kOk;
+}
+// boundary values and right-hand sides of ALL systems (plan stream; the factorisations do not depend on them), then the
+// layered-earth sensitivity scalars on the side stream
+int forward_bc(hmcmt_plan* pl, bool wantAdjoint) {
+    const MeshDev& M = pl->M;
+    cudaStream_t st = pl->stream;
+    const int nSys = pl->nSys, nCh = pl->nChains;
     {
         // as many profiles per block as shared memory allows: the serial phase keeps PB lanes of one warp busy and is bound by
         // FP64 issue slots, so fewer profiles per block (even when that avoids a second wave of blocks) measured slower
@@ -421,25 +429,32 @@ int forward_pre(hmcmt_plan* pl, bool wantAdjoint) {
     }
     return kOk;
 }
+int forward_pre(hmcmt_plan* pl, bool wantAdjoint) {
+    int rc = forward_model(pl);
+    return rc ? rc : forward_bc(pl, wantAdjoint);
+}
 
-// factorisation + forward solve + node-ordered fields of one range (the band kernels only take the whole batch)
-int forward_solve(hmcmt_plan* pl, const SysRange& r) {
+// factorisation + forward solve of one range (the band kernels only take the whole batch and do both in forward_factor);
+// rhsReady: event the forward solve waits for (the right-hand sides are produced on another stream), or null
+int forward_factor(hmcmt_plan* pl, const SysRange& r) {
     const MeshDev& M = pl->M;
-    int rc;
     if (pl->useMf) {
-        rc = pl->mfs->set_mt_values(r.st, M.N, pl->mfSys.p, r.s0, r.n);
+        int rc = pl->mfs->set_mt_values(r.st, M.N, pl->mfSys.p, r.s0, r.n);
         if (rc) return rc;
         ++pl->launches;
-        rc = pl->mfs->factor(r.st, pl->status.p, &pl->launches, r.s0, r.n);
-        if (rc) return rc;
-        rc = pl->mfs->solve(r.st, 1, pl->rhs.p, M.N, pl->x.p, M.N, &pl->launches, r.s0, r.n, pl->patRhs);
-    } else {
-        if (r.s0 != 0 || r.n != pl->nSys) return kErrArg;
-        int nl = 0;
-        rc = launch_factor(r.st, pl->T, pl->sysDesc.p, pl->nSys, pl->dom, pl->fwdJobs.p, &nl);
-        pl->launches += nl;
+        return pl->mfs->factor(r.st, pl->status.p, &pl->launches, r.s0, r.n);
     }
+    if (r.s0 != 0 || r.n != pl->nSys) return kErrArg;
+    int nl = 0;
+    int rc = launch_factor(r.st, pl->T, pl->sysDesc.p, pl->nSys, pl->dom, pl->fwdJobs.p, &nl);
+    pl->launches += nl;
     return rc;
+}
+int forward_solve(hmcmt_plan* pl, const SysRange& r, cudaEvent_t rhsReady = nullptr) {
+    const MeshDev& M = pl->M;
+    if (!pl->useMf) return kOk;      // fused into the band factorisation
+    if (rhsReady) HMCMT_CUDA_TRY(cudaStreamWaitEvent(r.st, rhsReady, 0));
+    return pl->mfs->solve(r.st, 1, pl->rhs.p, M.N, pl->x.p, M.N, &pl->launches, r.s0, r.n, pl->patRhs);
 }
 int forward_fields(hmcmt_plan* pl, const SysRange& r) {
     const MeshDev& M = pl->M;
@@ -466,7 +481,8 @@ int forward_phase(hmcmt_plan* pl, bool wantAdjoint) {
         HMCMT_CUDA_TRY(cudaEventRecord(ev->first, st));
     }
     const SysRange all{0, pl->nSys, st};
-    rc = forward_solve(pl, all);
+    rc = forward_factor(pl, all);
+    if (rc == kOk) rc = forward_solve(pl, all);
     if (rc) return rc;
     ++pl->factorLaunches;
     if (ev) HMCMT_CUDA_TRY(cudaEventRecord(ev->second, st));
@@ -539,15 +555,25 @@ int adjoint_phase(hmcmt_plan* pl, bool reduce = true) {
 // forward + adjoint gradient of the whole batch with the systems split into groups on their own streams
 int compute_step_grouped(hmcmt_plan* pl) {
     const int G = (int)pl->groupStreams.size();
-    int rc = forward_pre(pl, true);
+    int rc = forward_model(pl);
     if (rc) return rc;
     HMCMT_CUDA_TRY(cudaEventRecord(pl->evPre, pl->stream));
+    // the groups start factorising right away; boundary values / right-hand sides (plan stream) and the sensitivity scalars
+    // (side stream) are produced meanwhile and joined where they are first needed
+    std::vector<SysRange> rs;
     for (int g = 0; g < G; ++g) {
         const int s0 = (int)((int64_t)pl->nSys * g / G), s1 = (int)((int64_t)pl->nSys * (g + 1) / G);
         if (s1 <= s0) continue;
-        const SysRange r{s0, s1 - s0, pl->groupStreams[g]};
-        HMCMT_CUDA_TRY(cudaStreamWaitEvent(r.st, pl->evPre, 0));
-        if ((rc = forward_solve(pl, r)) || (rc = forward_fields(pl, r)) || (rc = rx_range(pl, r, true, nullptr)) || (rc = adjoint_range(pl, r)))
+        rs.push_back(SysRange{s0, s1 - s0, pl->groupStreams[g]});
+        HMCMT_CUDA_TRY(cudaStreamWaitEvent(rs.back().st, pl->evPre, 0));
+        if ((rc = forward_factor(pl, rs.back()))) return rc;
+    }
+    if ((rc = forward_bc(pl, true))) return rc;
+    HMCMT_CUDA_TRY(cudaEventRecord(pl->evRhs, pl->stream));
+    for (size_t g = 0; g < rs.size(); ++g) {
+        const SysRange& r = rs[g];
+        if ((rc = forward_solve(pl, r, pl->evRhs)) || (rc = forward_fields(pl, r)) || (rc = rx_range(pl, r, true, nullptr)) ||
+            (rc = adjoint_range(pl, r)))
             return rc;
         HMCMT_CUDA_TRY(cudaEventRecord(pl->groupDone[g], r.st));
         HMCMT_CUDA_TRY(cudaStreamWaitEvent(pl->stream, pl->groupDone[g], 0));
@@ -931,6 +957,7 @@ int hmcmt_plan_create(const hmcmt_problem* pr, hmcmt_plan** out) {
         cudaEventCreateWithFlags(&pl->evFork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&pl->evJoin, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&pl->evPre, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&pl->evRhs, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&pl->evA) != cudaSuccess || cudaEventCreate(&pl->evB) != cudaSuccess) {
         hmcmt_destroy(pl);
         return kErrCuda;
@@ -966,6 +993,7 @@ void hmcmt_destroy(hmcmt_plan* pl) {
     for (cudaStream_t s : pl->groupStreams) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
     for (cudaEvent_t e : pl->groupDone) cudaEventDestroy(e);
     if (pl->evPre) cudaEventDestroy(pl->evPre);
+    if (pl->evRhs) cudaEventDestroy(pl->evRhs);
     if (pl->evFork) cudaEventDestroy(pl->evFork);
     if (pl->evJoin) cudaEventDestroy(pl->evJoin);
     if (pl->evA) cudaEventDestroy(pl->evA);
