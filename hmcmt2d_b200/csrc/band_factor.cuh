@@ -260,7 +260,7 @@ __device__ __forceinline__ void gj_invert8(cplx& a0, cplx& a1, bool& bad, const 
             if (k < nsteps) pivot_step(k);
     } else {
 #pragma unroll 1
-        for (int k = 0; k < 8; ++k) pivot_step(k);
+        for (int k = 0; k < nsteps; ++k) pivot_step(k);
     }
     const double den = fma(q.x, q.x, q.y * q.y);
     if (!(den > 0.0) || isinf(den)) bad = true;

@@ -127,7 +127,7 @@ __device__ __forceinline__ void mf_front_factor(double* __restrict__ tiles, doub
             cplx a0 = mk(sym(g, 2 * t, 0), sym(g, 2 * t, 1)), a1 = mk(sym(g, 2 * t + 1, 0), sym(g, 2 * t + 1, 1));
             bool bad = false;
             const int left = sReal - 8 * kb;
-            gj_invert8<true>(a0, a1, bad, g, t, left < 8 ? (left < 0 ? 0 : left) : 8);
+            gj_invert8<(NW > 4)>(a0, a1, bad, g, t, left < 8 ? (left < 0 ? 0 : left) : 8);
             if (__any_sync(0xffffffffu, bad) && lane == 0) *fail = 1;
             TileFrag p;
             p.re[0] = -a0.x; p.re[1] = -a1.x; p.im[0] = -a0.y; p.im[1] = -a1.y;
@@ -194,19 +194,21 @@ __device__ __forceinline__ void mf_front_factor(double* __restrict__ tiles, doub
     __syncthreads();
     if (npb == 1) MF_SWEEP_MARK(0);
     // ---- C: M'(I, kb) = sum_j F21(I, j) (-G)(j, kb) ----
-    for (int q = warp; q < nub * npb; q += NW) {
-        const int Iu = q / npb, kb = q - Iu * npb, I = npb + Iu;
-        TileFrag c, x;
-        frag_zero(c); frag_zero(x);
-        for (int j = 0; j < npb; ++j) {
-            TileFrag a, b;
-            frag_load(a, mf_tile(tiles, I, j), lane);
-            if (kb >= j) frag_load(b, mf_tile(tiles, kb, j), lane);       // B[n][k] = (-G)(kb n, j k)
-            else frag_load_t(b, mf_tile(tiles, j, kb), g, t);
-            frag_mma(c, x, a, b);
+    for (int Iu = warp; Iu < nub; Iu += NW) {
+        const int I = npb + Iu;
+        for (int kb = 0; kb < npb; ++kb) {
+            TileFrag c, x;
+            frag_zero(c); frag_zero(x);
+            for (int j = 0; j < npb; ++j) {
+                TileFrag a, b;
+                frag_load(a, mf_tile(tiles, I, j), lane);
+                if (kb >= j) frag_load(b, mf_tile(tiles, kb, j), lane);       // B[n][k] = (-G)(kb n, j k)
+                else frag_load_t(b, mf_tile(tiles, j, kb), g, t);
+                frag_mma(c, x, a, b);
+            }
+            frag_add(c, x);
+            cfrag_store(c, mbuf + (size_t)(Iu * npb + kb) * 128, g, t);
         }
-        frag_add(c, x);
-        cfrag_store(c, mbuf + (size_t)q * 128, g, t);
     }
     __syncthreads();
     MF_SWEEP_MARK(2);      // slot 2: M' = F21 (-G)
@@ -275,7 +277,7 @@ __device__ __forceinline__ void mf_store_tile(const double* __restrict__ T, doub
 // (register budget: the two- and four-warp instantiations serve the thousands of tiny fronts at the bottom of the tree, where the
 // number of fronts resident per SM hides the latency of the 8x8 inversions: 64 registers per thread -> 16 / 8 CTAs per SM)
 template <int NW>
-__global__ void __launch_bounds__(NW * 32, NW <= 4 ? 32 / NW : 1)
+__global__ void __launch_bounds__(NW * 32, NW <= 4 ? 32 / NW : (NW == 8 ? 2 : 1))
 mf_small_kernel(Tables tb, const SmallDesc* __restrict__ descs) {
     constexpr int NT = NW * 32;
     extern __shared__ __align__(16) unsigned char mf_smem[];
@@ -341,7 +343,7 @@ mf_small_kernel(Tables tb, const SmallDesc* __restrict__ descs) {
 #pragma unroll
         for (int bq = 0; bq < kBatch; ++bq) {
             const int q = curQ + bq;
-            const int jg = q / nrb, i = (q - jg * nrb) * 32 + lane;
+            const int jg = nrb == 1 ? q : q / nrb, i = (q - jg * nrb) * 32 + lane;
             bt.jg[bq] = jg;
             bt.ii[bq] = (q < ng * nrb && i < cu && i >= 4 * jg) ? i : -1;
             if (bt.ii[bq] >= 0) {
@@ -394,14 +396,8 @@ mf_small_kernel(Tables tb, const SmallDesc* __restrict__ descs) {
         };
         while (b0.c >= 0) {
             scatter(b0);
-            load_batch(b0);
-            if (b1.c < 0) break;
-            scatter(b1);
+            b0 = b1;
             load_batch(b1);
-        }
-        // (b0 may still hold a batch when b1 ran dry first)
-        if (b0.c >= 0 && b1.c < 0) {
-            while (b0.c >= 0) { scatter(b0); load_batch(b0); }
         }
         while (passed < nChild - 1) { __syncthreads(); ++passed; }
         __syncthreads();
@@ -430,18 +426,16 @@ mf_small_kernel(Tables tb, const SmallDesc* __restrict__ descs) {
     const int sp = F.sp, up = F.up;
     {
         double* G = fac + F.gOff;
-        for (int q = warp; q < npb * npb; q += NW) {
-            const int I = q / npb, J = q - I * npb;
-            if (I >= J) mf_store_tile<false>(mf_tile(tiles, I, J), G, sp, I * 8, J * 8, -1.0, lane);
-            else mf_store_tile<true>(mf_tile(tiles, J, I), G, sp, I * 8, J * 8, -1.0, lane);
-        }
+        for (int I = warp; I < npb; I += NW)
+            for (int J = 0; J < npb; ++J) {
+                if (I >= J) mf_store_tile<false>(mf_tile(tiles, I, J), G, sp, I * 8, J * 8, -1.0, lane);
+                else mf_store_tile<true>(mf_tile(tiles, J, I), G, sp, I * 8, J * 8, -1.0, lane);
+            }
     }
     if (up > 0) {
         double* M = fac + F.mOff;
-        for (int q = warp; q < nub * npb; q += NW) {
-            const int I = q / npb, J = q - I * npb;
-            mf_store_tile<false>(mbuf + (size_t)q * 128, M, up, I * 8, J * 8, -1.0, lane);
-        }
+        for (int I = warp; I < nub; I += NW)
+            for (int J = 0; J < npb; ++J) mf_store_tile<false>(mbuf + (size_t)(I * npb + J) * 128, M, up, I * 8, J * 8, -1.0, lane);
         double* U = tb.arena[F.par] + (size_t)sys * tb.arenaStride[F.par] + F.uOff;
         int I = 0, J = warp;
         while (J > I) { J -= I + 1; ++I; }
