@@ -57,6 +57,9 @@ struct hmcmt_plan {
     cudaStream_t stream = nullptr, side = nullptr;      // side: 1-D sensitivity scalars overlap the factorisation
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
     cudaEvent_t evA = nullptr, evB = nullptr, evPre = nullptr, evRhs = nullptr;
+    cudaGraphExec_t graphExec = nullptr;                // the gradient evaluation, captured on its second call (compute_step_graph)
+    int graphState = 0;                                 // 0: not run yet, 1: warmed up, 2: graph ready, -1: disabled
+    int64_t graphLaunches = 0;
     std::vector<cudaStream_t> groupStreams;             // >= 2: the systems of a step run as groups on these streams (compute_step_grouped)
     std::vector<cudaEvent_t> groupDone;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> factorEvents;
@@ -584,10 +587,64 @@ int compute_step_grouped(hmcmt_plan* pl) {
     return reduce_grad(pl);
 }
 
+// The gradient evaluation as a CUDA graph.  Its launches (a few hundred per evaluation on the multifrontal path: one per tree
+// level, system group and phase) always have the same arguments — every buffer belongs to the plan — so the second evaluation
+// of a plan is captured from the streams (the groups' and the side stream join the capture through their events) and replayed
+// from then on: the host-buffer entry points no longer pay a launch per kernel before the device has work.  The first
+// evaluation runs eagerly (it also sets the per-device kernel attributes, which must not happen under capture).
+// HMCMT_GRAPH=0 switches it off.
+int compute_step_eager(hmcmt_plan* pl) {
+    if (pl->useMf && pl->groupStreams.size() >= 2) return compute_step_grouped(pl);
+    int rc = forward_phase(pl, true);
+    if (rc) return rc;
+    rc = rx_phase(pl, true, nullptr);
+    return rc ? rc : adjoint_phase(pl);
+}
+int compute_step_graph(hmcmt_plan* pl) {
+    if (pl->graphState == 0) {
+        pl->graphState = 1;
+        return compute_step_eager(pl);
+    }
+    if (pl->graphState == 1) {
+        const int64_t l0 = pl->launches, f0 = pl->factorLaunches;
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(pl->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            cudaGetLastError();
+            pl->graphState = -1;
+            return compute_step_eager(pl);
+        }
+        const int rc = compute_step_eager(pl);
+        const cudaError_t e = cudaStreamEndCapture(pl->stream, &graph);
+        pl->graphLaunches = pl->launches - l0;
+        pl->launches = l0;
+        pl->factorLaunches = f0;
+        if (rc != kOk || e != cudaSuccess || !graph || cudaGraphInstantiate(&pl->graphExec, graph, 0) != cudaSuccess) {
+            cudaGetLastError();
+            if (graph) cudaGraphDestroy(graph);
+            pl->graphExec = nullptr;
+            pl->graphState = -1;
+            fprintf(stderr, "[hmcmt_b200] graph capture of the evaluation failed (%s): launching eagerly\n", cudaGetErrorString(e));
+            return compute_step_eager(pl);
+        }
+        cudaGraphDestroy(graph);
+        pl->graphState = 2;
+    }
+    HMCMT_CUDA_TRY(cudaGraphLaunch(pl->graphExec, pl->stream));
+    pl->launches += pl->graphLaunches;
+    ++pl->factorLaunches;
+    pl->haveForward = true;
+    pl->haveSens = true;
+    return kOk;
+}
+
 // One evaluation of the hot path for the device-resident model pl->m:
 //   forward (all chains x modes x freqs) [+ adjoint gradient + prior gradient].
 int compute_step(hmcmt_plan* pl, bool wantAdjoint, const cplx* vin) {
-    if (wantAdjoint && !vin && pl->useMf && pl->groupStreams.size() >= 2 && !pl->timeFactor) return compute_step_grouped(pl);
+    if (wantAdjoint && !vin && !pl->timeFactor) {
+        // the graph holds the standard evaluation (sigma = exp(m), impedance responses); anything else is launched eagerly
+        const bool standard = !pl->sigmaDirect && pl->respKind == 0;
+        return pl->graphState >= 0 && standard ? compute_step_graph(pl) : compute_step_eager(pl);
+    }
     int rc = forward_phase(pl, wantAdjoint);
     if (rc) return rc;
     rc = rx_phase(pl, wantAdjoint, vin);
@@ -962,6 +1019,7 @@ int hmcmt_plan_create(const hmcmt_problem* pr, hmcmt_plan** out) {
         hmcmt_destroy(pl);
         return kErrCuda;
     }
+    if (const char* e = std::getenv("HMCMT_GRAPH"); e && !std::atoi(e)) pl->graphState = -1;
     if (pl->useMf) {
         // groups of systems on their own streams (compute_step_grouped); HMCMT_GROUPS=1 keeps everything on the plan's stream
         const char* env = std::getenv("HMCMT_GROUPS");
@@ -990,6 +1048,7 @@ void hmcmt_destroy(hmcmt_plan* pl) {
     }
     if (pl->stream) { cudaStreamSynchronize(pl->stream); cudaStreamDestroy(pl->stream); }
     if (pl->side) { cudaStreamSynchronize(pl->side); cudaStreamDestroy(pl->side); }
+    if (pl->graphExec) cudaGraphExecDestroy(pl->graphExec);
     for (cudaStream_t s : pl->groupStreams) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
     for (cudaEvent_t e : pl->groupDone) cudaEventDestroy(e);
     if (pl->evPre) cudaEventDestroy(pl->evPre);
