@@ -133,7 +133,9 @@ int Solver::build(int nsys_, int maxRhs_, int64_t valCount_) {
             MF_TRY(upload(descs, &pd));
             D.smallDescs = pd;
             const char* tw = std::getenv("HMCMT_MF_TINYWARPS");
-            D.smallWarps = mx <= 48 ? (tw ? std::atoi(tw) : kTinyWarps) : (mx <= 64 ? 4 : (mx <= 104 ? 8 : 16));
+            auto knob = [](const char* name, int dflt) { const char* e = std::getenv(name); return e ? std::atoi(e) : dflt; };
+            const int f2 = knob("HMCMT_MF_FP2", 48), f4 = knob("HMCMT_MF_FP4", 64), f8 = knob("HMCMT_MF_FP8", 104);      // largest front per CTA size
+            D.smallWarps = mx <= f2 ? (tw ? std::atoi(tw) : kTinyWarps) : (mx <= f4 ? 4 : (mx <= f8 ? 8 : 16));
         }
         D.nBig = (int)bg.size();
         D.bigBytes = (size_t)S.bigDoublesAtDepth[d] * sizeof(double);
