@@ -72,6 +72,7 @@ struct hmcmt_plan {
     std::vector<int> h_packed2full;      // [nData] full index (without chain) of each packed datum
     // device buffers
     DevBuf<double> yLen, zLen, zNode, freqs, fdy1, fdy2, wL, wR, bg, wmVal, wd, m, p, mref, sigma, meanSig, planes;
+    DevBuf<double> driftPart;                       // block maxima of the drift (k_drift_max)
     DevBuf<double> xbuf, Gpart, phiPart, phi, gsig, gdata, gtotal, energies, panels, curM, curP, chainScal, zmom;
     DevBuf<int> fid, iL, iR, cell2act, act2cell, wmPtr, wmIdx, status, driftFlag, packed2full, full2packed, Lsteps;
     DevBuf<cplx> obs, bc, bcs, rhs, x, F, lam, Lam, srows, qrow, scratch, predFull, ainvz, zadj, vin, predPacked, wexp, conCols, respFull;
@@ -719,10 +720,15 @@ int energies(hmcmt_plan* pl) {
     return kOk;
 }
 
+inline int kDriftBlocks(int nAC) { return std::max(1, std::min(128, (nAC + kHmcThreads - 1) / kHmcThreads)); }
 int drift(hmcmt_plan* pl, double dt) {
     int mrc = mass_apply(pl);
     if (mrc) return mrc;
-    k_drift<<<pl->nChains, kHmcThreads, 0, pl->stream>>>(pl->nAC, dt, pl->lo, pl->hi, pl->m.p, pl->p.p, pl->driftFlag.p, pl->massOn ? pl->gradK.p : nullptr);
+    const double* gk = pl->massOn ? pl->gradK.p : nullptr;
+    const dim3 grid(kDriftBlocks(pl->nAC), pl->nChains);
+    k_drift_max<<<grid, kHmcThreads, 0, pl->stream>>>(pl->nAC, dt, pl->p.p, gk, pl->driftPart.p);
+    LAUNCH_CHECK(pl);
+    k_drift<<<grid, kHmcThreads, 0, pl->stream>>>(pl->nAC, dt, pl->lo, pl->hi, pl->m.p, pl->p.p, pl->driftFlag.p, gk, pl->driftPart.p);
     LAUNCH_CHECK(pl);
     return kOk;
 }
@@ -893,7 +899,7 @@ int hmcmt_plan_create(const hmcmt_problem* pr, hmcmt_plan** out) {
     }
     const size_t nCh = pl->nChains, nSys = pl->nSys, N = M.N;
     ok(pl->m.alloc(nCh * pr->nAC)); ok(pl->p.alloc(nCh * pr->nAC)); ok(pl->mref.alloc(nCh * pr->nAC));
-    ok(pl->curM.alloc(nCh * pr->nAC)); ok(pl->curP.alloc(nCh * pr->nAC)); ok(pl->zmom.alloc(nCh * pr->nAC));
+    ok(pl->curM.alloc(nCh * pr->nAC)); ok(pl->curP.alloc(nCh * pr->nAC)); ok(pl->zmom.alloc(nCh * pr->nAC)); ok(pl->driftPart.alloc(nCh * 128));
     ok(pl->sigma.alloc(nCh * M.nCell)); ok(pl->meanSig.alloc(nCh * nz));
     ok(pl->planes.alloc(nCh * pl->nModes * 4 * N));
     ok(pl->bc.alloc(nSys * M.nb)); ok(pl->bcs.alloc(nSys * M.nb));
@@ -1062,7 +1068,7 @@ void hmcmt_destroy(hmcmt_plan* pl) {
     pl->wL.release(); pl->wR.release(); pl->bg.release(); pl->wmVal.release(); pl->wd.release(); pl->m.release(); pl->p.release();
     pl->mref.release(); pl->sigma.release(); pl->meanSig.release(); pl->planes.release(); pl->Gpart.release(); pl->phiPart.release();
     pl->phi.release(); pl->gsig.release(); pl->gdata.release(); pl->gtotal.release(); pl->energies.release(); pl->panels.release(); pl->curM.release();
-    pl->curP.release(); pl->chainScal.release(); pl->zmom.release(); pl->fid.release(); pl->iL.release(); pl->iR.release();
+    pl->curP.release(); pl->driftPart.release(); pl->chainScal.release(); pl->zmom.release(); pl->fid.release(); pl->iL.release(); pl->iR.release();
     pl->cell2act.release(); pl->act2cell.release(); pl->wmPtr.release(); pl->wmIdx.release(); pl->status.release();
     pl->driftFlag.release(); pl->packed2full.release(); pl->full2packed.release(); pl->Lsteps.release(); pl->obs.release(); pl->bc.release(); pl->bcs.release();
     pl->rhs.release(); pl->x.release(); pl->F.release(); pl->lam.release(); pl->Lam.release(); pl->srows.release(); pl->qrow.release();
@@ -1430,7 +1436,7 @@ int hmcmt_leapfrog_steps_device(hmcmt_plan* pl, double dt, int32_t nsteps) {
         if (rc) return rc;
         rc = compute_step(pl, true, nullptr);
         if (rc) return rc;
-        k_kick<<<pl->nChains, 1024, 0, pl->stream>>>(pl->nAC, dt, pl->gtotal.p, pl->p.p);
+        k_kick<<<dim3((pl->nAC + 255) / 256, pl->nChains), 256, 0, pl->stream>>>(pl->nAC, dt, pl->gtotal.p, pl->p.p);
         LAUNCH_CHECK(pl);
     }
     return kOk;
@@ -1510,7 +1516,7 @@ int hmcmt_step_finish(hmcmt_plan* pl, double dt) {
     k_unpack_exchange<<<dim3((pl->nAC + 1 + 255) / 256, pl->nChains), 256, 0, pl->stream>>>(
         pl->nAC, pl->xbuf.p, pl->m.p, pl->mref.p, pl->wmPtr.p, pl->wmIdx.p, pl->wmVal.p, pl->beta, pl->gdata.p, pl->gtotal.p, pl->phi.p);
     LAUNCH_CHECK(pl);
-    k_kick<<<pl->nChains, 1024, 0, pl->stream>>>(pl->nAC, dt, pl->gtotal.p, pl->p.p);
+    k_kick<<<dim3((pl->nAC + 255) / 256, pl->nChains), 256, 0, pl->stream>>>(pl->nAC, dt, pl->gtotal.p, pl->p.p);
     LAUNCH_CHECK(pl);
     return kOk;
 }

@@ -928,24 +928,37 @@ __device__ inline double block_reduce(double v, bool isMax, double* sh) {
     return r;
 }
 // p -= scale*dt*grad
+// grid (ceil(nAC / blockDim), nChains)
 __global__ void k_kick(int nAC, double dtScaled, const double* __restrict__ grad, double* __restrict__ p) {
-    int ch = blockIdx.x;
-    for (int a = threadIdx.x; a < nAC; a += blockDim.x) p[(size_t)ch * nAC + a] -= dtScaled * grad[(size_t)ch * nAC + a];
+    const int ch = blockIdx.y, a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a < nAC) p[(size_t)ch * nAC + a] -= dtScaled * grad[(size_t)ch * nAC + a];
 }
-// drift with max-step clip 3.0 and reflection at the log-conductivity bounds
+// drift with max-step clip 3.0 and reflection at the log-conductivity bounds (HMCSampler.jl:235-250, checkParameterBound! :515-559),
+// two launches of grid (nBlocks, nChains): the largest |dt gradK| of every block, then the update (every block first folds the
+// block maxima: a maximum does not depend on the order, so the result is the one a single block would produce)
 __global__ void __launch_bounds__(kHmcThreads)
-k_drift(int nAC, double dt, double lo, double hi, double* __restrict__ m, double* __restrict__ p, int* __restrict__ flag,
-        const double* __restrict__ gradK) {
+k_drift_max(int nAC, double dt, const double* __restrict__ p, const double* __restrict__ gradK, double* __restrict__ part) {
     // gradK = invM p (getKineticGradient HMCSampler.jl:424-431); null: identity mass matrix, gradK = p
     __shared__ double sh[32];
-    const int ch = blockIdx.x;
+    const int ch = blockIdx.y;
+    const double* gk = (gradK ? gradK : p) + (size_t)ch * nAC;
+    double mx = 0.0;
+    for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < nAC; a += gridDim.x * blockDim.x) mx = fmax(mx, fabs(dt * gk[a]));
+    mx = block_reduce(mx, true, sh);
+    if (threadIdx.x == 0) part[(size_t)ch * gridDim.x + blockIdx.x] = mx;
+}
+__global__ void __launch_bounds__(kHmcThreads)
+k_drift(int nAC, double dt, double lo, double hi, double* __restrict__ m, double* __restrict__ p, int* __restrict__ flag,
+        const double* __restrict__ gradK, const double* __restrict__ part) {
+    __shared__ double sh[32];
+    const int ch = blockIdx.y;
     double* mm = m + (size_t)ch * nAC;
     double* pp = p + (size_t)ch * nAC;
     const double* gk = gradK ? gradK + (size_t)ch * nAC : pp;
     double mx = 0.0;
-    for (int a = threadIdx.x; a < nAC; a += blockDim.x) mx = fmax(mx, fabs(dt * gk[a]));
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) mx = fmax(mx, part[(size_t)ch * gridDim.x + b]);
     mx = block_reduce(mx, true, sh);
-    for (int a = threadIdx.x; a < nAC; a += blockDim.x) {
+    for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < nAC; a += gridDim.x * blockDim.x) {
         double dm = dt * gk[a];
         if (mx > 3.0) dm = dm / mx * 3.0;
         double v = mm[a] + dm, mom = pp[a];
@@ -963,7 +976,6 @@ k_drift(int nAC, double dt, double lo, double hi, double* __restrict__ m, double
         pp[a] = mom;
     }
 }
-// energies: K = 1/2 p.p ; phi_m = 1/2 beta (m-mref)^T Wm (m-mref)     (getHamiltonian HMCSampler.jl:358-397)
 __global__ void __launch_bounds__(kHmcThreads)
 k_energies(int nAC, const double* __restrict__ m, const double* __restrict__ mref, const double* __restrict__ p,
            const int* __restrict__ wmPtr, const int* __restrict__ wmIdx, const double* __restrict__ wmVal, double beta,
