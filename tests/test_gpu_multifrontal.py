@@ -128,6 +128,60 @@ def test_multifrontal_equals_band_kernel(monkeypatch):
     assert np.abs(g1 - g0).max() / np.abs(g0).max() < 1e-10
 
 
+def test_execution_modes_are_bit_identical(monkeypatch):
+    """How an evaluation is issued must not change a single bit of it: one stream / three groups of systems on their own streams,
+    eager launches / the replayed CUDA graph (from the second evaluation of a plan on), pruned / complete forward eliminations.
+    Device-resident leapfrog steps (several evaluations per plan, so the graph is captured and replayed) and the host-buffer
+    entry point."""
+    from hmcmt2d_b200 import api, synthetic
+    mesh, data, inv, prior = synthetic.make_problem(70, 50, 4, nRx=9)
+    m0 = synthetic.stress_model(inv)
+    p0 = np.clip(np.random.default_rng(0).standard_normal(len(m0)), -2.5, 2.5)
+    results = []
+    for groups, graph, prune in [("1", "0", "0"), ("3", "0", "1"), ("1", "1", "1"), ("3", "1", "1"), ("8", "1", "0")]:
+        monkeypatch.setenv("HMCMT_SOLVER", "mf")
+        monkeypatch.setenv("HMCMT_GROUPS", groups)
+        monkeypatch.setenv("HMCMT_GRAPH", graph)
+        monkeypatch.setenv("HMCMT_MF_PRUNE", prune)
+        pl = api.Plan(mesh, data, inv, prior)
+        assert pl.info(11) == 1
+        pl.set_state(m0, p0, m0)
+        pl.leapfrog_steps_device(prior.dt, 4)
+        assert pl.status() == 0
+        m, p = pl.get_state()
+        outs = [pl.forward_gradient(m0) for _ in range(3)]          # eager, captured, replayed
+        for o in outs[1:]:
+            assert all(np.array_equal(a, b) for a, b in zip(o, outs[0]))
+        results.append((m.copy(), p.copy()) + tuple(np.array(a) for a in outs[0]))
+        pl.close()
+    for r in results[1:]:
+        assert all(np.array_equal(a, b) for a, b in zip(r, results[0]))
+
+
+@pytest.mark.parametrize("leaf,cross,push", [(16, 0, 0), (16, 0, 2), (9, 0, 7), (16, 13, 2), (36, 26, 0), (1, 0, 0)])
+def test_ordering_knobs_against_oracle(leaf, cross, push, monkeypatch):
+    """Leaf boxes, cross-shaped separators and the tile alignment of the leaves (excess unknowns handed to the separator above)
+    only change the elimination order: every variant must reproduce the oracle to 1e-9."""
+    from hmcmt2d_b200 import api, synthetic
+    from oracle import sampler as osamp
+    from tests.helpers import to_oracle
+    monkeypatch.setenv("HMCMT_SOLVER", "mf")
+    monkeypatch.setenv("HMCMT_MF_LEAF", str(leaf))
+    monkeypatch.setenv("HMCMT_MF_CROSS", str(cross))
+    monkeypatch.setenv("HMCMT_MF_PUSH", str(push))
+    mesh, data, inv, prior = synthetic.make_problem(64, 45, 2, nRx=8)
+    m = synthetic.stress_model(inv)
+    pl = api.Plan(mesh, data, inv, prior)
+    pred, phi, g = pl.forward_gradient(m)
+    pl.close()
+    om, od, oi, op = to_oracle(mesh, data, inv, prior)
+    oi.strModel = m.copy()
+    opred, ophi, og = osamp.compDataGradient(om, od, oi, op)
+    assert (np.abs(pred[0] - opred) / np.abs(opred)).max() < 1e-9
+    assert abs(phi[0] - ophi) / abs(ophi) < 1e-9
+    assert np.abs(g[0] - og).max() / np.abs(og).max() < 1e-9
+
+
 def test_frequency_sharded_steps_match_unsharded():
     """Two ranks' plans in one process, the all-reduce done by hand on the exchange buffers: the sharded leapfrog steps
     (partial -> sum -> finish) reproduce the unsharded device loop."""

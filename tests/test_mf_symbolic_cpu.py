@@ -21,6 +21,9 @@ def checker(tmp_path_factory):
     ("grid", "40", "25", "32", "80"),           # small fronts only
     ("grid", "64", "50", "16", "0"),            # every front through the large-front path, chunked pivots
     ("grid", "199", "99", "16", "144"),         # cfg2 system: mixed
+    ("grid", "199", "99", "16", "144", "0", "2"),   # the same with tile-aligned leaves (excess unknowns pushed to the separator)
+    ("grid", "64", "45", "9", "144", "0", "7"),     # every leaf excess pushed
+    ("grid", "60", "47", "16", "144", "13", "2"),   # cross-shaped separators at the bottom of the tree (four children per front)
     ("grid", "300", "3", "8", "48"),            # degenerate strip
     ("graph3d", "12", "10", "8", "24", "100"),  # level-set bisection of a 3-D grid (Level-1 shim ordering)
     ("graph3d", "30", "1", "1", "4", "144"),    # a path graph
