@@ -820,36 +820,50 @@ mf_bwd_kernel(Tables tb, SolveArgs sa, const int* __restrict__ list) {
 
 
 // Small fronts (single chunk, fp <= kSolveSmallMax): one WARP per (front, right-hand side), eight fronts per CTA, warp-level
-// synchronisation only.  list[blockIdx.x * 8 + warp] = front id.
+// synchronisation only.  descs[blockIdx.x * 8 + warp] = the front's record: every later load depends on it alone or on one
+// further index load, and the loads of the factor are issued before the gathers they will be combined with have arrived —
+// a leaf front streams 1..3 KB of factor, so what a sweep costs is the chain of dependent round trips, not the bytes.
 constexpr int kSolveSmallMax = 64;
 constexpr int kSolveWarpsPerCta = 8;
 __global__ void __launch_bounds__(kSolveWarpsPerCta * 32)
-mf_fwd_warp_kernel(Tables tb, SolveArgs sa, const int* __restrict__ list, int n) {
+mf_fwd_warp_kernel(Tables tb, SolveArgs sa, const SolveDesc* __restrict__ descs, int n) {
     __shared__ cplx wsh[kSolveWarpsPerCta][kSolveSmallMax];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int fi = blockIdx.x * kSolveWarpsPerCta + warp;
     if (fi >= n) return;
-    const Front& F = tb.fronts[list[fi]];
+    const SolveDesc D = descs[fi];
     const int vec = blockIdx.y, sys = vec / sa.nrhs;
-    const int sp = F.sp, up = F.up, fp = sp + up, fs = F.s, cbp = F.cbp;
+    const int sp = D.sp, up = D.up, fp = sp + up, fs = D.s, fu = D.u, cbp = D.cbp;
     cplx* w = wsh[warp];
     const cplx* b = sa.B + (size_t)vec * sa.ldb;
     cplx* v = sa.v + (size_t)vec * sa.Np;
     cplx* upd = sa.upd + (size_t)vec * sa.updEntries;
-    for (int i = lane; i < fp; i += 32) w[i] = i < fs ? b[tb.pos2orig[cbp + i]] : mk(0.0, 0.0);
+    // (a) requests that need the record only: own right-hand-side rows (through pos2orig), the children's row maps and update vectors
+    int orow[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) orow[h] = (lane + 32 * h < fs) ? tb.pos2orig[cbp + lane + 32 * h] : -1;
+    int crel[kDescChildren];
+    cplx cval[kDescChildren];
+#pragma unroll
+    for (int c = 0; c < kDescChildren; ++c) {
+        crel[c] = -1;
+        if (c < D.nChild && lane < D.cU[c]) { crel[c] = tb.rel[D.cRel[c] + lane]; cval[c] = upd[D.cUpd[c] + lane]; }
+    }
+    for (int i = lane; i < fp; i += 32) w[i] = mk(0.0, 0.0);
     __syncwarp();
-    const int nChild = F.nChild, childPtr = F.childPtr;
-    for (int c = 0; c < nChild; ++c) {
-        const Front& C = tb.fronts[tb.children[childPtr + c]];
-        const int* rel = tb.rel + C.rowPtr;
-        const cplx* uv = upd + C.updOff;
-        const int cu = C.u;
-        for (int i = lane; i < cu; i += 32) w[rel[i]] += uv[i];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) if (orow[h] >= 0) w[lane + 32 * h] = b[orow[h]];
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < kDescChildren; ++c) {
+        if (c >= D.nChild) break;
+        if (crel[c] >= 0) w[crel[c]] += cval[c];
+        for (int i = lane + 32; i < D.cU[c]; i += 32) w[tb.rel[D.cRel[c] + i]] += upd[D.cUpd[c] + i];      // (children wider than a warp)
         __syncwarp();
     }
     if (up > 0) {
-        const double* M = tb.fac + (size_t)sys * tb.facStride + tb.chunks[F.chunkPtr].mOff;
-        const int fu = F.u, ngr = (fs + 3) >> 2;      // real update rows / column groups holding a real pivot (the rest is padding)
+        const double* M = tb.fac + (size_t)sys * tb.facStride + D.mOff;
+        const int ngr = (fs + 3) >> 2;      // column groups holding a real pivot (the rest is padding); real update rows only
         for (int i = lane; i < fu; i += 32) {
             cplx acc = mk(0.0, 0.0);
             for (int kg = 0; kg < ngr; ++kg) {
@@ -863,39 +877,55 @@ mf_fwd_warp_kernel(Tables tb, SolveArgs sa, const int* __restrict__ list, int n)
                 cfma(acc, mk(r23.x, i23.x), wk[2]);
                 cfma(acc, mk(r23.y, i23.y), wk[3]);
             }
-            upd[F.updOff + i] = w[sp + i] - acc;
+            upd[D.updOff + i] = w[sp + i] - acc;
         }
     }
     for (int i = lane; i < sp; i += 32) v[cbp + i] = w[i];
 }
 
 __global__ void __launch_bounds__(kSolveWarpsPerCta * 32)
-mf_bwd_warp_kernel(Tables tb, SolveArgs sa, const int* __restrict__ list, int n) {
+mf_bwd_warp_kernel(Tables tb, SolveArgs sa, const SolveDesc* __restrict__ descs, int n) {
     __shared__ cplx xsh[kSolveWarpsPerCta][kSolveSmallMax];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int fi = blockIdx.x * kSolveWarpsPerCta + warp;
     if (fi >= n) return;
-    const Front& F = tb.fronts[list[fi]];
+    const SolveDesc D = descs[fi];
     const int vec = blockIdx.y, sys = vec / sa.nrhs;
-    const int sp = F.sp, up = F.up, fp = sp + up, fs = F.s, fu = F.u, cbp = F.cbp;
+    const int sp = D.sp, up = D.up, fs = D.s, fu = D.u, cbp = D.cbp;
     cplx* xf = xsh[warp];
     cplx* v = sa.v + (size_t)vec * sa.Np;
     cplx* x = sa.X + (size_t)vec * sa.ldx;
-    const int* rows = tb.rows + F.rowPtr;
-    for (int i = lane; i < fp; i += 32) {
-        cplx val = mk(0.0, 0.0);
-        if (i < sp) val = v[cbp + i];
-        else if (i - sp < fu) val = v[rows[i - sp]];
-        xf[i] = val;
-    }
-    __syncwarp();
-    const Chunk ch = tb.chunks[F.chunkPtr];
-    const double* G = tb.fac + (size_t)sys * tb.facStride + ch.gOff;
-    const double* M = tb.fac + (size_t)sys * tb.facStride + ch.mOff;
+    const int* rows = tb.rows + D.rowPtr;
+    const double* G = tb.fac + (size_t)sys * tb.facStride + D.gOff;
+    const double* M = tb.fac + (size_t)sys * tb.facStride + D.mOff;
+    // (a) needs the record only: the update-row indices, the own pivot part, where the solution goes
+    int urow[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) urow[h] = (lane + 32 * h < fu) ? rows[lane + 32 * h] : -1;
+    if (lane < sp) xf[lane] = v[cbp + lane];
+    if (lane + 32 < sp) xf[lane + 32] = v[cbp + lane + 32];
     // x1[k] = sum_j G[j][k] w1[j] - sum_i M[i][k] x2[i] : one lane per k (four lanes share a 32-byte sector); when the front has
     // fewer than 32 pivots the rows are split over 32 / width sub-groups of lanes and combined with shuffles.  Only the real
-    // pivots / update rows are visited: the identity padding (up to 7 of 16 pivots on a leaf) is never read back by anybody.
+    // pivots / update rows are visited: the identity padding is never read back by anybody.
     const int width = fs <= 8 ? 8 : (fs <= 16 ? 16 : 32), nparts = 32 / width, part = lane / width, kl = lane - part * width;
+    const int orig0 = (kl < fs && part == 0) ? tb.pos2orig[cbp + kl] : -1;      // (fronts of at most 32 pivots: the common case)
+    // (b) the first rows of M for this lane's column are requested before the parents' values they multiply have been gathered
+    constexpr int kPre = 4;
+    double pmr[kPre], pmi[kPre];
+    {
+        const bool on = kl < fs;
+        const double* mr = M + kg_off(up, 0, on ? kl : 0, 0);
+        const double* mi = M + kg_off(up, 0, on ? kl : 0, 1);
+#pragma unroll
+        for (int q = 0; q < kPre; ++q) {
+            const int i = part + q * nparts;
+            pmr[q] = (on && i < fu) ? mr[4 * i] : 0.0;
+            pmi[q] = (on && i < fu) ? mi[4 * i] : 0.0;
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) if (urow[h] >= 0) xf[sp + lane + 32 * h] = v[urow[h]];
+    __syncwarp();
     for (int k0 = 0; k0 < fs; k0 += width) {
         const int k = k0 + kl;
         cplx acc = mk(0.0, 0.0);
@@ -905,7 +935,12 @@ mf_bwd_warp_kernel(Tables tb, SolveArgs sa, const int* __restrict__ list, int n)
             for (int j = part; j < fs; j += nparts) cfma(acc, mk(gr[4 * j], gi[4 * j]), xf[j]);
             const double* mr = M + kg_off(up, 0, k, 0);
             const double* mi = M + kg_off(up, 0, k, 1);
-            for (int i = part; i < fu; i += nparts) cfma(acc, mk(-mr[4 * i], -mi[4 * i]), xf[sp + i]);
+            int i = part;
+            if (k0 == 0) {
+#pragma unroll
+                for (int q = 0; q < kPre; ++q, i += nparts) if (i < fu) cfma(acc, mk(-pmr[q], -pmi[q]), xf[sp + i]);
+            }
+            for (; i < fu; i += nparts) cfma(acc, mk(-mr[4 * i], -mi[4 * i]), xf[sp + i]);
         }
         for (int off = width; off < 32; off <<= 1) {
             acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
@@ -913,7 +948,7 @@ mf_bwd_warp_kernel(Tables tb, SolveArgs sa, const int* __restrict__ list, int n)
         }
         if (k < fs && part == 0) {
             v[cbp + k] = acc;
-            x[tb.pos2orig[cbp + k]] = acc;
+            x[k0 == 0 ? orig0 : tb.pos2orig[cbp + k]] = acc;
         }
     }
 }

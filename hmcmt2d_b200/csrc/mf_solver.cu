@@ -24,6 +24,8 @@ struct PerDeviceOnceMf {
 constexpr size_t kMaxSmem = 227 * 1024;
 constexpr int kSolveWarpMaxFp = 64;  // solves: warp-per-front kernels up to this front size
 constexpr int kTinyWarps = 2;       // warps per CTA for fronts with fp <= 48
+// solves: one warp per front (record-driven kernels) for small fronts with few children, one CTA per front otherwise
+inline bool solve_by_warp(const Front& F) { return !F.isBig && F.fp() <= kSolveWarpMaxFp && F.nChild <= kDescChildren; }
 
 template <int NW>
 int launch_small(cudaStream_t st, const Tables& tb, const SmallDesc* list, int n, int nsys, size_t smem) {
@@ -43,6 +45,27 @@ int Solver::upload(const std::vector<Tp>& h, Tp** d) {
     bytes += n * sizeof(Tp);
     if (!h.empty() && cudaMemcpy(*d, h.data(), h.size() * sizeof(Tp), cudaMemcpyHostToDevice) != cudaSuccess) return kErrCuda;
     return kOk;
+}
+
+int Solver::upload_solve_descs(const std::vector<int>& fr, const SolveDesc** d) {
+    std::vector<SolveDesc> v;
+    v.reserve(fr.size());
+    for (int k : fr) {
+        const Front& F = S.fronts[k];
+        SolveDesc sd{};
+        sd.sp = F.sp; sd.up = F.up; sd.s = F.s; sd.u = F.u; sd.cbp = F.cbp; sd.rowPtr = F.rowPtr; sd.updOff = (int)F.updOff;
+        sd.nChild = F.nChild;
+        sd.gOff = S.chunks[F.chunkPtr].gOff; sd.mOff = S.chunks[F.chunkPtr].mOff;
+        for (int c = 0; c < std::min(F.nChild, kDescChildren); ++c) {
+            const Front& C = S.fronts[S.children[F.childPtr + c]];
+            sd.cRel[c] = C.rowPtr; sd.cUpd[c] = (int)C.updOff; sd.cU[c] = C.u;
+        }
+        v.push_back(sd);
+    }
+    SolveDesc* p = nullptr;
+    int rc = upload(v, &p);
+    *d = p;
+    return rc;
 }
 
 Solver* Solver::create(Symbolic&& S, int nsys, int maxRhs, int64_t valCount, int* rc) {
@@ -141,10 +164,10 @@ int Solver::build(int nsys_, int maxRhs_, int64_t valCount_) {
         D.bigBytes = (size_t)S.bigDoublesAtDepth[d] * sizeof(double);
         // solves: one warp per front up to kSolveWarpMaxFp rows, one CTA per front above
         std::vector<int> sw, sc(bg);
-        for (int k : sm) (S.fronts[k].fp() <= kSolveWarpMaxFp ? sw : sc).push_back(k);
+        for (int k : sm) (solve_by_warp(S.fronts[k]) ? sw : sc).push_back(k);
         D.nSolveWarp = (int)sw.size();
         D.nSolveCta = (int)sc.size();
-        if (D.nSolveWarp) { MF_TRY(upload(sw, &p)); D.solveWarpList = p; }
+        if (D.nSolveWarp) MF_TRY(upload_solve_descs(sw, &D.solveWarpList));
         if (D.nSolveCta) { MF_TRY(upload(sc, &p)); D.solveCtaList = p; }
         if (!D.nBig) continue;
         MF_TRY(upload(bg, &p));
@@ -314,12 +337,12 @@ int Solver::add_rhs_pattern(const std::vector<unsigned char>& nz) {
     for (int d = 0; d <= S.maxDepth; ++d) {
         std::vector<int> sw, sc;
         for (int k : S.byDepthBig[d]) if (active[k]) sc.push_back(k);
-        for (int k : S.byDepthSmall[d]) if (active[k]) (S.fronts[k].fp() <= kSolveWarpMaxFp ? sw : sc).push_back(k);
-        int* p = nullptr;
-        if (!sw.empty()) MF_TRY(upload(sw, &p));
-        L.warpList.push_back(sw.empty() ? nullptr : p);
+        for (int k : S.byDepthSmall[d]) if (active[k]) (solve_by_warp(S.fronts[k]) ? sw : sc).push_back(k);
+        const SolveDesc* pd = nullptr;
+        if (!sw.empty()) MF_TRY(upload_solve_descs(sw, &pd));
+        L.warpList.push_back(pd);
         L.nWarp.push_back((int)sw.size());
-        p = nullptr;
+        int* p = nullptr;
         if (!sc.empty()) MF_TRY(upload(sc, &p));
         L.ctaList.push_back(sc.empty() ? nullptr : p);
         L.nCta.push_back((int)sc.size());
@@ -366,7 +389,7 @@ int Solver::solve(cudaStream_t st, int nrhs, const cplx* B, int64_t ldb, cplx* X
     for (int d = S.maxDepth; d >= 0; --d) {
         const DepthSchedule& D = sched[d];
         const int nW = P ? P->nWarp[d] : D.nSolveWarp, nC = P ? P->nCta[d] : D.nSolveCta;
-        const int* wl = P ? P->warpList[d] : D.solveWarpList;
+        const SolveDesc* wl = P ? P->warpList[d] : D.solveWarpList;
         const int* cl = P ? P->ctaList[d] : D.solveCtaList;
         if (nW) {
             mf_fwd_warp_kernel<<<dim3((nW + kSolveWarpsPerCta - 1) / kSolveWarpsPerCta, nvec), kSolveWarpsPerCta * 32, 0, st>>>(tb, sa, wl, nW);

@@ -29,6 +29,15 @@ struct SmallDesc {
     int cLd[kDescChildren], cFirst[kDescChildren], cU[kDescChildren], cRel[kDescChildren];   // ld, first row / column, real rows, rel offset
 };
 
+// The same for the warp-per-front solve kernels (fronts of at most 64 rows, a single pivot chunk): offsets / counts of the front
+// and of its children's update vectors in one 96-byte record.
+struct SolveDesc {
+    int sp, up, s, u;
+    int cbp, rowPtr, updOff, nChild;
+    int64_t gOff, mOff;                        // factor arena (doubles)
+    int cRel[kDescChildren], cUpd[kDescChildren], cU[kDescChildren];      // children: row map offset, update vector offset, real rows
+};
+
 struct DepthSchedule {
     int nSmall = 0, smallWarps = 4;
     size_t smallSmem = 0;
@@ -51,7 +60,7 @@ struct DepthSchedule {
     };
     std::vector<ChunkStep> chunkSteps;
     size_t bigBytes = 0;                     // leading part of the depth arena holding the large fronts (zeroed before assembly)
-    const int* solveWarpList = nullptr;      // solves: fronts handled one per warp / one per CTA
+    const SolveDesc* solveWarpList = nullptr;      // solves: fronts handled one per warp (records) / one per CTA (front ids)
     const int* solveCtaList = nullptr;
     int nSolveWarp = 0, nSolveCta = 0;
 };
@@ -93,6 +102,7 @@ class Solver {
     int build(int nsys, int maxRhs, int64_t valCount);
     template <typename Tp>
     int upload(const std::vector<Tp>& h, Tp** d);
+    int upload_solve_descs(const std::vector<int>& fronts, const SolveDesc** d);
     Symbolic S;
     int nsys = 0, maxRhs = 1;
     int64_t valCount = 0;
@@ -100,7 +110,8 @@ class Solver {
     std::vector<void*> owned;
     std::vector<DepthSchedule> sched;
     struct FwdLists {                            // forward-elimination launch lists of one right-hand-side pattern, per depth
-        std::vector<const int*> warpList, ctaList;
+        std::vector<const SolveDesc*> warpList;
+        std::vector<const int*> ctaList;
         std::vector<int> nWarp, nCta;
         int nFronts = 0;
     };
