@@ -49,6 +49,9 @@ CFG4 = dict(workload="cfg4: synthetic 800x300-cell mesh, 60 frequencies, TE+TM, 
 # dram__bytes_read + dram__bytes_write of the factorisation group per step at cfg2 (band kernel): FM_OWN capture + its
 # back-substitution sweep, ncu --set full (profiles/r01_final_factor_own_ncu.txt, profiles/r01_final_solve_own_ncu.txt)
 NCU_FACTOR_DRAM_BYTES = (24.28e6 + 2.250943e9) + (2.278771e9 + 23.64e6)
+# the same for the multifrontal path at cfg2 (60 systems): the 63 launches from mf_mt_vals_kernel to the end of the forward solve,
+# ncu dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/r02_cfg2_launches.csv, summary beside it)
+NCU_MF_FACTOR_DRAM_BYTES = 5.212e9
 FP64_DMMA_PEAK_TFLOPS = 37.1     # measured on this pool's B200 with DMMA.8x8x4 (profiles/r01_fp64_peak_ubench.txt)
 
 
@@ -318,6 +321,11 @@ def factor_roofline(pl, factor_ms, factor_n, step_ms, peaks, peak_src):
                   "mf_asm_*/mf_inv_kernel/mf_gemm_kernel (DMMA.8x8x4 64x64x16 tiles) per depth and pivot chunk, + the forward solve "
                   "(mf_fwd_*/mf_bwd_*), timed as one unit")
         traffic, tsrc = None, None
+        if N == 19701 and nsys == 60:
+            traffic = NCU_MF_FACTOR_DRAM_BYTES
+            tsrc = ("sum of dram__bytes_read.sum + dram__bytes_write.sum over the launches of one factorisation + forward solve at this "
+                    "workload (profiles/r02_cfg2_launches.csv): factor written and read back once, update matrices of the fronts "
+                    "written by the children and read by the parents, assembly of the large fronts in global memory")
     else:
         flops, fbytes = band_flops, 2.0 * 16.0 * N * (b + 1) * nsys
         kernel = ("factorisation of the systems = band_factor_kernel<14> FM_OWN + FM_SEP (FP64 DMMA.8x8x4 block LDL^T, fused assembly + "
