@@ -277,20 +277,19 @@ __device__ __forceinline__ void mf_store_tile(const double* __restrict__ T, doub
 // (register budget: the two- and four-warp instantiations serve the thousands of tiny fronts at the bottom of the tree, where the
 // number of fronts resident per SM hides the latency of the 8x8 inversions: 64 registers per thread -> 16 / 8 CTAs per SM)
 template <int NW>
-__global__ void __launch_bounds__(NW * 32, NW <= 4 ? 32 / NW : (NW == 8 ? 2 : 1))
+__global__ void __launch_bounds__(NW * 32, NW <= 4 ? (NW == 1 ? 16 : 32 / NW) : (NW == 8 ? 2 : 1))
 mf_small_kernel(Tables tb, const SmallDesc* __restrict__ descs) {
     constexpr int NT = NW * 32;
     extern __shared__ __align__(16) unsigned char mf_smem[];
     SmallDesc& F = *reinterpret_cast<SmallDesc*>(mf_smem);      // the first kFrontDescBytes of the dynamic block
     const int sys = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-    constexpr int _pc = NW == 2 ? 0 : (NW == 4 ? 1 : (NW == 8 ? 2 : 3));      // profiler class
+    constexpr int _pc = NW <= 2 ? 0 : (NW == 4 ? 1 : (NW == 8 ? 2 : 3));      // profiler class
     long long _t0 = clock64();
     // the front's record: one coalesced read
-    static_assert(sizeof(SmallDesc) % 4 == 0 && sizeof(SmallDesc) / 4 <= 64 && sizeof(SmallDesc) <= kFrontDescBytes,
-                  "SmallDesc is copied by the first two warps into the head of the dynamic shared memory");
-    if (tid < (int)(sizeof(SmallDesc) / 4))
-        reinterpret_cast<int*>(&F)[tid] = reinterpret_cast<const int*>(descs + blockIdx.x)[tid];
+    static_assert(sizeof(SmallDesc) % 4 == 0 && sizeof(SmallDesc) <= kFrontDescBytes, "SmallDesc is copied word by word into the head of the dynamic shared memory");
+    for (int i = tid; i < (int)(sizeof(SmallDesc) / 4); i += NT)
+        reinterpret_cast<int*>(&F)[i] = reinterpret_cast<const int*>(descs + blockIdx.x)[i];
     __syncthreads();
     const int fp = F.sp + F.up, nb = fp >> 3, npb = F.sp >> 3, nub = nb - npb;
     const int nT = nb * (nb + 1) / 2;

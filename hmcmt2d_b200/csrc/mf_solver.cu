@@ -279,7 +279,8 @@ int Solver::factor(cudaStream_t st, int* dStatus, int64_t* nLaunches, int sys0, 
         const int par = d & 1;
         if (D.nSmall) {
             int rc = kOk;
-            if (D.smallWarps == 2) rc = launch_small<2>(st, tb, D.smallDescs, D.nSmall, nsys, D.smallSmem);
+            if (D.smallWarps == 1) rc = launch_small<1>(st, tb, D.smallDescs, D.nSmall, nsys, D.smallSmem);
+            else if (D.smallWarps == 2) rc = launch_small<2>(st, tb, D.smallDescs, D.nSmall, nsys, D.smallSmem);
             else if (D.smallWarps == 4) rc = launch_small<4>(st, tb, D.smallDescs, D.nSmall, nsys, D.smallSmem);
             else if (D.smallWarps == 8) rc = launch_small<8>(st, tb, D.smallDescs, D.nSmall, nsys, D.smallSmem);
             else rc = launch_small<16>(st, tb, D.smallDescs, D.nSmall, nsys, D.smallSmem);
