@@ -23,7 +23,6 @@ struct PerDeviceOnceMf {
 };
 constexpr size_t kMaxSmem = 227 * 1024;
 constexpr int kSolveWarpMaxFp = 64;  // solves: warp-per-front kernels up to this front size
-constexpr int kTinyWarps = 2;       // warps per CTA for fronts with fp <= 48
 // solves: one warp per front (record-driven kernels) for small fronts with few children, one CTA per front otherwise
 inline bool solve_by_warp(const Front& F) { return !F.isBig && F.fp() <= kSolveWarpMaxFp && F.nChild <= kDescChildren; }
 
@@ -155,10 +154,10 @@ int Solver::build(int nsys_, int maxRhs_, int64_t valCount_) {
             SmallDesc* pd = nullptr;
             MF_TRY(upload(descs, &pd));
             D.smallDescs = pd;
-            const char* tw = std::getenv("HMCMT_MF_TINYWARPS");
             auto knob = [](const char* name, int dflt) { const char* e = std::getenv(name); return e ? std::atoi(e) : dflt; };
-            const int f2 = knob("HMCMT_MF_FP2", 48), f4 = knob("HMCMT_MF_FP4", 64), f8 = knob("HMCMT_MF_FP8", 104);      // largest front per CTA size
-            D.smallWarps = mx <= f2 ? (tw ? std::atoi(tw) : kTinyWarps) : (mx <= f4 ? 4 : (mx <= f8 ? 8 : 16));
+            // warps per front by the largest front of the launch (measured optimum at cfg2; one warp per front needs no CTA barrier)
+            const int f1 = knob("HMCMT_MF_FP1", 40), f2 = knob("HMCMT_MF_FP2", 40), f4 = knob("HMCMT_MF_FP4", 64), f8 = knob("HMCMT_MF_FP8", 104);
+            D.smallWarps = mx <= f1 ? 1 : (mx <= f2 ? 2 : (mx <= f4 ? 4 : (mx <= f8 ? 8 : 16)));
         }
         D.nBig = (int)bg.size();
         D.bigBytes = (size_t)S.bigDoublesAtDepth[d] * sizeof(double);
