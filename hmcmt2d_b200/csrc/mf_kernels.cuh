@@ -882,48 +882,54 @@ mf_fwd_warp_kernel(Tables tb, SolveArgs sa, const SolveDesc* __restrict__ descs,
     for (int i = lane; i < sp; i += 32) v[cbp + i] = w[i];
 }
 
+// Backward substitution, one warp per front.  G and M of a single-chunk front are ONE contiguous block of 16 sp (sp + up) bytes in
+// the factor arena ([G | M], k-grouped): blocks of up to kBwdStageBytes are fetched whole with 16-byte cp.async copies into the
+// warp's shared-memory stage as soon as the record has arrived — all of the front's factor bytes are in flight at once, fully
+// coalesced, while the index loads and the gathers of the parents' values take their round trips — and the products then read
+// shared memory.  (The direct version gathered 8 bytes per lane and load: 3.1 TB/s on the leaf level, latency bound.)
+constexpr int kBwdStageBytes = 8192;
 __global__ void __launch_bounds__(kSolveWarpsPerCta * 32)
 mf_bwd_warp_kernel(Tables tb, SolveArgs sa, const SolveDesc* __restrict__ descs, int n) {
+    extern __shared__ __align__(16) unsigned char mf_smem[];
     __shared__ cplx xsh[kSolveWarpsPerCta][kSolveSmallMax];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int fi = blockIdx.x * kSolveWarpsPerCta + warp;
     if (fi >= n) return;
-    const SolveDesc D = descs[fi];
+    const SolveDesc& D = descs[fi];                // (fields are read as needed; the row indices ride in the same record)
     const int vec = blockIdx.y, sys = vec / sa.nrhs;
     const int sp = D.sp, up = D.up, fs = D.s, fu = D.u, cbp = D.cbp;
     cplx* xf = xsh[warp];
     cplx* v = sa.v + (size_t)vec * sa.Np;
     cplx* x = sa.X + (size_t)vec * sa.ldx;
     const int* rows = tb.rows + D.rowPtr;
-    const double* G = tb.fac + (size_t)sys * tb.facStride + D.gOff;
-    const double* M = tb.fac + (size_t)sys * tb.facStride + D.mOff;
-    // (a) needs the record only: the update-row indices, the own pivot part, where the solution goes
+    const double* Gg = tb.fac + (size_t)sys * tb.facStride + D.gOff;
+    const int blockBytes = 16 * sp * (sp + up);
+    const bool staged = blockBytes <= kBwdStageBytes && D.mOff == D.gOff + 2 * (int64_t)sp * sp;
+    const double* G = Gg;
+    if (staged) {
+        double* stage = reinterpret_cast<double*>(mf_smem) + (size_t)warp * (kBwdStageBytes / 8);
+        for (int o = lane * 16; o < blockBytes; o += 32 * 16) cp_async16(reinterpret_cast<unsigned char*>(stage) + o, reinterpret_cast<const unsigned char*>(Gg) + o, 16u);
+        cp_async_commit();
+        G = stage;
+    }
+    const double* M = G + 2 * (size_t)sp * sp + (staged ? 0 : (D.mOff - D.gOff - 2 * (int64_t)sp * sp));
+    // needs the record only: the update-row indices, the own pivot part, where the solution goes
     int urow[2];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) urow[h] = (lane + 32 * h < fu) ? rows[lane + 32 * h] : -1;
+    for (int h = 0; h < 2; ++h) {
+        const int i = lane + 32 * h;
+        urow[h] = i < fu ? (i < kDescRows ? D.rows[i] : rows[i]) : -1;
+    }
     if (lane < sp) xf[lane] = v[cbp + lane];
     if (lane + 32 < sp) xf[lane + 32] = v[cbp + lane + 32];
-    // x1[k] = sum_j G[j][k] w1[j] - sum_i M[i][k] x2[i] : one lane per k (four lanes share a 32-byte sector); when the front has
-    // fewer than 32 pivots the rows are split over 32 / width sub-groups of lanes and combined with shuffles.  Only the real
-    // pivots / update rows are visited: the identity padding is never read back by anybody.
+    // x1[k] = sum_j G[j][k] w1[j] - sum_i M[i][k] x2[i] : one lane per k; when the front has fewer than 32 pivots the rows are
+    // split over 32 / width sub-groups of lanes and combined with shuffles.  Only the real pivots / update rows are visited: the
+    // identity padding is never read back by anybody.
     const int width = fs <= 8 ? 8 : (fs <= 16 ? 16 : 32), nparts = 32 / width, part = lane / width, kl = lane - part * width;
     const int orig0 = (kl < fs && part == 0) ? tb.pos2orig[cbp + kl] : -1;      // (fronts of at most 32 pivots: the common case)
-    // (b) the first rows of M for this lane's column are requested before the parents' values they multiply have been gathered
-    constexpr int kPre = 4;
-    double pmr[kPre], pmi[kPre];
-    {
-        const bool on = kl < fs;
-        const double* mr = M + kg_off(up, 0, on ? kl : 0, 0);
-        const double* mi = M + kg_off(up, 0, on ? kl : 0, 1);
-#pragma unroll
-        for (int q = 0; q < kPre; ++q) {
-            const int i = part + q * nparts;
-            pmr[q] = (on && i < fu) ? mr[4 * i] : 0.0;
-            pmi[q] = (on && i < fu) ? mi[4 * i] : 0.0;
-        }
-    }
 #pragma unroll
     for (int h = 0; h < 2; ++h) if (urow[h] >= 0) xf[sp + lane + 32 * h] = v[urow[h]];
+    if (staged) cp_async_wait<0>();
     __syncwarp();
     for (int k0 = 0; k0 < fs; k0 += width) {
         const int k = k0 + kl;
@@ -934,12 +940,7 @@ mf_bwd_warp_kernel(Tables tb, SolveArgs sa, const SolveDesc* __restrict__ descs,
             for (int j = part; j < fs; j += nparts) cfma(acc, mk(gr[4 * j], gi[4 * j]), xf[j]);
             const double* mr = M + kg_off(up, 0, k, 0);
             const double* mi = M + kg_off(up, 0, k, 1);
-            int i = part;
-            if (k0 == 0) {
-#pragma unroll
-                for (int q = 0; q < kPre; ++q, i += nparts) if (i < fu) cfma(acc, mk(-pmr[q], -pmi[q]), xf[sp + i]);
-            }
-            for (; i < fu; i += nparts) cfma(acc, mk(-mr[4 * i], -mi[4 * i]), xf[sp + i]);
+            for (int i = part; i < fu; i += nparts) cfma(acc, mk(-mr[4 * i], -mi[4 * i]), xf[sp + i]);
         }
         for (int off = width; off < 32; off <<= 1) {
             acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);

@@ -59,6 +59,7 @@ int Solver::upload_solve_descs(const std::vector<int>& fr, const SolveDesc** d) 
             const Front& C = S.fronts[S.children[F.childPtr + c]];
             sd.cRel[c] = C.rowPtr; sd.cUpd[c] = (int)C.updOff; sd.cU[c] = C.u;
         }
+        for (int i = 0; i < std::min(F.u, kDescRows); ++i) sd.rows[i] = S.rows[F.rowPtr + i];
         v.push_back(sd);
     }
     SolveDesc* p = nullptr;
@@ -377,6 +378,7 @@ int Solver::solve(cudaStream_t st, int nrhs, const cplx* B, int64_t ldb, cplx* X
     if (once.need()) {
         HMCMT_CUDA_TRY(cudaFuncSetAttribute(mf_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
         HMCMT_CUDA_TRY(cudaFuncSetAttribute(mf_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+        HMCMT_CUDA_TRY(cudaFuncSetAttribute(mf_bwd_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSolveWarpsPerCta * kBwdStageBytes));
     }
     const int nvec = nsys * nrhs;
     int64_t nl = 0;
@@ -403,7 +405,8 @@ int Solver::solve(cudaStream_t st, int nrhs, const cplx* B, int64_t ldb, cplx* X
     for (int d = 0; d <= S.maxDepth; ++d) {
         const DepthSchedule& D = sched[d];
         if (D.nSolveWarp) {
-            mf_bwd_warp_kernel<<<dim3((D.nSolveWarp + kSolveWarpsPerCta - 1) / kSolveWarpsPerCta, nvec), kSolveWarpsPerCta * 32, 0, st>>>(
+            mf_bwd_warp_kernel<<<dim3((D.nSolveWarp + kSolveWarpsPerCta - 1) / kSolveWarpsPerCta, nvec), kSolveWarpsPerCta * 32,
+                                 (size_t)kSolveWarpsPerCta * kBwdStageBytes, st>>>(
                 tb, sa, D.solveWarpList, D.nSolveWarp);
             ++nl;
         }

@@ -31,11 +31,13 @@ struct SmallDesc {
 
 // The same for the warp-per-front solve kernels (fronts of at most 64 rows, a single pivot chunk): offsets / counts of the front
 // and of its children's update vectors in one 96-byte record.
+constexpr int kDescRows = 40;                      // update-row indices carried inside the record (fronts of up to 48 rows)
 struct SolveDesc {
     int sp, up, s, u;
     int cbp, rowPtr, updOff, nChild;
     int64_t gOff, mOff;                        // factor arena (doubles)
     int cRel[kDescChildren], cUpd[kDescChildren], cU[kDescChildren];      // children: row map offset, update vector offset, real rows
+    int rows[kDescRows];                       // the first min(u, kDescRows) update rows (positions in the permuted numbering)
 };
 
 struct DepthSchedule {
