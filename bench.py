@@ -280,19 +280,21 @@ def host_stepper(evaluate, inv, prior, m0, dt):
 
     def step(m, p):
         dm = dt * p
-        mx = np.abs(dm).max()
+        mx = max(dm.max(), -dm.min())
         if mx > 3.0:
             dm = dm / mx * 3.0
         m = m + dm
         for _ in range(500):                                   # checkParameterBound! (HMCSampler.jl:515-559)
-            low, high = m < lo, m > hi
-            if not (low.any() or high.any()):
+            if m.min() >= lo and m.max() <= hi:
                 break
+            low = m < lo
             m = np.where(low, 2 * lo - m, m); p = np.where(low, -p, p)
             high = m > hi
             m = np.where(high, 2 * hi - m, m); p = np.where(high, -p, p)
         pred, phi, g = evaluate(m)                             # H2D m ; D2H pred, phi, grad  (pinned staging inside)
-        p = p - dt * (g + beta * (Wm @ (m - m0)))
+        g += beta * (Wm @ (m - m0))
+        g *= dt
+        p = p - g
         return m, p, phi
     return step
 

@@ -1343,15 +1343,43 @@ int hmcmt_forward_gradient(hmcmt_plan* pl, const double* m, double* pred, double
     if (!pl || !m) return kErrArg;
     HMCMT_CUDA_TRY(cudaSetDevice(pl->device));
     pl->sigmaDirect = false;
-    int rc = upload_model(pl, m);
+    // One pinned staging buffer for everything that crosses the bus: [model up | pred | phi | gradient | error flags down], one
+    // stream synchronisation per call (device-to-host copies into pageable caller memory would be staged by the driver one by one).
+    const size_t nM = sizeof(double) * (size_t)pl->nChains * pl->nAC, nP = sizeof(cplx) * (size_t)pl->nChains * pl->nData;
+    const size_t nPhi = sizeof(double) * pl->nChains, nS = sizeof(int) * ((size_t)pl->nSys + 1);
+    const size_t oP = (nM + 255) & ~(size_t)255, oPhi = oP + ((nP + 255) & ~(size_t)255), oG = oPhi + ((nPhi + 255) & ~(size_t)255);
+    const size_t oS = oG + ((nM + 255) & ~(size_t)255), total = oS + nS;
+    int rc = ensure_pin(pl, std::max(total, (size_t)1 << 20));
     if (rc) return rc;
+    unsigned char* pin = reinterpret_cast<unsigned char*>(pl->pin);
+    std::memcpy(pin, m, nM);
+    HMCMT_CUDA_TRY(cudaMemcpyAsync(pl->m.p, pin, nM, cudaMemcpyHostToDevice, pl->stream));
     rc = compute_step(pl, true, nullptr);
     if (rc) return rc;
-    if (pred) { rc = download_pred(pl, pred); if (rc) return rc; }
-    if (phid) HMCMT_CUDA_TRY(cudaMemcpyAsync(phid, pl->phi.p, sizeof(double) * pl->nChains, cudaMemcpyDeviceToHost, pl->stream));
-    if (grad) HMCMT_CUDA_TRY(cudaMemcpyAsync(grad, pl->gdata.p, sizeof(double) * (size_t)pl->nChains * pl->nAC, cudaMemcpyDeviceToHost, pl->stream));
+    if (pred) {
+        k_pack_pred<<<dim3((pl->nData + 255) / 256, pl->nChains), 256, 0, pl->stream>>>(pl->nData, pl->nFull, pl->packed2full.p,
+                                                                                        pl->predFull.p, pl->predPacked.p);
+        LAUNCH_CHECK(pl);
+        HMCMT_CUDA_TRY(cudaMemcpyAsync(pin + oP, pl->predPacked.p, nP, cudaMemcpyDeviceToHost, pl->stream));
+    }
+    if (phid) HMCMT_CUDA_TRY(cudaMemcpyAsync(pin + oPhi, pl->phi.p, nPhi, cudaMemcpyDeviceToHost, pl->stream));
+    if (grad) HMCMT_CUDA_TRY(cudaMemcpyAsync(pin + oG, pl->gdata.p, nM, cudaMemcpyDeviceToHost, pl->stream));
+    HMCMT_CUDA_TRY(cudaMemcpyAsync(pin + oS, pl->status.p, sizeof(int) * pl->nSys, cudaMemcpyDeviceToHost, pl->stream));
+    HMCMT_CUDA_TRY(cudaMemcpyAsync(pin + oS + sizeof(int) * pl->nSys, pl->driftFlag.p, sizeof(int), cudaMemcpyDeviceToHost, pl->stream));
     HMCMT_CUDA_TRY(cudaStreamSynchronize(pl->stream));
-    return check_status(pl);
+    if (pred) std::memcpy(pred, pin + oP, nP);
+    if (phid) std::memcpy(phid, pin + oPhi, nPhi);
+    if (grad) std::memcpy(grad, pin + oG, nM);
+    // error flags of this call (same meaning as check_status; cleared when set so that they do not poison later evaluations)
+    const int* st = reinterpret_cast<const int*>(pin + oS);
+    rc = kOk;
+    for (int i = 0; i < pl->nSys; ++i) if (st[i]) { rc = st[i]; break; }
+    if (rc == kOk && st[pl->nSys]) rc = kErrBounds;
+    if (rc != kOk) {
+        HMCMT_CUDA_TRY(cudaMemsetAsync(pl->status.p, 0, sizeof(int) * pl->nSys, pl->stream));
+        HMCMT_CUDA_TRY(cudaMemsetAsync(pl->driftFlag.p, 0, sizeof(int), pl->stream));
+    }
+    return rc;
 }
 
 int hmcmt_set_state(hmcmt_plan* pl, const double* m, const double* p, const double* mref) {
