@@ -372,9 +372,7 @@ mf_small_kernel(Tables tb, const SmallDesc* __restrict__ descs) {
         return tiles + (size_t)((a >> 3) * ((a >> 3) + 1) / 2 + (b >> 3)) * 128 + tl_off(a & 7, b & 7);
     };
     {
-        int passed = 0;                           // child boundaries (CTA barriers) this warp went through: nChild - 1 in the end
         auto scatter = [&](const Batch& bt) {
-            while (passed < bt.c) { __syncthreads(); ++passed; }
             const int2* relC = relS + ((bt.c > 0 ? F.cU[0] : 0) + (bt.c > 1 ? F.cU[1] : 0) + (bt.c > 2 ? F.cU[2] : 0));
 #pragma unroll
             for (int bq = 0; bq < kBatch; ++bq) {
@@ -393,13 +391,18 @@ mf_small_kernel(Tables tb, const SmallDesc* __restrict__ descs) {
                 }
             }
         };
-        while (b0.c >= 0) {
-            scatter(b0);
-            b0 = b1;
-            load_batch(b1);
+        // one child after the other; every warp takes the same nChild trips through the ONE barrier below, whatever its share of
+        // the batches (the batches in flight at a child boundary already belong to the next child)
+        for (int c = 0; c < nChild; ++c) {
+            while (b0.c == c) {
+                scatter(b0);
+                b0 = b1;
+                load_batch(b1);
+            }
+            __syncwarp();
+            __syncthreads();
         }
-        while (passed < nChild - 1) { __syncthreads(); ++passed; }
-        __syncthreads();
+        if (nChild == 0) __syncthreads();
     }
     MF_PROF_MARK(2);
     // original matrix entries of the pivot columns
