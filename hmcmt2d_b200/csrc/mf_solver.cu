@@ -127,6 +127,7 @@ int Solver::build(int nsys_, int maxRhs_, int64_t valCount_) {
     }
 
     // launch schedule
+    std::vector<int> invMapsHost;
     sched.assign(S.maxDepth + 1, DepthSchedule());
     for (int d = 0; d <= S.maxDepth; ++d) {
         DepthSchedule& D = sched[d];
@@ -183,19 +184,27 @@ int Solver::build(int nsys_, int maxRhs_, int64_t valCount_) {
         int2* p2 = nullptr;
         D.nOrigPairs = (int)op.size();
         if (D.nOrigPairs) { MF_TRY(upload(op, &p2)); D.origPairs = p2; }
-        for (int c = 0; c < maxChild; ++c) {
-            std::vector<int2> cp;
+        {
+            std::vector<AsmTile> tiles;
             for (int k : bg) {
                 const Front& F = S.fronts[k];
-                if (F.nChild > c) {
-                    const int ch = S.children[F.childPtr + c];
-                    cp.push_back(make_int2(k, ch));
-                    D.maxChildU = std::max(D.maxChildU, S.fronts[ch].u);
+                const int fp = F.fp(), nt = (fp + 63) / 64;
+                const int invPtr = (int)invMapsHost.size();
+                for (int c = 0; c < F.nChild; ++c) {
+                    const Front& C = S.fronts[S.children[F.childPtr + c]];
+                    std::vector<int> inv(fp, -1);
+                    for (int i = 0; i < C.u; ++i) inv[S.rel[C.rowPtr + i]] = i;
+                    invMapsHost.insert(invMapsHost.end(), inv.begin(), inv.end());
                 }
+                for (int bi = 0; bi < nt; ++bi)
+                    for (int bj = 0; bj <= bi; ++bj) tiles.push_back(AsmTile{k, bi, bj, invPtr});
             }
-            MF_TRY(upload(cp, &p2));
-            D.childPasses.emplace_back(p2, (int)cp.size());
+            AsmTile* pt = nullptr;
+            MF_TRY(upload(tiles, &pt));
+            D.asmTiles = pt;
+            D.nAsmTiles = (int)tiles.size();
         }
+        (void)maxChild;
         for (int c = 0; c < maxChunk; ++c) {
             DepthSchedule::ChunkStep cs;
             std::vector<int> inv;
@@ -243,6 +252,7 @@ int Solver::build(int nsys_, int maxRhs_, int64_t valCount_) {
             D.chunkSteps.push_back(cs);
         }
     }
+    MF_TRY(upload(invMapsHost, &d_invMaps));
     solveSmem = (size_t)(2 * S.maxFp + 16) * sizeof(cplx);
     if (solveSmem > kMaxSmem) return kErrArg;
 #undef MF_TRY
@@ -288,15 +298,12 @@ int Solver::factor(cudaStream_t st, int* dStatus, int64_t* nLaunches, int sys0, 
             ++nl;
         }
         if (!D.nBig) continue;
-        HMCMT_CUDA_TRY(cudaMemset2DAsync(tb.arena[par], (size_t)S.arenaDoubles[par] * sizeof(double), 0, D.bigBytes, nsys, st));
-        if (D.nOrigPairs) {
-            mf_asm_orig_kernel<<<dim3((D.nOrigPairs + 255) / 256, nsys), 256, 0, st>>>(tb, D.origPairs, D.nOrigPairs);
+        if (D.nAsmTiles) {
+            mf_asm_gather_kernel<<<dim3(D.nAsmTiles, nsys), 256, 0, st>>>(tb, (const AsmTile*)D.asmTiles, d_invMaps);
             ++nl;
         }
-        for (const auto& cp : D.childPasses) {
-            if (!cp.second) continue;
-            const int nseg = std::max(1, std::min(32, (D.maxChildU + 3) / 4));
-            mf_asm_child_kernel<<<dim3(cp.second, nsys, nseg), 256, 0, st>>>(tb, cp.first);
+        if (D.nOrigPairs) {
+            mf_asm_orig_kernel<<<dim3((D.nOrigPairs + 255) / 256, nsys), 256, 0, st>>>(tb, D.origPairs, D.nOrigPairs);
             ++nl;
         }
         for (size_t c = 0; c < D.chunkSteps.size(); ++c) {

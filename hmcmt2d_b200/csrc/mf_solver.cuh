@@ -48,8 +48,8 @@ struct DepthSchedule {
     const int* bigList = nullptr;
     int nOrigPairs = 0;
     const int2* origPairs = nullptr;
-    std::vector<std::pair<const int2*, int>> childPasses;      // (pairs, count)
-    int maxChildU = 0;
+    const void* asmTiles = nullptr;          // AsmTile[nAsmTiles]: 64 x 64 lower tiles of the large fronts (gather assembly)
+    int nAsmTiles = 0;
     struct ChunkStep {
         const int* invList = nullptr;
         int nInv = 0;
@@ -61,7 +61,7 @@ struct DepthSchedule {
         int nSchurTiles = 0;
     };
     std::vector<ChunkStep> chunkSteps;
-    size_t bigBytes = 0;                     // leading part of the depth arena holding the large fronts (zeroed before assembly)
+    size_t bigBytes = 0;                     // leading part of the depth arena holding the large fronts
     const SolveDesc* solveWarpList = nullptr;      // solves: fronts handled one per warp (records) / one per CTA (front ids)
     const int* solveCtaList = nullptr;
     int nSolveWarp = 0, nSolveCta = 0;
@@ -126,6 +126,7 @@ class Solver {
     double* d_fac = nullptr;
     double* d_arena[2] = {nullptr, nullptr};
     cplx *d_vals = nullptr, *d_v = nullptr, *d_upd = nullptr;
+    int* d_invMaps = nullptr;                  // inverse row maps (front row -> child row) of the large fronts
     size_t solveSmem = 0;
     unsigned long long* d_prof = nullptr;      // HMCMT_MF_PROF=1: phase cycle counters of mf_small_kernel
 };
