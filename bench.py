@@ -50,9 +50,9 @@ CFG4 = dict(workload="cfg4: synthetic 800x300-cell mesh, 60 frequencies, TE+TM, 
 # dram__bytes_read + dram__bytes_write of the factorisation group per step at cfg2 (band kernel): FM_OWN capture + its
 # back-substitution sweep, ncu --set full (profiles/r01_final_factor_own_ncu.txt, profiles/r01_final_solve_own_ncu.txt)
 NCU_FACTOR_DRAM_BYTES = (24.28e6 + 2.250943e9) + (2.278771e9 + 23.64e6)
-# the same for the multifrontal path at cfg2 (60 systems): the 63 launches from mf_mt_vals_kernel to the end of the forward solve,
+# the same for the multifrontal path at cfg2 (60 systems): the 59 launches from mf_mt_vals_kernel to the end of the forward solve,
 # ncu dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/r02_cfg2_launches.csv, summary beside it)
-NCU_MF_FACTOR_DRAM_BYTES = 5.262e9
+NCU_MF_FACTOR_DRAM_BYTES = 5.120e9
 FP64_DMMA_PEAK_TFLOPS = 37.1     # measured on this pool's B200 with DMMA.8x8x4 (profiles/r01_fp64_peak_ubench.txt)
 
 
