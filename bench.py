@@ -15,8 +15,9 @@ chain per GPU (weak scaling, no data-path collective: "replicas only", as parall
 `value` : steps/s with the chain state resident in HBM (hmcmt_leapfrog_steps_device), CUDA events on the library's stream,
           max over ranks.
 `e2e`   : the same step through the reference-facing call (compDataGradient-equivalent through the C ABI) with HOST buffers:
-          the model goes host->device and predicted data / misfit / gradient come back every step; drift and kick run on the host
-          exactly as the reference's proposeLeapfrog does.
+          the model goes host->device and predicted data / misfit / gradient come back every step; drift, bound reflection and
+          kick run on the host as in the reference's proposeLeapfrog.  The gradient that comes back is data + model-norm part
+          (hmcmt_forward_gradient_total: the library forms beta Wm (m - m_ref) on the device in every evaluation anyway).
 `validated` : the device loop's error flags are clear, its states are finite, one device step and one host step from the same
           (m0, p0) agree to 1e-9, three steps to 1e-7, and the final states of the two timed arms (W+K steps each) are still on the
           same trajectory (the dynamics amplify round-off differences step by step: reported, bounded at 1e-2); on every rank.
@@ -273,8 +274,10 @@ class Dist:
             self.dist.destroy_process_group()
 
 
-def host_stepper(evaluate, inv, prior, m0, dt):
-    """The reference's proposeLeapfrog inner step on the host (HMCSampler.jl:235-265) around a host-buffer gradient call."""
+def host_stepper(evaluate, inv, prior, m0, dt, total_gradient=False):
+    """The reference's proposeLeapfrog inner step on the host (HMCSampler.jl:235-265) around a host-buffer gradient call.
+    total_gradient: `evaluate` already returns data + model-norm gradient (hmcmt_forward_gradient_total: the library forms
+    beta Wm (m - m_ref) on the device in every evaluation anyway), otherwise the host adds the model-norm part as the reference does."""
     lo, hi = np.log(prior.sigBounds[0]), np.log(prior.sigBounds[1])
     Wm, beta = inv.Wm, prior.regParam
 
@@ -292,7 +295,8 @@ def host_stepper(evaluate, inv, prior, m0, dt):
             high = m > hi
             m = np.where(high, 2 * hi - m, m); p = np.where(high, -p, p)
         pred, phi, g = evaluate(m)                             # H2D m ; D2H pred, phi, grad  (pinned staging inside)
-        g += beta * (Wm @ (m - m0))
+        if not total_gradient:
+            g += beta * (Wm @ (m - m0))
         g *= dt
         p = p - g
         return m, p, phi
@@ -367,7 +371,8 @@ def run_cfg2(args, D, local_rank):
     p0 = np.clip(rng.standard_normal(len(m0)), -2.5, 2.5)
     dt = prior.dt
     K, W = args.steps, max(3, args.warmup)
-    step = host_stepper(lambda m: (lambda r: (r[0], float(r[1][0]), r[2][0]))(pl.forward_gradient(m)), inv, prior, m0, dt)
+    step = host_stepper(lambda m: (lambda r: (r[0], float(r[1][0]), r[2][0]))(pl.forward_gradient(m, total=True)), inv, prior, m0, dt,
+                        total_gradient=True)
 
     # ---------------- validation (untimed): device-resident steps vs host-loop steps from the same state ----------------
     # one step: same state in -> same state out at the north_star tolerance (1e-9); three steps: the chain stays together while the

@@ -233,14 +233,17 @@ class Plan:
         _lib.check(self.L.hmcmt_jacobian(self.h, J.ctypes.data_as(C.POINTER(C.c_double))), "hmcmt_jacobian")
         return J
 
-    def forward_gradient(self, m):
+    def forward_gradient(self, m, total=False):
+        """compDataGradient (HMCSampler.jl:277-330): predicted data, data misfit, gradient w.r.t. ln(sigma).  total=True adds the
+        model-norm part beta Wm (m - m_ref) on the device (m_ref from set_state), as proposeLeapfrog does right afterwards."""
         self.generation = getattr(self, "generation", 0) + 1
         mm = self._m(m)
         pred = np.zeros((self.nChains, self.nData), dtype=np.complex128)
         phi = np.zeros(self.nChains)
         g = np.zeros((self.nChains, self.nAC))
-        _lib.check(self.L.hmcmt_forward_gradient(self.h, _lib.f64(mm), pred.ctypes.data_as(C.POINTER(C.c_double)),
-                                                 _lib.f64(phi), _lib.f64(g)), "hmcmt_forward_gradient")
+        fn = self.L.hmcmt_forward_gradient_total if total else self.L.hmcmt_forward_gradient
+        _lib.check(fn(self.h, _lib.f64(mm), pred.ctypes.data_as(C.POINTER(C.c_double)), _lib.f64(phi), _lib.f64(g)),
+                   "hmcmt_forward_gradient")
         return pred, phi, g
 
     def set_state(self, m=None, p=None, mref=None):

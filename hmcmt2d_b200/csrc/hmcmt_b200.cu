@@ -1339,7 +1339,14 @@ int hmcmt_jacobian(hmcmt_plan* pl, double* J) {
     return check_status(pl);
 }
 
+static int forward_gradient_impl(hmcmt_plan* pl, const double* m, double* pred, double* phid, double* grad, bool withPrior);
 int hmcmt_forward_gradient(hmcmt_plan* pl, const double* m, double* pred, double* phid, double* grad) {
+    return forward_gradient_impl(pl, m, pred, phid, grad, false);
+}
+int hmcmt_forward_gradient_total(hmcmt_plan* pl, const double* m, double* pred, double* phid, double* grad) {
+    return forward_gradient_impl(pl, m, pred, phid, grad, true);
+}
+static int forward_gradient_impl(hmcmt_plan* pl, const double* m, double* pred, double* phid, double* grad, bool withPrior) {
     if (!pl || !m) return kErrArg;
     HMCMT_CUDA_TRY(cudaSetDevice(pl->device));
     pl->sigmaDirect = false;
@@ -1363,7 +1370,7 @@ int hmcmt_forward_gradient(hmcmt_plan* pl, const double* m, double* pred, double
         HMCMT_CUDA_TRY(cudaMemcpyAsync(pin + oP, pl->predPacked.p, nP, cudaMemcpyDeviceToHost, pl->stream));
     }
     if (phid) HMCMT_CUDA_TRY(cudaMemcpyAsync(pin + oPhi, pl->phi.p, nPhi, cudaMemcpyDeviceToHost, pl->stream));
-    if (grad) HMCMT_CUDA_TRY(cudaMemcpyAsync(pin + oG, pl->gdata.p, nM, cudaMemcpyDeviceToHost, pl->stream));
+    if (grad) HMCMT_CUDA_TRY(cudaMemcpyAsync(pin + oG, withPrior ? pl->gtotal.p : pl->gdata.p, nM, cudaMemcpyDeviceToHost, pl->stream));
     HMCMT_CUDA_TRY(cudaMemcpyAsync(pin + oS, pl->status.p, sizeof(int) * pl->nSys, cudaMemcpyDeviceToHost, pl->stream));
     HMCMT_CUDA_TRY(cudaMemcpyAsync(pin + oS + sizeof(int) * pl->nSys, pl->driftFlag.p, sizeof(int), cudaMemcpyDeviceToHost, pl->stream));
     HMCMT_CUDA_TRY(cudaStreamSynchronize(pl->stream));

@@ -67,6 +67,7 @@ def load() -> C.CDLL:
     lib.hmcmt_set_response_kind.argtypes = [vp, C.c_int32]
     lib.hmcmt_get_responses.argtypes = [vp, _f64p]
     lib.hmcmt_forward_gradient.argtypes = [vp, _f64p, _f64p, _f64p, _f64p]
+    lib.hmcmt_forward_gradient_total.argtypes = [vp, _f64p, _f64p, _f64p, _f64p]
     lib.hmcmt_set_state.argtypes = [vp, _f64p, _f64p, _f64p]
     lib.hmcmt_get_state.argtypes = [vp, _f64p, _f64p]
     lib.hmcmt_leapfrog_trajectory.argtypes = [vp, C.c_double, _i32p, _f64p, _f64p]
@@ -108,7 +109,7 @@ EXPORTED_SYMBOLS = [
     "factor_mumps_cmplx_", "factor_mumps_", "solve_mumps_cmplx_", "solve_mumps_", "solve_mumps_sparse_rhs_",
     "solve_mumps_cmplx_sparse_rhs_", "destroy_mumps_", "destroy_mumps_cmplx_",
     "hmcmt_plan_create", "hmcmt_destroy", "hmcmt_plan_info", "hmcmt_forward", "hmcmt_forward_sigma", "hmcmt_jtvec",
-    "hmcmt_forward_gradient", "hmcmt_jacobian", "hmcmt_status", "hmcmt_set_mass_matrix", "hmcmt_set_response_kind", "hmcmt_get_responses",
+    "hmcmt_forward_gradient", "hmcmt_forward_gradient_total", "hmcmt_jacobian", "hmcmt_status", "hmcmt_set_mass_matrix", "hmcmt_set_response_kind", "hmcmt_get_responses",
     "hmcmt_set_state", "hmcmt_get_state", "hmcmt_leapfrog_trajectory", "hmcmt_leapfrog_steps_device", "hmcmt_sync",
     "hmcmt_step_partial", "hmcmt_exchange_buffer", "hmcmt_step_finish", "hmcmt_nccl_unique_id", "hmcmt_nccl_init",
     "hmcmt_leapfrog_steps_sharded",

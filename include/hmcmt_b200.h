@@ -137,6 +137,10 @@ int hmcmt_jacobian(hmcmt_plan* plan, double* J);
  * m -> pred [nChains][nData] complex, phi_d [nChains], grad [nChains][nAC] (w.r.t. log conductivity,
  * data part only, as the reference returns it). Host buffers; H2D/D2H inside. */
 int hmcmt_forward_gradient(hmcmt_plan* plan, const double* m, double* pred, double* phid, double* grad);
+/* The same evaluation, but grad = data part + model-norm part beta Wm (m - m_ref): the quantity proposeLeapfrog forms on the host
+ * right after compDataGradient (HMCSampler.jl:240-262, getModelNormGradient).  m_ref is the reference model of the device-resident
+ * chain state (hmcmt_set_state); the library computes that sum on the device in every evaluation anyway. */
+int hmcmt_forward_gradient_total(hmcmt_plan* plan, const double* m, double* pred, double* phid, double* grad);
 
 /* Device-resident chain state (hmcParamCurrent: rhomodel, momentum; invParam.refModel). */
 int hmcmt_set_state(hmcmt_plan* plan, const double* m, const double* p, const double* mref);

@@ -316,3 +316,22 @@ def test_explicit_jacobian_matches_reference_derivation():
     # the responses of the plan are intact after the adjoint passes
     pred2, _ = api.MT2DFwdSolver(pm, pd)
     assert np.array_equal(pred2, pred)
+
+
+def test_total_gradient_entry_point():
+    """hmcmt_forward_gradient_total = data gradient + beta Wm (m - m_ref) (the sum proposeLeapfrog forms, HMCSampler.jl:240-262)."""
+    from hmcmt2d_b200 import api
+    from tests.helpers import tiny_problem, to_product
+    mesh, data, inv, prior = tiny_problem(seed=5)
+    pm, pd, pi, pp = to_product(mesh, data, inv, prior)
+    pl = api.Plan(pm, pd, pi, pp)
+    rng = np.random.default_rng(1)
+    mref = pi.strModel.copy()
+    m = mref + 0.3 * rng.standard_normal(len(mref))
+    pl.set_state(m, np.zeros_like(m), mref)
+    pred, phi, g = pl.forward_gradient(m)
+    pred2, phi2, gt = pl.forward_gradient(m, total=True)
+    assert np.array_equal(pred, pred2) and np.array_equal(phi, phi2)
+    want = g[0] + pp.regParam * (pi.Wm @ (m - mref))
+    assert np.abs(gt[0] - want).max() <= 1e-12 * np.abs(want).max()
+    pl.close()
