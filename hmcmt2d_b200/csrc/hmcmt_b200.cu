@@ -807,9 +807,10 @@ int hmcmt_plan_create(const hmcmt_problem* pr, hmcmt_plan** out) {
     {
         // "mf" / "band" force a solver (band only where the register window fits); default: see below
         const char* env = std::getenv("HMCMT_SOLVER");
-        // measured on B200 (tools/dev/t_mf.py crossover): the multifrontal solver wins from ~2 000 unknowns per system upwards
-        // (96x56 cells: 1.16 vs 1.60 ms per evaluation; 200x100: 6.1 vs 6.7 ms; 400x100: 5.1 vs 12.8 ms), the band kernel below
-        const bool wantMf = env ? !std::strcmp(env, "mf") : (M.N >= 2000);
+        // measured on B200 (tools/dev/t_groups.py ... HMCMT_SOLVER band mf, ms per leapfrog step): the multifrontal solver wins
+        // from ~1 000 unknowns per system upwards (20x16 cells: 0.25 vs 0.23; 30x24: 0.31 vs 0.32; 40x30: 0.37 vs 0.44; 48x40: 0.49 vs
+        // 0.61; 96x56: 0.76 vs 1.52; 200x100: 4.04 vs 6.67), the band kernel below
+        const bool wantMf = env ? !std::strcmp(env, "mf") : (M.N >= 1000);
         pl->useMf = pl->T == 0 || wantMf;
         if (pl->useMf) pl->T = 0;
     }
