@@ -54,6 +54,8 @@ NCU_FACTOR_DRAM_BYTES = (24.28e6 + 2.250943e9) + (2.278771e9 + 23.64e6)
 # the same for the multifrontal path at cfg2 (60 systems): the 59 launches from mf_mt_vals_kernel to the end of the forward solve,
 # ncu dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/r02_cfg2_launches.csv, summary beside it)
 NCU_MF_FACTOR_DRAM_BYTES = 5.120e9
+NCU_MF_FACTOR_ONLY_DRAM_BYTES = 3.697e9         # the 33 launches of the factorisation alone
+NCU_MF_FWD_SOLVE_DRAM_BYTES = 1.425e9           # the 26 launches of the forward solve
 FP64_DMMA_PEAK_TFLOPS = 37.1     # measured on this pool's B200 with DMMA.8x8x4 (profiles/r01_fp64_peak_ubench.txt)
 
 
@@ -312,6 +314,7 @@ def factor_pass(pl, run_steps, K):
     pl.timer_start()
     run_steps(K)
     serial_ms = pl.timer_stop()
+    pl._factor_split = pl.kernel_time_split()      # (factorisation alone, forward solve alone), same events
     factor_ms, factor_n = pl.kernel_time(reset=-1)
     return factor_ms, factor_n, serial_ms
 
@@ -341,7 +344,22 @@ def factor_roofline(pl, factor_ms, factor_n, step_ms, peaks, peak_src):
         tsrc = ("dram__bytes_read.sum + dram__bytes_write.sum of ncu --set full captures at this workload: FM_OWN launch "
                 "(profiles/r01_final_factor_own_ncu.txt) + one factor-streaming sweep (profiles/r01_final_solve_own_ncu.txt)")
     achieved = flops / (fac_ms * 1e-3) / 1e12
-    return dict(bound="tensor", kernel=kernel, achieved=achieved, peak=FP64_DMMA_PEAK_TFLOPS, unit="TFLOP/s",
+    parts = None
+    split = getattr(pl, "_factor_split", None)
+    if mf and split and split[0] > 0 and split[1] > 0:
+        # the two halves of the unit, from the same events: the factorisation alone against the tensor roof, the forward solve
+        # (sparse forward elimination + complete backward substitution) against the HBM roof
+        f_ms, s_ms = split[0] / max(1, factor_n), split[1] / max(1, factor_n)
+        cfg2 = N == 19701 and nsys == 60
+        sbytes = float(pl.info(9)) * nsys                             # >= : the backward substitution streams the whole factor once
+        parts = dict(
+            factorisation=dict(bound="tensor", achieved=flops / (f_ms * 1e-3) / 1e12, peak=FP64_DMMA_PEAK_TFLOPS, unit="TFLOP/s",
+                               frac=flops / (f_ms * 1e-3) / 1e12 / FP64_DMMA_PEAK_TFLOPS, avg_launch_ms=f_ms,
+                               traffic=NCU_MF_FACTOR_ONLY_DRAM_BYTES if cfg2 else None),
+            forward_solve=dict(bound="hbm", achieved=sbytes / (s_ms * 1e-3) / 1e9, peak=peaks.get("hbm_gbs"), unit="GB/s",
+                               frac=sbytes / (s_ms * 1e-3) / 1e9 / peaks.get("hbm_gbs", 6650.0), avg_launch_ms=s_ms,
+                               algorithmic_bytes_per_launch=sbytes, traffic=NCU_MF_FWD_SOLVE_DRAM_BYTES if cfg2 else None))
+    return dict(bound="tensor", kernel=kernel, parts=parts, achieved=achieved, peak=FP64_DMMA_PEAK_TFLOPS, unit="TFLOP/s",
                 frac=achieved / FP64_DMMA_PEAK_TFLOPS,
                 peak_source="measured FP64 DMMA m8n8k4 rate on this pool's B200 (profiles/r01_fp64_peak_ubench.txt); "
                             "MEASURED_PEAKS.json holds only bf16/HBM peaks: " + peak_src,

@@ -284,6 +284,12 @@ class Plan:
         _lib.check(self.L.hmcmt_kernel_time(self.h, int(reset), C.byref(ms), C.byref(n)), "hmcmt_kernel_time")
         return float(ms.value), int(n.value)
 
+    def kernel_time_split(self):
+        """(factorisation alone, forward solve alone) of the evaluations timed since the last reset, ms."""
+        a, b = C.c_float(0), C.c_float(0)
+        _lib.check(self.L.hmcmt_kernel_time_split(self.h, C.byref(a), C.byref(b)), "hmcmt_kernel_time_split")
+        return float(a.value), float(b.value)
+
     def status(self) -> int:
         """Device error flags of everything queued so far (synchronises, clears): 0, -10 singular pivot, -21 bounds."""
         return int(self.L.hmcmt_status(self.h))

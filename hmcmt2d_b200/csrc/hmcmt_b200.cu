@@ -63,6 +63,7 @@ struct hmcmt_plan {
     std::vector<cudaStream_t> groupStreams;             // >= 2: the systems of a step run as groups on these streams (compute_step_grouped)
     std::vector<cudaEvent_t> groupDone;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> factorEvents;
+    std::vector<cudaEvent_t> factorMid;                 // between the factorisation and the forward solve of a timed evaluation
     size_t factorEventsUsed = 0;
     int64_t launches = 0, factorLaunches = 0;
     bool haveForward = false, haveSens = false, sigmaDirect = false, useMf = false, timeFactor = false;
@@ -480,12 +481,16 @@ int forward_phase(hmcmt_plan* pl, bool wantAdjoint) {
             HMCMT_CUDA_TRY(cudaEventCreate(&a));
             HMCMT_CUDA_TRY(cudaEventCreate(&b));
             pl->factorEvents.emplace_back(a, b);
+            cudaEvent_t c;
+            HMCMT_CUDA_TRY(cudaEventCreate(&c));
+            pl->factorMid.push_back(c);
         }
         ev = &pl->factorEvents[pl->factorEventsUsed++];
         HMCMT_CUDA_TRY(cudaEventRecord(ev->first, st));
     }
     const SysRange all{0, pl->nSys, st};
     rc = forward_factor(pl, all);
+    if (rc == kOk && ev) HMCMT_CUDA_TRY(cudaEventRecord(pl->factorMid[pl->factorEventsUsed - 1], st));
     if (rc == kOk) rc = forward_solve(pl, all);
     if (rc) return rc;
     ++pl->factorLaunches;
@@ -1065,6 +1070,7 @@ void hmcmt_destroy(hmcmt_plan* pl) {
     if (pl->evA) cudaEventDestroy(pl->evA);
     if (pl->evB) cudaEventDestroy(pl->evB);
     for (auto& e : pl->factorEvents) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    for (cudaEvent_t e : pl->factorMid) cudaEventDestroy(e);
     pl->yLen.release(); pl->zLen.release(); pl->zNode.release(); pl->freqs.release(); pl->fdy1.release(); pl->fdy2.release();
     pl->wL.release(); pl->wR.release(); pl->bg.release(); pl->wmVal.release(); pl->wd.release(); pl->m.release(); pl->p.release();
     pl->mref.release(); pl->sigma.release(); pl->meanSig.release(); pl->planes.release(); pl->Gpart.release(); pl->phiPart.release();
@@ -1209,6 +1215,21 @@ int hmcmt_timer_stop(hmcmt_plan* pl, float* ms) {
     HMCMT_CUDA_TRY(cudaEventRecord(pl->evB, pl->stream));
     HMCMT_CUDA_TRY(cudaEventSynchronize(pl->evB));
     HMCMT_CUDA_TRY(cudaEventElapsedTime(ms, pl->evA, pl->evB));
+    return kOk;
+}
+int hmcmt_kernel_time_split(hmcmt_plan* pl, float* factor_only_ms, float* forward_solve_ms) {
+    if (!pl) return kErrArg;
+    HMCMT_CUDA_TRY(cudaStreamSynchronize(pl->stream));
+    float a = 0.f, b = 0.f;
+    for (size_t i = 0; i < pl->factorEventsUsed; ++i) {
+        float ms = 0.f;
+        HMCMT_CUDA_TRY(cudaEventElapsedTime(&ms, pl->factorEvents[i].first, pl->factorMid[i]));
+        a += ms;
+        HMCMT_CUDA_TRY(cudaEventElapsedTime(&ms, pl->factorMid[i], pl->factorEvents[i].second));
+        b += ms;
+    }
+    if (factor_only_ms) *factor_only_ms = a;
+    if (forward_solve_ms) *forward_solve_ms = b;
     return kOk;
 }
 int hmcmt_kernel_time(hmcmt_plan* pl, int reset, float* factor_ms, int64_t* factor_launches) {

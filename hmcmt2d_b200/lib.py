@@ -82,6 +82,7 @@ def load() -> C.CDLL:
     lib.hmcmt_timer_start.argtypes = [vp]
     lib.hmcmt_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
     lib.hmcmt_kernel_time.argtypes = [vp, C.c_int, C.POINTER(C.c_float), _i64p]
+    lib.hmcmt_kernel_time_split.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.hmcmt_run_chain.argtypes = [vp, C.c_double, C.c_int32, C.c_double, _f64p, _f64p, _i32p, _f64p, _f64p, C.c_int32,
                                     _f64p, _f64p, _i32p, _f64p]
     lib.hmcmt_export_system.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, _i64p, _i64p, _f64p, _f64p, _f64p]
@@ -113,7 +114,7 @@ EXPORTED_SYMBOLS = [
     "hmcmt_set_state", "hmcmt_get_state", "hmcmt_leapfrog_trajectory", "hmcmt_leapfrog_steps_device", "hmcmt_sync",
     "hmcmt_step_partial", "hmcmt_exchange_buffer", "hmcmt_step_finish", "hmcmt_nccl_unique_id", "hmcmt_nccl_init",
     "hmcmt_leapfrog_steps_sharded",
-    "hmcmt_timer_start", "hmcmt_timer_stop", "hmcmt_kernel_time", "hmcmt_run_chain", "hmcmt_export_system", "hmcmt_version",
+    "hmcmt_timer_start", "hmcmt_timer_stop", "hmcmt_kernel_time", "hmcmt_kernel_time_split", "hmcmt_run_chain", "hmcmt_export_system", "hmcmt_version",
 ]
 
 

@@ -207,6 +207,9 @@ int hmcmt_timer_stop(hmcmt_plan* plan, float* ms);
  * the factorisation alone; reset = -1: clear and switch it off again (the default: groups of systems on their own streams
  * overlap each other, HMCMT_GROUPS); reset = 0: read only. */
 int hmcmt_kernel_time(hmcmt_plan* plan, int reset, float* factor_ms, int64_t* factor_launches);
+/* the same accumulated time split at the end of the factorisation: factorisation alone / forward solve alone (on the band path both
+ * are one fused group of launches: everything is reported in the first part).  Read before a reset. */
+int hmcmt_kernel_time_split(hmcmt_plan* plan, float* factor_only_ms, float* forward_solve_ms);
 
 /* runHMCSampler(mtMesh,mtData,invParam,hmcprior)  HMCSampler.jl:72-196 for all chains of the plan with injected
  * random draws in the reference's draw order:
