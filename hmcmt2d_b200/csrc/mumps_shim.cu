@@ -39,16 +39,30 @@ struct Factor {
     double* panels = nullptr;
     cplx* ainvz = nullptr;
     mf::Solver* mfs = nullptr;          // multifrontal factor (general ordering); else the band factor above
+    const void* pattern = nullptr;      // identity of the cached symbolic analysis the solver was built from
+    int64_t epoch = 0;                  // generation of the symbolic cache it belongs to
 };
 std::mutex g_mu;
 std::unordered_map<int64_t, Factor*> g_factors;
 int64_t g_next = 1;
 
+// Solvers (device tables, launch schedule, factor / update arenas) of destroyed factors are kept per pattern and handed to the next
+// factorisation of the same pattern: the unmodified reference factorises one matrix per frequency and mode with an identical
+// pattern, destroys the handles after the gradient and starts over in the next step (MT2DFwdSolver.jl:119-120, HMCSampler.jl:316-321)
+std::unordered_map<const void*, std::vector<mf::Solver*>> g_pool;
+constexpr size_t kPoolMax = 256;
+int64_t g_epoch = 0;                    // bumped whenever the symbolic cache is dropped (pattern pointers may be reused afterwards)
+
 void free_factor(Factor* f) {
     if (!f) return;
     if (f->panels) cudaFree(f->panels);
     if (f->ainvz) cudaFree(f->ainvz);
-    delete f->mfs;
+    if (f->mfs) {
+        std::lock_guard<std::mutex> lk(g_mu);
+        std::vector<mf::Solver*>& v = g_pool[f->pattern];
+        if (f->pattern && f->epoch == g_epoch && v.size() < kPoolMax) v.push_back(f->mfs);
+        else delete f->mfs;
+    }
     delete f;
 }
 
@@ -99,6 +113,10 @@ const mf::Symbolic* symbolic_for(int64_t n, const int64_t* rowval, const int64_t
     if (!mf::mf_symbolic((int)n, sn, ent, mf_small_front(), *S)) { delete S; return nullptr; }
     std::lock_guard<std::mutex> lk(g_mu);
     if (g_symbolic.size() >= 8) {                         // a handful of patterns at most (TE / TM, real / complex tests)
+        for (auto& kv : g_pool)
+            for (mf::Solver* sv : kv.second) delete sv;
+        g_pool.clear();
+        ++g_epoch;
         for (auto& kv : g_symbolic) delete kv.second;
         g_symbolic.clear();
     }
@@ -112,8 +130,18 @@ int64_t factor_mf(int64_t n, const double* nzval, const int64_t* rowval, const i
     if (!S0) return fail(kErrArg);
     const int64_t nnz = colptr[n] - 1;
     int rc = kOk;
-    mf::Symbolic copy = *S0;
-    mf::Solver* sv = mf::Solver::create(std::move(copy), 1, kShimMaxRhs, nnz, &rc);
+    mf::Solver* sv = nullptr;
+    int64_t epoch = 0;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        epoch = g_epoch;
+        auto it = g_pool.find(S0);
+        if (it != g_pool.end() && !it->second.empty()) { sv = it->second.back(); it->second.pop_back(); }
+    }
+    if (!sv) {
+        mf::Symbolic copy = *S0;
+        sv = mf::Solver::create(std::move(copy), 1, kShimMaxRhs, nnz, &rc);
+    }
     if (!sv) return fail(rc);
     std::vector<cplx> hv((size_t)nnz);
     for (int64_t k = 0; k < nnz; ++k) hv[k] = isReal ? mk(nzval[k], 0.0) : mk(nzval[2 * k], nzval[2 * k + 1]);
@@ -128,7 +156,7 @@ int64_t factor_mf(int64_t n, const double* nzval, const int64_t* rowval, const i
     cudaFree(dstatus);
     if (rc != kOk || hst != 0) { delete sv; return fail(rc != kOk ? rc : hst); }
     Factor* f = new Factor();
-    f->n = (int)n; f->isReal = isReal; f->mfs = sv;
+    f->n = (int)n; f->isReal = isReal; f->mfs = sv; f->pattern = S0; f->epoch = epoch;
     std::lock_guard<std::mutex> lk(g_mu);
     int64_t h = g_next++;
     g_factors[h] = f;
