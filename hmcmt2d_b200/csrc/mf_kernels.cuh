@@ -1,17 +1,18 @@
 // Numeric phase of the nested-dissection multifrontal solver: batched dense partial factorisations of the fronts on the
 // FP64 tensor cores (DMMA.8x8x4) and the level-by-level triangular solves.  Replaces `factorMUMPS(Aii,1)` / `applyMUMPS`
-// (mt2DTE.jl:50-53, compJacTMatVec.jl:220-224, MUMPSfuncs.jl:24-39,75-132) for systems whose half-bandwidth exceeds the
-// register-window kernel (band_factor.cuh) and for arbitrary symmetric matrices handed to the Level-1 shim.
+// (mt2DTE.jl:50-53, compJacTMatVec.jl:220-224, MUMPSfuncs.jl:24-39,75-132) for the MT systems of 1 000 unknowns and more (below
+// that the register-window band kernel, band_factor.cuh, is faster) and for arbitrary symmetric matrices handed to the Level-1 shim.
 //
 // Front arithmetic (pivot-free, complex symmetric, no conjugation; prototype tools/proto/mf_proto.py), front = [pivots | update]:
 //     G = F11^{-1},   M = F21 G,   U = F22 - M F21^T          (the block "sweep" of the pivots; 8x8 pivot blocks inverted in
 //                                                               registers by gj_invert8)
 //     forward  w2 -= M w1 ;   backward  x1 = G w1 - M^T x2       — no triangular solves: every step is a dense product.
-//   * small fronts (fp <= fSmall): ONE CTA assembles the front in shared memory (original entries + extend-add of the
-//     children's update matrices), sweeps it tile by tile and writes G, M (factor arena) and U (update arena);
-//   * large fronts live in global memory: assembly kernels, then per chunk of <= 96 pivots: mf_inv_kernel (G of the diagonal
-//     block, shared memory), mf_gemm_kernel (M = F21 G), mf_gemm_kernel (trailing update U -= M F21^T) — cp.async-staged
-//     64x64x16 tiles, 8 warps, DMMA.
+//   * small fronts (fp <= fSmall): ONE CTA (1 ... 16 warps) assembles the front in shared memory (original entries + extend-add
+//     of the children's update matrices), sweeps the pivot block, forms M and U as two tile products and writes G, M (factor
+//     arena) and U (update arena);
+//   * large fronts live in global memory: gather assembly (mf_asm_gather_kernel, mf_asm_orig_kernel), then per chunk of <= 96
+//     pivots: mf_inv_kernel (G of the diagonal block, shared memory), mf_gemm_kernel (M = F21 G), mf_gemm_kernel (trailing update
+//     U -= M F21^T) — cp.async-staged 64x64x16 tiles, 8 warps, DMMA.
 //
 // Matrix storage ("k-grouped"): element (i,j) of a matrix with ld rows sits at ((j/4*2 + plane)*ld + i)*4 + j%4 doubles
 // (plane 0 = real, 1 = imaginary).  A block of rows of four consecutive columns is contiguous — exactly the DMMA A/B operand

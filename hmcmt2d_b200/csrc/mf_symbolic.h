@@ -408,7 +408,7 @@ inline bool mf_symbolic(int N, const std::vector<std::vector<int>>& snodes, cons
         for (int k = 0; k < K; ++k)
             for (int i = S.fronts[k].s; i < S.fronts[k].sp; ++i) S.orig[at[k]++] = OrigEntry{i, i, -1};
     }
-    // numeric layout: per depth the large fronts first (that part of the arena is zeroed before assembly), then the update
+    // numeric layout: per depth the large fronts first (that part of the arena is written completely by the gather assembly), then the update
     // matrices of the small fronts
     S.byDepthSmall.assign(S.maxDepth + 1, {});
     S.byDepthBig.assign(S.maxDepth + 1, {});
