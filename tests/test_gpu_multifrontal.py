@@ -158,6 +158,25 @@ def test_execution_modes_are_bit_identical(monkeypatch):
         assert all(np.array_equal(a, b) for a, b in zip(r, results[0]))
 
 
+def test_error_flags_through_graph_replay(monkeypatch):
+    """A non-finite model makes some pivot block singular: the call that caused it returns -10 (eager launch or graph replay), the
+    flags are cleared, and the next valid evaluation of the same plan is correct again."""
+    from hmcmt2d_b200 import api, lib, synthetic
+    monkeypatch.setenv("HMCMT_SOLVER", "mf")
+    mesh, data, inv, prior = synthetic.make_problem(64, 45, 2, nRx=8)
+    m = synthetic.stress_model(inv)
+    pl = api.Plan(mesh, data, inv, prior)
+    good = [pl.forward_gradient(m) for _ in range(3)]          # eager, capture, replay
+    bad = m.copy()
+    bad[: len(bad) // 2] = np.nan
+    with pytest.raises(lib.HmcmtError) as e:
+        pl.forward_gradient(bad)
+    assert e.value.code == -10
+    again = pl.forward_gradient(m)
+    assert all(np.array_equal(a, b) for a, b in zip(again, good[0]))
+    pl.close()
+
+
 @pytest.mark.parametrize("leaf,cross,push", [(16, 0, 0), (16, 0, 2), (9, 0, 7), (16, 13, 2), (36, 26, 0), (1, 0, 0)])
 def test_ordering_knobs_against_oracle(leaf, cross, push, monkeypatch):
     """Leaf boxes, cross-shaped separators and the tile alignment of the leaves (excess unknowns handed to the separator above)
