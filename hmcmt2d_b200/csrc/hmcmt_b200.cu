@@ -506,6 +506,7 @@ int forward_phase(hmcmt_plan* pl, bool wantAdjoint) {
 int rx_range(hmcmt_plan* pl, const SysRange& r, bool wantAdjoint, const cplx* vin) {
     const MeshDev& M = pl->M;
     size_t rxSmem = (size_t)(6 * (M.ny + 1) + 3 * M.ny) * sizeof(cplx);
+    if (wantAdjoint) HMCMT_CUDA_TRY(cudaMemsetAsync(pl->lam.p + (size_t)r.s0 * M.N, 0, sizeof(cplx) * (size_t)r.n * M.N, r.st));
     k_rx_adjoint<<<r.n, kRxThreads, rxSmem, r.st>>>(M, pl->rx, pl->sm, pl->freqs.p, pl->sigma.p, pl->F.p, pl->obs.p, pl->wd.p, vin,
                                                     pl->predFull.p, pl->phiPart.p, pl->srows.p, pl->qrow.p, pl->lam.p, wantAdjoint ? 1 : 0,
                                                     pl->respKind, pl->respFull.p, r.s0);

@@ -158,7 +158,7 @@ int Solver::build(int nsys_, int maxRhs_, int64_t valCount_) {
             D.smallDescs = pd;
             auto knob = [](const char* name, int dflt) { const char* e = std::getenv(name); return e ? std::atoi(e) : dflt; };
             // warps per front by the largest front of the launch (measured optimum at cfg2; one warp per front needs no CTA barrier)
-            const int f1 = knob("HMCMT_MF_FP1", 40), f2 = knob("HMCMT_MF_FP2", 40), f4 = knob("HMCMT_MF_FP4", 64), f8 = knob("HMCMT_MF_FP8", 104);
+            const int f1 = knob("HMCMT_MF_FP1", 40), f2 = knob("HMCMT_MF_FP2", 40), f4 = knob("HMCMT_MF_FP4", 64), f8 = knob("HMCMT_MF_FP8", 96);
             D.smallWarps = mx <= f1 ? 1 : (mx <= f2 ? 2 : (mx <= f4 ? 4 : (mx <= f8 ? 8 : 16)));
         }
         D.nBig = (int)bg.size();

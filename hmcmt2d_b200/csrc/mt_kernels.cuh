@@ -471,10 +471,9 @@ k_rx_adjoint(MeshDev M, RxDev rx, SysMap sm, const double* __restrict__ freqs, c
     for (int n = tid; n <= ny; n += kRxThreads) { so[n] = aF0[n]; so[ny + 1 + n] = aF1[n]; }
     cplx* qo = qrow + (size_t)sys * ny;
     for (int j = tid; j < ny; j += kRxThreads) qo[j] = qv[j];
-    // adjoint right-hand side s[ii] in internal ordering (dense, zero elsewhere)
+    // adjoint right-hand side s[ii] in internal ordering (dense, zero elsewhere: the caller has cleared the vector — a memset
+    // of the whole range instead of N stores by this one CTA)
     cplx* ar = adjrhs + (size_t)sys * M.N;
-    for (int q = tid; q < M.N; q += kRxThreads) ar[q] = mk(0.0, 0.0);
-    __syncthreads();
     for (int n = tid; n < 2 * (ny + 1); n += kRxThreads) {
         int row = n / (ny + 1), jn = n - row * (ny + 1), kn = M.zid + row;
         if (jn >= 1 && jn <= ny - 1 && kn >= 1 && kn <= M.nz - 1) ar[q_of(M, jn, kn)] = row ? aF1[jn] : aF0[jn];
