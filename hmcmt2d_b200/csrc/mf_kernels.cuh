@@ -715,19 +715,19 @@ struct SolveArgs {
     int64_t Np, updEntries;
     int nrhs;
 };
-constexpr int kSolveMfThreads = 256;
+constexpr int kSolveMfThreads = 256;      // upper bound; launched with 128 threads where no front of the depth exceeds 144 rows
 
 __global__ void __launch_bounds__(kSolveMfThreads)
 mf_fwd_kernel(Tables tb, SolveArgs sa, const int* __restrict__ list) {
     extern __shared__ __align__(16) unsigned char mf_smem[];
     cplx* w = reinterpret_cast<cplx*>(mf_smem);
     const Front F = tb.fronts[list[blockIdx.x]];
-    const int vec = blockIdx.y, sys = vec / sa.nrhs, tid = threadIdx.x;
+    const int vec = blockIdx.y, sys = vec / sa.nrhs, tid = threadIdx.x, nthr = blockDim.x;
     const int fp = F.sp + F.up;
     const cplx* b = sa.B + (size_t)vec * sa.ldb;
     cplx* v = sa.v + (size_t)vec * sa.Np;
     cplx* upd = sa.upd + (size_t)vec * sa.updEntries;
-    for (int i = tid; i < fp; i += kSolveMfThreads) {
+    for (int i = tid; i < fp; i += nthr) {
         cplx x = mk(0.0, 0.0);
         if (i < F.s) x = b[tb.pos2orig[F.cbp + i]];
         w[i] = x;
@@ -738,7 +738,7 @@ mf_fwd_kernel(Tables tb, SolveArgs sa, const int* __restrict__ list) {
         const int* rel = tb.rel + C.rowPtr;
         const cplx* uv = upd + C.updOff;
         const int cu = C.u;
-        for (int i = tid; i < cu; i += kSolveMfThreads) w[rel[i]] += uv[i];
+        for (int i = tid; i < cu; i += nthr) w[rel[i]] += uv[i];
         __syncthreads();
     }
     const double* fac = tb.fac + (size_t)sys * tb.facStride;
@@ -746,7 +746,7 @@ mf_fwd_kernel(Tables tb, SolveArgs sa, const int* __restrict__ list) {
         const Chunk ch = tb.chunks[F.chunkPtr + c];
         const int sc = ch.p1 - ch.p0, mr = fp - ch.p1;
         const double* M = fac + ch.mOff;
-        for (int i = tid; i < mr; i += kSolveMfThreads) {
+        for (int i = tid; i < mr; i += nthr) {
             cplx acc = mk(0.0, 0.0);
             for (int kg = 0; kg < (sc >> 2); ++kg) {
                 const double* pr = M + kg_off(mr, i, 4 * kg, 0);
@@ -763,22 +763,22 @@ mf_fwd_kernel(Tables tb, SolveArgs sa, const int* __restrict__ list) {
         }
         __syncthreads();
     }
-    for (int i = tid; i < F.sp; i += kSolveMfThreads) v[F.cbp + i] = w[i];
-    for (int i = tid; i < F.up; i += kSolveMfThreads) upd[F.updOff + i] = w[F.sp + i];
+    for (int i = tid; i < F.sp; i += nthr) v[F.cbp + i] = w[i];
+    for (int i = tid; i < F.up; i += nthr) upd[F.updOff + i] = w[F.sp + i];
 }
 
 __global__ void __launch_bounds__(kSolveMfThreads)
 mf_bwd_kernel(Tables tb, SolveArgs sa, const int* __restrict__ list) {
     extern __shared__ __align__(16) unsigned char mf_smem[];
     const Front F = tb.fronts[list[blockIdx.x]];
-    const int vec = blockIdx.y, sys = vec / sa.nrhs, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int vec = blockIdx.y, sys = vec / sa.nrhs, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
     const int fp = F.sp + F.up;
     cplx* xf = reinterpret_cast<cplx*>(mf_smem);        // [fp]
     cplx* tmp = xf + fp;                                 // [kChunkMax or sp]
     cplx* v = sa.v + (size_t)vec * sa.Np;
     cplx* x = sa.X + (size_t)vec * sa.ldx;
     const int* rows = tb.rows + F.rowPtr;
-    for (int i = tid; i < fp; i += kSolveMfThreads) {
+    for (int i = tid; i < fp; i += nthr) {
         cplx val = mk(0.0, 0.0);
         if (i < F.sp) val = v[F.cbp + i];
         else if (i - F.sp < F.u) val = v[rows[i - F.sp]];
@@ -786,7 +786,7 @@ mf_bwd_kernel(Tables tb, SolveArgs sa, const int* __restrict__ list) {
     }
     __syncthreads();
     const double* fac = tb.fac + (size_t)sys * tb.facStride;
-    constexpr int NWS = kSolveMfThreads / 32;
+    const int NWS = nthr / 32;
     for (int c = F.nChunk - 1; c >= 0; --c) {
         const Chunk ch = tb.chunks[F.chunkPtr + c];
         const int sc = ch.p1 - ch.p0, mr = fp - ch.p1;
@@ -823,10 +823,10 @@ mf_bwd_kernel(Tables tb, SolveArgs sa, const int* __restrict__ list) {
             if (lane == 0) { tmp[4 * kg] = a0; tmp[4 * kg + 1] = a1; tmp[4 * kg + 2] = a2; tmp[4 * kg + 3] = a3; }
         }
         __syncthreads();
-        for (int k = tid; k < sc; k += kSolveMfThreads) xf[ch.p0 + k] = tmp[k];
+        for (int k = tid; k < sc; k += nthr) xf[ch.p0 + k] = tmp[k];
         __syncthreads();
     }
-    for (int i = tid; i < F.sp; i += kSolveMfThreads) {
+    for (int i = tid; i < F.sp; i += nthr) {
         v[F.cbp + i] = xf[i];
         if (i < F.s) x[tb.pos2orig[F.cbp + i]] = xf[i];
     }

@@ -170,6 +170,13 @@ int Solver::build(int nsys_, int maxRhs_, int64_t valCount_) {
         D.nSolveCta = (int)sc.size();
         if (D.nSolveWarp) MF_TRY(upload_solve_descs(sw, &D.solveWarpList));
         if (D.nSolveCta) { MF_TRY(upload(sc, &p)); D.solveCtaList = p; }
+        {
+            int mxc = 0;
+            for (int k : sc) mxc = std::max(mxc, S.fronts[k].fp());
+            const char* e = std::getenv("HMCMT_MF_SOLVE_THREADS");      // 0: by front size
+            const int forced = e ? std::atoi(e) : 0;
+            D.solveCtaThreads = forced ? forced : (mxc <= 144 ? 128 : kSolveMfThreads);
+        }
         if (!D.nBig) continue;
         MF_TRY(upload(bg, &p));
         D.bigList = p;
@@ -405,7 +412,7 @@ int Solver::solve(cudaStream_t st, int nrhs, const cplx* B, int64_t ldb, cplx* X
             ++nl;
         }
         if (nC) {
-            mf_fwd_kernel<<<dim3(nC, nvec), kSolveMfThreads, solveSmem, st>>>(tb, sa, cl);
+            mf_fwd_kernel<<<dim3(nC, nvec), D.solveCtaThreads, solveSmem, st>>>(tb, sa, cl);
             ++nl;
         }
     }
@@ -418,7 +425,7 @@ int Solver::solve(cudaStream_t st, int nrhs, const cplx* B, int64_t ldb, cplx* X
             ++nl;
         }
         if (D.nSolveCta) {
-            mf_bwd_kernel<<<dim3(D.nSolveCta, nvec), kSolveMfThreads, solveSmem, st>>>(tb, sa, D.solveCtaList);
+            mf_bwd_kernel<<<dim3(D.nSolveCta, nvec), D.solveCtaThreads, solveSmem, st>>>(tb, sa, D.solveCtaList);
             ++nl;
         }
     }

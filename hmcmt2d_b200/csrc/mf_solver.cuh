@@ -65,6 +65,7 @@ struct DepthSchedule {
     const SolveDesc* solveWarpList = nullptr;      // solves: fronts handled one per warp (records) / one per CTA (front ids)
     const int* solveCtaList = nullptr;
     int nSolveWarp = 0, nSolveCta = 0;
+    int solveCtaThreads = 256;               // threads per CTA of the CTA-per-front solve kernels at this depth
 };
 
 class Solver {
