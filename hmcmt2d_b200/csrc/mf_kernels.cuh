@@ -512,7 +512,7 @@ mf_asm_gather_kernel(Tables tb, const AsmTile* __restrict__ tilesList, const int
 }
 
 // G of the diagonal block of chunk `c` of every listed large front: grid (nfronts, nsys), kInvWarps warps
-constexpr int kInvWarps = 16;
+constexpr int kInvWarps = 8;
 __global__ void __launch_bounds__(kInvWarps * 32)
 mf_inv_kernel(Tables tb, const int* __restrict__ list, int c) {
     constexpr int NT = kInvWarps * 32;
