@@ -897,15 +897,10 @@ mf_fwd_warp_kernel(Tables tb, SolveArgs sa, const SolveDesc* __restrict__ descs,
     for (int i = lane; i < sp; i += 32) v[cbp + i] = w[i];
 }
 
-// Backward substitution, one warp per front.  G and M of a single-chunk front are ONE contiguous block of 16 sp (sp + up) bytes in
-// the factor arena ([G | M], k-grouped): blocks of up to kBwdStageBytes are fetched whole with 16-byte cp.async copies into the
-// warp's shared-memory stage as soon as the record has arrived — all of the front's factor bytes are in flight at once, fully
-// coalesced, while the index loads and the gathers of the parents' values take their round trips — and the products then read
-// shared memory.  (The direct version gathered 8 bytes per lane and load: 3.1 TB/s on the leaf level, latency bound.)
-constexpr int kBwdStageBytes = 8192;
+// Backward substitution, one warp per front.  (Fetching the front's contiguous [G | M] block whole into a shared-memory stage
+// with cp.async was measured: no faster than the direct loads below at any stage size, and slower once the stage costs occupancy.)
 __global__ void __launch_bounds__(kSolveWarpsPerCta * 32)
 mf_bwd_warp_kernel(Tables tb, SolveArgs sa, const SolveDesc* __restrict__ descs, int n) {
-    extern __shared__ __align__(16) unsigned char mf_smem[];
     __shared__ cplx xsh[kSolveWarpsPerCta][kSolveSmallMax];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int fi = blockIdx.x * kSolveWarpsPerCta + warp;
@@ -917,17 +912,8 @@ mf_bwd_warp_kernel(Tables tb, SolveArgs sa, const SolveDesc* __restrict__ descs,
     cplx* v = sa.v + (size_t)vec * sa.Np;
     cplx* x = sa.X + (size_t)vec * sa.ldx;
     const int* rows = tb.rows + D.rowPtr;
-    const double* Gg = tb.fac + (size_t)sys * tb.facStride + D.gOff;
-    const int blockBytes = 16 * sp * (sp + up);
-    const bool staged = blockBytes <= kBwdStageBytes && D.mOff == D.gOff + 2 * (int64_t)sp * sp;
-    const double* G = Gg;
-    if (staged) {
-        double* stage = reinterpret_cast<double*>(mf_smem) + (size_t)warp * (kBwdStageBytes / 8);
-        for (int o = lane * 16; o < blockBytes; o += 32 * 16) cp_async16(reinterpret_cast<unsigned char*>(stage) + o, reinterpret_cast<const unsigned char*>(Gg) + o, 16u);
-        cp_async_commit();
-        G = stage;
-    }
-    const double* M = G + 2 * (size_t)sp * sp + (staged ? 0 : (D.mOff - D.gOff - 2 * (int64_t)sp * sp));
+    const double* G = tb.fac + (size_t)sys * tb.facStride + D.gOff;
+    const double* M = tb.fac + (size_t)sys * tb.facStride + D.mOff;
     // needs the record only: the update-row indices, the own pivot part, where the solution goes
     int urow[2];
 #pragma unroll
@@ -944,7 +930,6 @@ mf_bwd_warp_kernel(Tables tb, SolveArgs sa, const SolveDesc* __restrict__ descs,
     const int orig0 = (kl < fs && part == 0) ? tb.pos2orig[cbp + kl] : -1;      // (fronts of at most 32 pivots: the common case)
 #pragma unroll
     for (int h = 0; h < 2; ++h) if (urow[h] >= 0) xf[sp + lane + 32 * h] = v[urow[h]];
-    if (staged) cp_async_wait<0>();
     __syncwarp();
     for (int k0 = 0; k0 < fs; k0 += width) {
         const int k = k0 + kl;

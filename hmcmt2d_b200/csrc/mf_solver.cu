@@ -392,7 +392,6 @@ int Solver::solve(cudaStream_t st, int nrhs, const cplx* B, int64_t ldb, cplx* X
     if (once.need()) {
         HMCMT_CUDA_TRY(cudaFuncSetAttribute(mf_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
         HMCMT_CUDA_TRY(cudaFuncSetAttribute(mf_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-        HMCMT_CUDA_TRY(cudaFuncSetAttribute(mf_bwd_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSolveWarpsPerCta * kBwdStageBytes));
     }
     const int nvec = nsys * nrhs;
     int64_t nl = 0;
@@ -419,8 +418,7 @@ int Solver::solve(cudaStream_t st, int nrhs, const cplx* B, int64_t ldb, cplx* X
     for (int d = 0; d <= S.maxDepth; ++d) {
         const DepthSchedule& D = sched[d];
         if (D.nSolveWarp) {
-            mf_bwd_warp_kernel<<<dim3((D.nSolveWarp + kSolveWarpsPerCta - 1) / kSolveWarpsPerCta, nvec), kSolveWarpsPerCta * 32,
-                                 (size_t)kSolveWarpsPerCta * kBwdStageBytes, st>>>(
+            mf_bwd_warp_kernel<<<dim3((D.nSolveWarp + kSolveWarpsPerCta - 1) / kSolveWarpsPerCta, nvec), kSolveWarpsPerCta * 32, 0, st>>>(
                 tb, sa, D.solveWarpList, D.nSolveWarp);
             ++nl;
         }
