@@ -53,9 +53,9 @@ CFG4 = dict(workload="cfg4: synthetic 800x300-cell mesh, 60 frequencies, TE+TM, 
 NCU_FACTOR_DRAM_BYTES = (24.28e6 + 2.250943e9) + (2.278771e9 + 23.64e6)
 # the same for the multifrontal path at cfg2 (60 systems): the 59 launches from mf_mt_vals_kernel to the end of the forward solve,
 # ncu dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/r02_cfg2_launches.csv, summary beside it)
-NCU_MF_FACTOR_DRAM_BYTES = 5.120e9
-NCU_MF_FACTOR_ONLY_DRAM_BYTES = 3.697e9         # the 33 launches of the factorisation alone
-NCU_MF_FWD_SOLVE_DRAM_BYTES = 1.425e9           # the 26 launches of the forward solve
+NCU_MF_FACTOR_DRAM_BYTES = 5.044e9
+NCU_MF_FACTOR_ONLY_DRAM_BYTES = 3.700e9         # the 33 launches of the factorisation alone
+NCU_MF_FWD_SOLVE_DRAM_BYTES = 1.344e9           # the 26 launches of the forward solve
 FP64_DMMA_PEAK_TFLOPS = 37.1     # measured on this pool's B200 with DMMA.8x8x4 (profiles/r01_fp64_peak_ubench.txt)
 
 
