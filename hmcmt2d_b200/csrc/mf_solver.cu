@@ -181,11 +181,10 @@ int Solver::build(int nsys_, int maxRhs_, int64_t valCount_) {
         MF_TRY(upload(bg, &p));
         D.bigList = p;
         std::vector<int2> op;
-        int maxChild = 0, maxChunk = 0;
+        int maxChunk = 0;
         for (int k : bg) {
             const Front& F = S.fronts[k];
             for (int e = 0; e < F.nOrig; ++e) op.push_back(make_int2(k, F.origPtr + e));
-            maxChild = std::max(maxChild, F.nChild);
             maxChunk = std::max(maxChunk, F.nChunk);
         }
         int2* p2 = nullptr;
@@ -211,7 +210,6 @@ int Solver::build(int nsys_, int maxRhs_, int64_t valCount_) {
             D.asmTiles = pt;
             D.nAsmTiles = (int)tiles.size();
         }
-        (void)maxChild;
         for (int c = 0; c < maxChunk; ++c) {
             DepthSchedule::ChunkStep cs;
             std::vector<int> inv;
@@ -293,7 +291,6 @@ int Solver::factor(cudaStream_t st, int* dStatus, int64_t* nLaunches, int sys0, 
     int64_t nl = 0;
     for (int d = S.maxDepth; d >= 0; --d) {
         const DepthSchedule& D = sched[d];
-        const int par = d & 1;
         if (D.nSmall) {
             int rc = kOk;
             if (D.smallWarps == 1) rc = launch_small<1>(st, tb, D.smallDescs, D.nSmall, nsys, D.smallSmem);
